@@ -1,0 +1,157 @@
+// WGAN-GP scalar pieces (train.py:142-150), Adam (train.py:256-257) and the
+// generator EMA (accumulate(), train.py:17-22).  All fp32, all HBM-bound:
+// float4 accesses, warp-shuffle reductions, grids in multiples of the SM count.
+#include "common.cuh"
+
+namespace pg {
+
+// x_hat[n,:] = eps[n]*real[n,:] + (1-eps[n])*fake[n,:]
+__global__ void __launch_bounds__(256)
+interp_xhat_kernel(const float *__restrict__ real, const float *__restrict__ fake,
+                   const float *__restrict__ eps, float *__restrict__ out, int N, long long D) {
+  const long long D4 = D >> 2;
+  const long long total = (long long)N * D4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / D4, j = i - n * D4;
+    const float e = eps[n];
+    const float4 r = reinterpret_cast<const float4 *>(real + n * D)[j];
+    const float4 f = reinterpret_cast<const float4 *>(fake + n * D)[j];
+    float4 o;
+    // same association as the reference expression eps*x + (1-eps)*G(z)
+    const float e1 = 1.f - e;
+    o.x = e * r.x + e1 * f.x;
+    o.y = e * r.y + e1 * f.y;
+    o.z = e * r.z + e1 * f.z;
+    o.w = e * r.w + e1 * f.w;
+    reinterpret_cast<float4 *>(out + n * D)[j] = o;
+  }
+}
+
+// one CTA per sample: norms[n] = ||g[n,:]||_2
+__global__ void __launch_bounds__(1024)
+gp_norm_kernel(const float *__restrict__ g, float *__restrict__ norms, long long D) {
+  __shared__ float red[32];
+  const float *p = g + (long long)blockIdx.x * D;
+  const long long D4 = D >> 2;
+  float s = 0.f;
+  for (long long j = threadIdx.x; j < D4; j += blockDim.x) {
+    const float4 v = reinterpret_cast<const float4 *>(p)[j];
+    s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) norms[blockIdx.x] = sqrtf(s);
+}
+
+__global__ void gp_loss_kernel(const float *__restrict__ norms, float *__restrict__ gp, int N,
+                               float lambda) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    const float d = norms[n] - 1.f;
+    s += d * d;
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) *gp = lambda * s / (float)N;
+}
+
+__global__ void __launch_bounds__(256)
+gp_bwd_kernel(const float *__restrict__ g, const float *__restrict__ norms,
+              const float *__restrict__ upstream, float *__restrict__ v, int N, long long D,
+              float lambda) {
+  const long long D4 = D >> 2;
+  const long long total = (long long)N * D4;
+  const float up = upstream ? *upstream : 1.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / D4, j = i - n * D4;
+    const float nm = norms[n];
+    const float k = up * 2.f * lambda / (float)N * (nm - 1.f) / nm;
+    float4 x = reinterpret_cast<const float4 *>(g + n * D)[j];
+    x.x *= k; x.y *= k; x.z *= k; x.w *= k;
+    reinterpret_cast<float4 *>(v + n * D)[j] = x;
+  }
+}
+
+// Adam, torch.optim.Adam semantics (no weight decay, no amsgrad):
+//   m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g^2
+//   p -= lr / (1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+__global__ void __launch_bounds__(256)
+adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
+            float *__restrict__ v, long long n, float lr, float b1, float b2, float eps,
+            const float *__restrict__ step_dev, float grad_scale) {
+  const float t = *step_dev;
+  const float bc1 = 1.f - powf(b1, t);
+  const float bc2_sqrt = sqrtf(1.f - powf(b2, t));
+  const float step_size = lr / bc1;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * grad_scale;
+    float mi = gi;
+    if (m) {
+      mi = b1 * m[i] + (1.f - b1) * gi;
+      m[i] = mi;
+    }
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = p[i] - step_size * (mi / denom);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+ema_kernel(float *__restrict__ ema, const float *__restrict__ p, long long n, float decay) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    ema[i] = ema[i] * decay + (1.f - decay) * p[i];
+}
+
+}  // namespace pg
+
+using namespace pg;
+
+extern "C" int pg_interp_xhat(const float *real, const float *fake, const float *eps, float *out,
+                              int N, long long D, void *stream) {
+  PG_CHECK_ARG(real && fake && eps && out, "pg_interp_xhat: null pointer");
+  PG_CHECK_ARG(N > 0 && D > 0 && D % 4 == 0, "pg_interp_xhat: need D %% 4 == 0");
+  const int grid = bw_grid((long long)N * (D / 4), 256);
+  interp_xhat_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(real, fake, eps, out, N, D);
+  PG_CHECK_LAUNCH("pg_interp_xhat");
+}
+
+extern "C" int pg_gp_fwd(const float *g, float *norms, float *gp, int N, long long D,
+                         float lambda, void *stream) {
+  PG_CHECK_ARG(g && norms && gp, "pg_gp_fwd: null pointer");
+  PG_CHECK_ARG(N > 0 && D > 0 && D % 4 == 0, "pg_gp_fwd: need D %% 4 == 0");
+  int threads = 1024;
+  while (threads > 32 && (long long)threads * 4 > D) threads >>= 1;
+  gp_norm_kernel<<<N, threads, 0, (cudaStream_t)stream>>>(g, norms, D);
+  gp_loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(norms, gp, N, lambda);
+  PG_CHECK_LAUNCH("pg_gp_fwd");
+}
+
+extern "C" int pg_gp_bwd(const float *g, const float *norms, const float *upstream, float *v,
+                         int N, long long D, float lambda, void *stream) {
+  PG_CHECK_ARG(g && norms && v, "pg_gp_bwd: null pointer");
+  PG_CHECK_ARG(N > 0 && D > 0 && D % 4 == 0, "pg_gp_bwd: need D %% 4 == 0");
+  const int grid = bw_grid((long long)N * (D / 4), 256);
+  gp_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g, norms, upstream, v, N, D, lambda);
+  PG_CHECK_LAUNCH("pg_gp_bwd");
+}
+
+extern "C" int pg_adam_step(float *p, const float *g, float *m, float *v, long long n, float lr,
+                            float beta1, float beta2, float eps, const float *step_dev,
+                            float grad_scale, void *stream) {
+  PG_CHECK_ARG(p && g && v && step_dev, "pg_adam_step: null pointer");
+  PG_CHECK_ARG(m || beta1 == 0.f, "pg_adam_step: beta1 != 0 needs a first-moment buffer");
+  PG_CHECK_ARG(n > 0, "pg_adam_step: n must be > 0");
+  adam_kernel<<<bw_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2,
+                                                                 eps, step_dev, grad_scale);
+  PG_CHECK_LAUNCH("pg_adam_step");
+}
+
+extern "C" int pg_ema(float *ema, const float *p, long long n, float decay, void *stream) {
+  PG_CHECK_ARG(ema && p && n > 0, "pg_ema: bad args");
+  ema_kernel<<<bw_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(ema, p, n, decay);
+  PG_CHECK_LAUNCH("pg_ema");
+}

@@ -1,0 +1,235 @@
+// 1x1 heads with a 3- (or 1-, 4-) channel image side: from_rgb, to_rgb, final linear.
+// Reference: EqualConv2d(3, C, 1) / EqualConv2d(C, 3, 1) / EqualLinear(C, 1) at
+// progan_modules.py:195-200, 270-276, 280 (aten::convolution / addmm with K or N = 3,
+// i.e. HBM-bound, never a tensor-core op — SURVEY.md §8 a10,a11,a13).
+//
+// img side: NCHW fp32 [N,K,HW] (exactly what the train scripts pass / receive);
+// act side: NHWC [N*HW, C].  Logical weight w(c,k) = w[c*w_sc + k*w_sk].
+#include "common.cuh"
+
+namespace pg {
+
+constexpr int kMaxK = 4;
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+pw_expand_kernel(const float *__restrict__ img, const float *__restrict__ w,
+                 const float *__restrict__ bias, T *__restrict__ act, int N, long long HW,
+                 int K, int C, int w_sc, int w_sk, float scale) {
+  extern __shared__ float sw[];  // [K][C] then bias[C]
+  float *sb = sw + K * C;
+  for (int i = threadIdx.x; i < K * C; i += blockDim.x) {
+    const int k = i / C, c = i - k * C;
+    sw[i] = w[(long long)c * w_sc + (long long)k * w_sk] * scale;
+  }
+  for (int c = threadIdx.x; c < C; c += blockDim.x) sb[c] = bias ? bias[c] : 0.f;
+  __syncthreads();
+  const int nch = C >> 3;
+  const long long total = (long long)N * HW * nch;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cj = (int)(i % nch);
+    const long long pix = i / nch;
+    const long long n = pix / HW, hw = pix - n * HW;
+    float xin[kMaxK];
+#pragma unroll
+    for (int k = 0; k < kMaxK; ++k)
+      xin[k] = (k < K) ? img[(n * K + k) * HW + hw] : 0.f;
+    F8 o;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = cj * 8 + e;
+      float v = sb[c];
+#pragma unroll
+      for (int k = 0; k < kMaxK; ++k)
+        if (k < K) v = fmaf(xin[k], sw[k * C + c], v);
+      o.v[e] = v;
+    }
+    st8(act + pix * C + (long long)cj * 8, o);
+  }
+}
+
+template <typename T, int TPP>
+__global__ void __launch_bounds__(256)
+pw_reduce_kernel(const T *__restrict__ act, const float *__restrict__ w,
+                 const float *__restrict__ bias, float *__restrict__ img, int N, long long HW,
+                 int K, int C, int w_sc, int w_sk, float scale) {
+  extern __shared__ float sw[];  // [K][C]
+  for (int i = threadIdx.x; i < K * C; i += blockDim.x) {
+    const int k = i / C, c = i - k * C;
+    sw[i] = w[(long long)c * w_sc + (long long)k * w_sk] * scale;
+  }
+  __syncthreads();
+  const int sub = threadIdx.x % TPP;
+  const long long ppb = blockDim.x / TPP;
+  const int nch = C >> 3;
+  const long long P = (long long)N * HW;
+  const long long Pr = ((P + ppb - 1) / ppb) * ppb;
+  for (long long pix = blockIdx.x * ppb + threadIdx.x / TPP; pix < Pr;
+       pix += (long long)gridDim.x * ppb) {
+    float acc[kMaxK] = {0.f, 0.f, 0.f, 0.f};
+    if (pix < P) {
+      for (int ch = sub; ch < nch; ch += TPP) {
+        F8 v = ld8(act + pix * C + (long long)ch * 8);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int c = ch * 8 + e;
+#pragma unroll
+          for (int k = 0; k < kMaxK; ++k)
+            if (k < K) acc[k] = fmaf(v.v[e], sw[k * C + c], acc[k]);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kMaxK; ++k) {
+#pragma unroll
+      for (int o = TPP / 2; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+    }
+    if (pix < P && sub == 0) {
+      const long long n = pix / HW, hw = pix - n * HW;
+#pragma unroll
+      for (int k = 0; k < kMaxK; ++k)
+        if (k < K) img[(n * K + k) * HW + hw] = acc[k] + (bias ? bias[k] : 0.f);
+    }
+  }
+}
+
+// dw(c,k) += scale * sum_pix act[pix,c] * img[k,pix]
+template <typename T>
+__global__ void __launch_bounds__(256)
+pw_wgrad_kernel(const T *__restrict__ act, const float *__restrict__ img,
+                float *__restrict__ dw, int N, long long HW, int K, int C, int w_sc, int w_sk,
+                float scale) {
+  extern __shared__ float sm[];  // [rows][K][C]
+  const int nch = C >> 3;
+  const int rows = blockDim.x / nch;
+  const int cj = threadIdx.x % nch, rj = threadIdx.x / nch;
+  const long long P = (long long)N * HW;
+  float acc[kMaxK][8];
+#pragma unroll
+  for (int k = 0; k < kMaxK; ++k)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[k][e] = 0.f;
+  if (rj < rows) {
+    for (long long pix = (long long)blockIdx.x * rows + rj; pix < P;
+         pix += (long long)gridDim.x * rows) {
+      const long long n = pix / HW, hw = pix - n * HW;
+      F8 v = ld8(act + pix * C + (long long)cj * 8);
+#pragma unroll
+      for (int k = 0; k < kMaxK; ++k) {
+        if (k < K) {
+          const float g = img[(n * K + k) * HW + hw];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[k][e] = fmaf(v.v[e], g, acc[k][e]);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kMaxK; ++k)
+      if (k < K) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sm[(rj * K + k) * C + cj * 8 + e] = acc[k][e];
+      }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < K * C; i += blockDim.x) {
+    const int k = i / C, c = i - k * C;
+    float s = 0.f;
+    for (int r = 0; r < rows; ++r) s += sm[(r * K + k) * C + c];
+    atomicAdd(dw + (long long)c * w_sc + (long long)k * w_sk, s * scale);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+img_chansum_kernel(const float *__restrict__ img, float *__restrict__ out, int N, long long HW,
+                   int K) {
+  __shared__ float red[32];
+  // grid.y = plane (n*K + k); grid.x strides over HW
+  const int plane = blockIdx.y;
+  const int k = plane % K;
+  const float *p = img + (long long)plane * HW;
+  float s = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < HW;
+       i += (long long)gridDim.x * blockDim.x)
+    s += p[i];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) atomicAdd(out + k, s);
+}
+
+}  // namespace pg
+
+using namespace pg;
+
+static int check_pw(const char *name, int N, long long HW, int K, int C) {
+  PG_CHECK_ARG(N > 0 && HW > 0, "%s: bad dims", name);
+  PG_CHECK_ARG(K >= 1 && K <= kMaxK, "%s: image channels K=%d must be in 1..%d", name, K, kMaxK);
+  PG_CHECK_ARG(C > 0 && C % 8 == 0 && C <= 2048, "%s: need C %% 8 == 0 and C <= 2048 (C=%d)",
+               name, C);
+  return PG_OK;
+}
+
+extern "C" int pg_pw_expand(const float *img, const float *w, const float *bias, void *act, int N,
+                            long long HW, int K, int C, int w_sc, int w_sk, float scale,
+                            int dtype, void *stream) {
+  PG_CHECK_ARG(img && w && act, "pg_pw_expand: null pointer");
+  if (int rc = check_pw("pg_pw_expand", N, HW, K, C)) return rc;
+  const long long total = (long long)N * HW * (C / 8);
+  const int grid = bw_grid(total, 256);
+  const size_t smem = (size_t)(K + 1) * C * sizeof(float);
+  PG_DISPATCH_DTYPE(dtype, T, pw_expand_kernel<T><<<grid, 256, smem, (cudaStream_t)stream>>>(
+                                  img, w, bias, (T *)act, N, HW, K, C, w_sc, w_sk, scale));
+  PG_CHECK_LAUNCH("pg_pw_expand");
+}
+
+extern "C" int pg_pw_reduce(const void *act, const float *w, const float *bias, float *img, int N,
+                            long long HW, int K, int C, int w_sc, int w_sk, float scale,
+                            int dtype, void *stream) {
+  PG_CHECK_ARG(img && w && act, "pg_pw_reduce: null pointer");
+  if (int rc = check_pw("pg_pw_reduce", N, HW, K, C)) return rc;
+  const int nch = C / 8;
+  const size_t smem = (size_t)K * C * sizeof(float);
+  const long long P = (long long)N * HW;
+  cudaStream_t s = (cudaStream_t)stream;
+#define PG_LAUNCH_PWR(TPP)                                                                  \
+  {                                                                                         \
+    const int grid = bw_grid(P, 256 / TPP);                                                 \
+    pw_reduce_kernel<T, TPP><<<grid, 256, smem, s>>>((const T *)act, w, bias, img, N, HW, K, \
+                                                     C, w_sc, w_sk, scale);                 \
+  }
+  PG_DISPATCH_DTYPE(dtype, T, {
+    if (nch <= 4) PG_LAUNCH_PWR(4)
+    else if (nch <= 8) PG_LAUNCH_PWR(8)
+    else if (nch <= 16) PG_LAUNCH_PWR(16)
+    else PG_LAUNCH_PWR(32)
+  });
+#undef PG_LAUNCH_PWR
+  PG_CHECK_LAUNCH("pg_pw_reduce");
+}
+
+extern "C" int pg_pw_wgrad(const void *act, const float *img, float *dw, int N, long long HW,
+                           int K, int C, int w_sc, int w_sk, float scale, int dtype,
+                           void *stream) {
+  PG_CHECK_ARG(img && dw && act, "pg_pw_wgrad: null pointer");
+  if (int rc = check_pw("pg_pw_wgrad", N, HW, K, C)) return rc;
+  const int nch = C / 8;
+  const int rows = 256 / nch;
+  PG_CHECK_ARG(rows >= 1, "pg_pw_wgrad: C too large");
+  const long long P = (long long)N * HW;
+  const int grid = bw_grid(P, rows * 16, 4);
+  const size_t smem = (size_t)rows * K * C * sizeof(float);
+  PG_DISPATCH_DTYPE(dtype, T, pw_wgrad_kernel<T><<<grid, 256, smem, (cudaStream_t)stream>>>(
+                                  (const T *)act, img, dw, N, HW, K, C, w_sc, w_sk, scale));
+  PG_CHECK_LAUNCH("pg_pw_wgrad");
+}
+
+extern "C" int pg_img_chansum(const float *img, float *out, int N, long long HW, int K,
+                              void *stream) {
+  PG_CHECK_ARG(img && out, "pg_img_chansum: null pointer");
+  PG_CHECK_ARG(N > 0 && HW > 0 && K > 0 && (long long)N * K <= 65535, "pg_img_chansum: bad dims");
+  int gx = (int)((HW + 256 * 8 - 1) / (256 * 8));
+  if (gx < 1) gx = 1;
+  if (gx > 64) gx = 64;
+  dim3 grid(gx, N * K);
+  img_chansum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img, out, N, HW, K);
+  PG_CHECK_LAUNCH("pg_img_chansum");
+}

@@ -1,0 +1,363 @@
+"""torch.autograd.Function families over the explicit kernels.
+
+The reference gets every derivative of the step from autograd over ATen ops, including
+the WGAN-GP double backward (train.py:146-151).  Here each fused op is a Function whose
+backward is *another* Function — the pattern the reference's own plugin ops use
+(ada/torch_utils/ops/bias_act.py:145-206, conv2d_gradfix.py:107-165) — so that
+`torch.autograd.grad(..., create_graph=True)` followed by `.backward()` in the train
+scripts keeps working, but every node of both graphs is one explicit kernel:
+
+  conv family   : ConvFwd(op) <-> ConvFwd(op.adjoint()) (data-grad), ConvWgrad(op)
+  1x1 heads     : PwFwd(expand|reduce), PwWgrad
+  activation    : ConvAct (fused conv+bias+PixelNorm+LeakyReLU epilogue) -> Act -> ActBwd,
+                  ActBwd.backward = the hand-derived PixelNorm second-order kernel
+  resampling    : Linear1(avgpool2|avgpool2_bwd|upsample2|upsample2_bwd), Blend, Scale
+  mbstd, tanh, gradient-penalty scalar.
+
+The tensor that links ConvAct to Act holds the stored post-activation y, but autograd-wise
+it *is* the pre-activation a: gradients w.r.t. it are true d/da, so the Hessian term that
+PixelNorm contributes during the GP double backward and the ordinary chain-rule term are
+summed by autograd and sent through ONE data-grad + ONE weight-grad per conv (6 F_D total,
+SURVEY.md §3.4), and the pre-activation never has to be written to HBM.
+"""
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import kernels as _k
+from .kernels import ConvOp, EPI_LINEAR, EPI_LRELU, EPI_PN_LRELU
+
+
+def K():
+    return _k.get_kernels()
+
+
+def _acc_node(p):
+    node = getattr(p, "_pg_acc_node", None)
+    if node is None:
+        node = p.view_as(p).grad_fn.next_functions[0][0]
+        try:
+            p._pg_acc_node = node
+        except Exception:
+            pass
+    return node
+
+
+def _wants_grad(ctx, idx, t):
+    """needs_input_grad refined by the engine's execution plan: for
+    autograd.grad(inputs=[x_hat]) / backward(inputs=G.parameters()) the weight-gradient
+    kernels of parameters that are not requested are skipped, as ATen's own
+    convolution_backward does through its output mask."""
+    if not ctx.needs_input_grad[idx]:
+        return False
+    if t is None or not (t.is_leaf and t.requires_grad):
+        return True
+    try:
+        return bool(torch._C._will_engine_execute_node(_acc_node(t)))
+    except Exception:
+        return True
+
+
+# --------------------------------------------------------------------------- conv
+class ConvFwd(Function):
+    """y = scale * conv(x; Wl(w)) — linear in x and w, no bias."""
+
+    @staticmethod
+    def forward(ctx, x, w, op, scale):
+        ctx.op, ctx.scale = op, scale
+        ctx.save_for_backward(x, w)
+        y, _ = K().conv_fwd(x, w, None, op, scale, EPI_LINEAR)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = ConvFwd.apply(dy, w, ctx.op.adjoint(), ctx.scale)
+        if _wants_grad(ctx, 1, w):
+            dw = ConvWgrad.apply(x, dy, ctx.op, ctx.scale, tuple(w.shape))
+        return dx, dw, None, None
+
+
+class ConvWgrad(Function):
+    """dw = scale * sum_pix dy (x) x  in the parameter's own layout."""
+
+    @staticmethod
+    def forward(ctx, x, dy, op, scale, wshape):
+        ctx.op, ctx.scale = op, scale
+        ctx.save_for_backward(x, dy)
+        return K().conv_wgrad(x, dy, wshape, op, scale)
+
+    @staticmethod
+    def backward(ctx, ddw):
+        x, dy = ctx.saved_tensors
+        ddw = ddw.contiguous()
+        cx = cdy = None
+        if ctx.needs_input_grad[0]:
+            cx = ConvFwd.apply(dy, ddw, ctx.op.adjoint(), ctx.scale)
+        if ctx.needs_input_grad[1]:
+            cdy = ConvFwd.apply(x, ddw, ctx.op, ctx.scale)
+        return cx, cdy, None, None, None
+
+
+class ColSum(Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.shape, ctx.dtype = x.shape, x.dtype
+        return K().colsum(x)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        return g.to(ctx.dtype).expand(ctx.shape).contiguous()
+
+
+class ConvAct(Function):
+    """Fused y = lrelu(pixelnorm(scale*conv(x;w) + b)) — one kernel, epilogue-fused.
+    Returns (A, r): A carries y's data but stands for the pre-activation in the graph."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, op, scale, slope, use_pn):
+        ctx.op, ctx.scale = op, scale
+        ctx.save_for_backward(x, w, b)
+        y, r = K().conv_fwd(x, w, b, op, scale, EPI_PN_LRELU if use_pn else EPI_LRELU, slope)
+        if r is None:
+            r = torch.empty(0, device=x.device, dtype=torch.float32)
+        ctx.mark_non_differentiable(r)
+        return y, r
+
+    @staticmethod
+    def backward(ctx, dA, _dr):
+        x, w, b = ctx.saved_tensors
+        dA = dA.contiguous()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = ConvFwd.apply(dA, w, ctx.op.adjoint(), ctx.scale)
+        if _wants_grad(ctx, 1, w):
+            dw = ConvWgrad.apply(x, dA, ctx.op, ctx.scale, tuple(w.shape))
+        if b is not None and _wants_grad(ctx, 2, b):
+            db = ColSum.apply(dA)
+        return dx, dw, db, None, None, None, None
+
+
+class Act(Function):
+    """Graph marker turning the 'pre-activation handle' A into the activation y (same data)."""
+
+    @staticmethod
+    def forward(ctx, A, r, slope, use_pn):
+        ctx.slope, ctx.use_pn = slope, use_pn
+        ctx.save_for_backward(A, r)
+        return A.view_as(A)
+
+    @staticmethod
+    def backward(ctx, dy):
+        A, r = ctx.saved_tensors
+        return ActBwd.apply(dy.contiguous(), A, r, ctx.slope, ctx.use_pn), None, None, None
+
+
+class ActBwd(Function):
+    """da = Jpn(a)^T (m * dy)  — first-order PixelNorm+LeakyReLU backward."""
+
+    @staticmethod
+    def forward(ctx, dy, A, r, slope, use_pn):
+        ctx.slope, ctx.use_pn = slope, use_pn
+        ctx.save_for_backward(dy, A, r)
+        return K().pn_lrelu_bwd(dy, A, r if use_pn else None, slope, use_pn)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, t):
+        dy, A, r = ctx.saved_tensors
+        cot_dy, cot_a = K().pn_lrelu_bwd_bwd(t.contiguous(), dy, A, r if ctx.use_pn else None,
+                                             ctx.slope, ctx.use_pn)
+        if not ctx.needs_input_grad[1] or not ctx.use_pn:
+            cot_a = None
+        return cot_dy, cot_a, None, None, None
+
+
+def conv_act(x, w, b, op, scale, slope=0.2, use_pn=True):
+    A, r = ConvAct.apply(x, w, b, op, scale, slope, use_pn)
+    return Act.apply(A, r, slope, use_pn)
+
+
+# ---------------------------------------------------------------------- 1x1 heads
+class PwFwd(Function):
+    """from_rgb ('expand': image NCHW fp32 -> act NHWC) / to_rgb, linear ('reduce')."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, kind, C, Kc, w_sc, w_sk, scale, act_dtype):
+        ctx.cfg = (kind, C, Kc, w_sc, w_sk, scale, act_dtype)
+        ctx.save_for_backward(x, w, b)
+        if kind == "expand":
+            return K().pw_expand(x, w, b, C, w_sc, w_sk, scale, act_dtype)
+        return K().pw_reduce(x, w, b, Kc, w_sc, w_sk, scale)
+
+    @staticmethod
+    def backward(ctx, dy):
+        kind, C, Kc, w_sc, w_sk, scale, act_dtype = ctx.cfg
+        x, w, b = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = dw = db = None
+        other = "reduce" if kind == "expand" else "expand"
+        if ctx.needs_input_grad[0]:
+            dx = PwFwd.apply(dy, w, None, other, C, Kc, w_sc, w_sk, scale, act_dtype)
+        if _wants_grad(ctx, 1, w):
+            act, img = (dy, x) if kind == "expand" else (x, dy)
+            dw = PwWgrad.apply(act, img, tuple(w.shape), C, Kc, w_sc, w_sk, scale, act_dtype)
+        if b is not None and _wants_grad(ctx, 2, b):
+            db = ColSum.apply(dy) if kind == "expand" else ImgChanSum.apply(dy)
+        return (dx, dw, db) + (None,) * 7
+
+
+class PwWgrad(Function):
+    @staticmethod
+    def forward(ctx, act, img, wshape, C, Kc, w_sc, w_sk, scale, act_dtype):
+        ctx.cfg = (C, Kc, w_sc, w_sk, scale, act_dtype)
+        ctx.save_for_backward(act, img)
+        return K().pw_wgrad(act, img, wshape, w_sc, w_sk, scale)
+
+    @staticmethod
+    def backward(ctx, ddw):
+        C, Kc, w_sc, w_sk, scale, act_dtype = ctx.cfg
+        act, img = ctx.saved_tensors
+        ddw = ddw.contiguous()
+        ca = ci = None
+        if ctx.needs_input_grad[0]:
+            ca = PwFwd.apply(img, ddw, None, "expand", C, Kc, w_sc, w_sk, scale, act_dtype)
+        if ctx.needs_input_grad[1]:
+            ci = PwFwd.apply(act, ddw, None, "reduce", C, Kc, w_sc, w_sk, scale, act_dtype)
+        return (ca, ci) + (None,) * 7
+
+
+class ImgChanSum(Function):
+    @staticmethod
+    def forward(ctx, img):
+        ctx.shape = img.shape
+        return K().img_chansum(img)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        return g.view(1, -1, 1, 1).expand(ctx.shape).contiguous()
+
+
+# --------------------------------------------------------------------- resampling
+_PARTNER = {"avgpool2": "avgpool2_bwd", "avgpool2_bwd": "avgpool2",
+            "upsample2": "upsample2_bwd", "upsample2_bwd": "upsample2"}
+
+
+class Linear1(Function):
+    """A parameter-free linear map and its transpose (bilinear x2 / x0.5 resampling)."""
+
+    @staticmethod
+    def forward(ctx, x, name, fmt):
+        ctx.name, ctx.fmt = name, fmt
+        return getattr(K(), name)(x, fmt)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return Linear1.apply(dy.contiguous(), _PARTNER[ctx.name], ctx.fmt), None, None
+
+
+def avgpool2(x, fmt="nhwc"):
+    return Linear1.apply(x, "avgpool2", fmt)
+
+
+def upsample2(x, fmt="nhwc"):
+    return Linear1.apply(x, "upsample2", fmt)
+
+
+class Scale(Function):
+    """out = (c0 + c1*alpha) * x, alpha read from device memory."""
+
+    @staticmethod
+    def forward(ctx, x, c0, c1, alpha_dev):
+        ctx.c = (c0, c1)
+        ctx.alpha_dev = alpha_dev
+        return K().scale(x, c0, c1, alpha_dev)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return Scale.apply(dy.contiguous(), ctx.c[0], ctx.c[1], ctx.alpha_dev), None, None, None
+
+
+class Blend(Function):
+    """out = (1-alpha)*a + alpha*b   (progan_modules.py:212, 305)."""
+
+    @staticmethod
+    def forward(ctx, a, b, alpha_dev):
+        ctx.alpha_dev = alpha_dev
+        return K().blend(a, b, alpha_dev)
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = dy.contiguous()
+        da = Scale.apply(dy, 1.0, -1.0, ctx.alpha_dev) if ctx.needs_input_grad[0] else None
+        db = Scale.apply(dy, 0.0, 1.0, ctx.alpha_dev) if ctx.needs_input_grad[1] else None
+        return da, db, None
+
+
+class Tanh(Function):
+    @staticmethod
+    def forward(ctx, x):
+        y = K().tanh_fwd(x)
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        return K().tanh_bwd(dy.contiguous(), y)
+
+
+# -------------------------------------------------------------------------- mbstd
+class Mbstd(Function):
+    @staticmethod
+    def forward(ctx, x, Cp):
+        ctx.save_for_backward(x)
+        return K().mbstd_fwd(x, Cp)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (x,) = ctx.saved_tensors
+        return MbstdBwd.apply(dout.contiguous(), x), None
+
+
+class MbstdBwd(Function):
+    @staticmethod
+    def forward(ctx, dout, x):
+        ctx.save_for_backward(dout, x)
+        return K().mbstd_bwd(dout, x)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, t):
+        dout, x = ctx.saved_tensors
+        cot_dout, cot_x = K().mbstd_bwd_bwd(t.contiguous(), dout, x)
+        return cot_dout, cot_x
+
+
+# ---------------------------------------------------------------- gradient penalty
+class GradPenalty(Function):
+    """gp = lambda * mean_n (||g_n||_2 - 1)^2   (train.py:148-150)."""
+
+    @staticmethod
+    def forward(ctx, g, lam):
+        g = g.contiguous()
+        gp, norms = K().gp_fwd(g, lam)
+        ctx.lam = lam
+        ctx.save_for_backward(g, norms)
+        return gp
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, up):
+        g, norms = ctx.saved_tensors
+        return K().gp_bwd(g, norms, up.contiguous(), ctx.lam), None
+
+
+def gradient_penalty(grad_x_hat, lam=10.0):
+    return GradPenalty.apply(grad_x_hat, lam)

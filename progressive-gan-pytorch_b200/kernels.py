@@ -1,0 +1,398 @@
+"""Host shim over the C-ABI: shape/dtype/contiguity checks, output allocation, launch.
+
+Mirrors what the reference's C++ wrappers do around their kernels
+(ada/torch_utils/ops/bias_act.cpp:32-97: TORCH_CHECK list, empty_like, launch on the
+current stream) — but in Python, with torch used only as the allocator / stream owner.
+
+Tensor conventions
+  act   : [N,H,W,C] contiguous, float32 (check mode) or bfloat16 (product mode)
+  image : [N,K,H,W] contiguous float32 (the module boundary, as the train scripts pass it)
+  params, param grads, per-pixel statistics: float32
+"""
+import weakref
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+
+EPI_LINEAR, EPI_PN_LRELU, EPI_LRELU = 0, 1, 2
+WL_TAP_CI_CO, WL_CO_TAP_CI = 0, 1
+
+_DT = {torch.float32: 0, torch.bfloat16: 1}
+
+
+@dataclass(frozen=True)
+class ConvOp:
+    """A 'logical' stride-1 cross-correlation y = conv_k,pad(x; Wl(w)).
+
+    Wl is derived from the stored parameter w[d0,d1,k,k] by (swap, flip):
+      swap=False: Wl[co][ci] = w[co][ci]   (nn.Conv2d, progan_modules.py:67)
+      swap=True : Wl[co][ci] = w[ci][co]   (nn.ConvTranspose2d IOHW, :81, and data-grads)
+      flip      : taps reversed.
+    adjoint() is the op whose forward is this op's data-gradient.
+    """
+    k: int
+    pad: int
+    swap: bool = False
+    flip: bool = False
+
+    def adjoint(self):
+        return ConvOp(self.k, self.k - 1 - self.pad, not self.swap, not self.flip)
+
+    def cout(self, wshape):
+        return wshape[1] if self.swap else wshape[0]
+
+    def cin(self, wshape):
+        return wshape[0] if self.swap else wshape[1]
+
+
+def _dt(t):
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise RuntimeError("progan_b200: unsupported activation dtype %s" % t.dtype)
+
+
+def _chk(t, name, dtype=None, ndim=None):
+    if not isinstance(t, torch.Tensor):
+        raise RuntimeError("progan_b200: %s must be a tensor" % name)
+    if not t.is_cuda:
+        raise RuntimeError(
+            "progan_b200: %s is on %s; the kernels are CUDA-only (sm_100a) and there is no "
+            "CPU fallback" % (name, t.device))
+    if not t.is_contiguous():
+        raise RuntimeError("progan_b200: %s must be contiguous" % name)
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError("progan_b200: %s must be %s, got %s" % (name, dtype, t.dtype))
+    if ndim is not None and t.dim() != ndim:
+        raise RuntimeError("progan_b200: %s must have %d dims, got %s" % (name, ndim, tuple(t.shape)))
+    return t
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+class CudaKernels:
+    """The product backend: every method is one (or two) launches of a hand-written kernel."""
+
+    name = "cuda"
+
+    def __init__(self):
+        self.lib = _lib.load()
+        self.conv_impl = "tc"          # "tc": tcgen05 where the shape allows; "simt": always CUDA cores
+        self.launches = 0              # kernels launched through this shim (bench `gpu_launches`)
+        self._packs = {}               # id(param) -> (weakref, version, {variant: tensor})
+
+    # ------------------------------------------------------------------ utils
+    @staticmethod
+    def _stream():
+        return torch.cuda.current_stream().cuda_stream
+
+    def _call(self, name, *args):
+        rc = getattr(self.lib, name)(*args)
+        if rc != 0:
+            _lib.check(rc, name)
+        self.launches += 1
+
+    def tc_eligible(self, x, wshape, op):
+        if self.conv_impl != "tc" or x.dtype != torch.bfloat16:
+            return False
+        cin, cout = op.cin(wshape), op.cout(wshape)
+        return (op.k == 3 and op.pad == 1 and cin % 32 == 0 and cout in (32, 64, 128, 256)
+                and x.shape[-1] == cin)
+
+    # --------------------------------------------------------------- packing
+    def invalidate_packs(self):
+        self._packs.clear()
+
+    def packed(self, w, op, layout, dtype):
+        """Operand-layout copy of weight_orig for (op, layout, dtype); cached per parameter
+        version (in-place optimizer updates bump Tensor._version)."""
+        key = (op.swap, op.flip, layout, dtype)
+        cacheable = isinstance(w, torch.nn.Parameter)
+        if cacheable:
+            ent = self._packs.get(id(w))
+            if ent is not None and ent[0]() is w and ent[1] == w._version:
+                hit = ent[2].get(key)
+                if hit is not None:
+                    return hit
+            else:
+                ent = (weakref.ref(w), w._version, {})
+                self._packs[id(w)] = ent
+        _chk(w, "weight", torch.float32, 4)
+        d0, d1, kh, kw = w.shape
+        cout, cin = op.cout(w.shape), op.cin(w.shape)
+        out = torch.empty(cout * kh * kw * cin, device=w.device, dtype=dtype)
+        self._call("pg_pack_conv_weight", w.data_ptr(), out.data_ptr(), d0, d1, kh, kw,
+                   int(op.swap), int(op.flip), layout, cin, _DT[dtype], self._stream())
+        if cacheable:
+            ent[2][key] = out
+        return out
+
+    # ------------------------------------------------------------------ conv
+    def conv_fwd(self, x, w, bias, op, scale, epi=EPI_LINEAR, slope=0.2):
+        """y = epi(scale * conv(x; Wl(w)) + bias).  Returns (y, r) with r the per-pixel
+        PixelNorm rsqrt (fp32 [N,Ho,Wo]) for EPI_PN_LRELU, else None."""
+        _chk(x, "x", ndim=4)
+        _chk(w, "w", torch.float32, 4)
+        if bias is not None:
+            _chk(bias, "bias", torch.float32, 1)
+        N, H, W, C = x.shape
+        cin, cout = op.cin(w.shape), op.cout(w.shape)
+        if C != cin or w.shape[2] != op.k or w.shape[3] != op.k:
+            raise RuntimeError("progan_b200: conv shape mismatch x=%s w=%s op=%s"
+                               % (tuple(x.shape), tuple(w.shape), op))
+        Ho, Wo = H + 2 * op.pad - op.k + 1, W + 2 * op.pad - op.k + 1
+        y = torch.empty((N, Ho, Wo, cout), device=x.device, dtype=x.dtype)
+        r = torch.empty((N, Ho, Wo), device=x.device, dtype=torch.float32) if epi == EPI_PN_LRELU else None
+        if self.tc_eligible(x, w.shape, op):
+            wp = self.packed(w, op, WL_CO_TAP_CI, torch.bfloat16)
+            self._call("pg_conv_tc", x.data_ptr(), wp.data_ptr(), _ptr(bias), y.data_ptr(), _ptr(r),
+                       N, H, W, cin, cout, 9, float(scale), epi, float(slope), self._stream())
+        else:
+            wp = self.packed(w, op, WL_TAP_CI_CO, x.dtype)
+            self._call("pg_conv_fwd_simt", x.data_ptr(), wp.data_ptr(), _ptr(bias), y.data_ptr(),
+                       _ptr(r), N, H, W, cin, cout, op.k, op.pad, float(scale), epi, float(slope),
+                       _dt(x), self._stream())
+        return y, r
+
+    def conv_wgrad(self, x, dy, wshape, op, scale):
+        """dw[wshape] = scale * sum_pix dy (x) x for the conv `op` (fp32)."""
+        _chk(x, "x", ndim=4)
+        _chk(dy, "dy", x.dtype, 4)
+        N, H, W, cin = x.shape
+        cout = dy.shape[-1]
+        if cin != op.cin(wshape) or cout != op.cout(wshape):
+            raise RuntimeError("progan_b200: wgrad shape mismatch")
+        dw = torch.zeros(tuple(wshape), device=x.device, dtype=torch.float32)
+        if self.tc_eligible(x, wshape, op):
+            self._call("pg_conv_wgrad_tc", x.data_ptr(), dy.data_ptr(), dw.data_ptr(), N, H, W, cin,
+                       cout, 9, float(scale), int(op.swap), int(op.flip), self._stream())
+        else:
+            self._call("pg_conv_wgrad_simt", x.data_ptr(), dy.data_ptr(), dw.data_ptr(), N, H, W,
+                       cin, cout, op.k, op.pad, float(scale), int(op.swap), int(op.flip), _dt(x),
+                       self._stream())
+        return dw
+
+    # ------------------------------------------------- PixelNorm + LeakyReLU
+    def pn_lrelu_bwd(self, dy, y, r, slope, use_pn):
+        _chk(dy, "dy", y.dtype)
+        _chk(y, "y")
+        C = y.shape[-1]
+        da = torch.empty_like(y)
+        self._call("pg_pn_lrelu_bwd", dy.data_ptr(), y.data_ptr(), _ptr(r), da.data_ptr(),
+                   y.numel() // C, C, float(slope), int(use_pn), _dt(y), self._stream())
+        return da
+
+    def pn_lrelu_bwd_bwd(self, t, dy, y, r, slope, use_pn):
+        _chk(t, "t", y.dtype)
+        _chk(dy, "dy", y.dtype)
+        C = y.shape[-1]
+        cot_dy, cot_a = torch.empty_like(y), torch.empty_like(y)
+        self._call("pg_pn_lrelu_bwd_bwd", t.data_ptr(), dy.data_ptr(), y.data_ptr(), _ptr(r),
+                   cot_dy.data_ptr(), cot_a.data_ptr(), y.numel() // C, C, float(slope),
+                   int(use_pn), _dt(y), self._stream())
+        return cot_dy, cot_a
+
+    def colsum(self, x):
+        _chk(x, "x")
+        C = x.shape[-1]
+        out = torch.zeros(C, device=x.device, dtype=torch.float32)
+        self._call("pg_colsum", x.data_ptr(), out.data_ptr(), x.numel() // C, C, _dt(x), self._stream())
+        return out
+
+    # ------------------------------------------------------------ 1x1 heads
+    def pw_expand(self, img, w, bias, C, w_sc, w_sk, scale, dtype):
+        _chk(img, "img", torch.float32, 4)
+        _chk(w, "w", torch.float32)
+        N, Kc, H, W = img.shape
+        act = torch.empty((N, H, W, C), device=img.device, dtype=dtype)
+        self._call("pg_pw_expand", img.data_ptr(), w.data_ptr(), _ptr(bias), act.data_ptr(), N, H * W,
+                   Kc, C, w_sc, w_sk, float(scale), _DT[dtype], self._stream())
+        return act
+
+    def pw_reduce(self, act, w, bias, Kc, w_sc, w_sk, scale):
+        _chk(act, "act", ndim=4)
+        _chk(w, "w", torch.float32)
+        N, H, W, C = act.shape
+        img = torch.empty((N, Kc, H, W), device=act.device, dtype=torch.float32)
+        self._call("pg_pw_reduce", act.data_ptr(), w.data_ptr(), _ptr(bias), img.data_ptr(), N, H * W,
+                   Kc, C, w_sc, w_sk, float(scale), _dt(act), self._stream())
+        return img
+
+    def pw_wgrad(self, act, img, wshape, w_sc, w_sk, scale):
+        _chk(act, "act", ndim=4)
+        _chk(img, "img", torch.float32, 4)
+        N, H, W, C = act.shape
+        Kc = img.shape[1]
+        dw = torch.zeros(tuple(wshape), device=act.device, dtype=torch.float32)
+        self._call("pg_pw_wgrad", act.data_ptr(), img.data_ptr(), dw.data_ptr(), N, H * W, Kc, C,
+                   w_sc, w_sk, float(scale), _dt(act), self._stream())
+        return dw
+
+    def img_chansum(self, img):
+        _chk(img, "img", torch.float32, 4)
+        N, Kc, H, W = img.shape
+        out = torch.zeros(Kc, device=img.device, dtype=torch.float32)
+        self._call("pg_img_chansum", img.data_ptr(), out.data_ptr(), N, H * W, Kc, self._stream())
+        return out
+
+    # ------------------------------------------------------------- resample
+    def _resample(self, fn, x, fmt, out_hw):
+        _chk(x, "x", ndim=4)
+        if fmt == "nchw":
+            N, Kc, H, W = x.shape
+            n_, c_ = N * Kc, 1
+            out = torch.empty((N, Kc) + out_hw(H, W), device=x.device, dtype=x.dtype)
+        else:
+            N, H, W, C = x.shape
+            n_, c_ = N, C
+            out = torch.empty((N,) + out_hw(H, W) + (C,), device=x.device, dtype=x.dtype)
+        return out, n_, H, W, c_
+
+    def avgpool2(self, x, fmt="nhwc"):
+        out, n, H, W, c = self._resample("avgpool2", x, fmt, lambda h, w: (h // 2, w // 2))
+        self._call("pg_avgpool2", x.data_ptr(), out.data_ptr(), n, H, W, c, _dt(x), self._stream())
+        return out
+
+    def avgpool2_bwd(self, dy, fmt="nhwc"):
+        out, n, H, W, c = self._resample("avgpool2_bwd", dy, fmt, lambda h, w: (2 * h, 2 * w))
+        self._call("pg_avgpool2_bwd", dy.data_ptr(), out.data_ptr(), n, 2 * H, 2 * W, c, _dt(dy),
+                   self._stream())
+        return out
+
+    def upsample2(self, x, fmt="nhwc"):
+        out, n, H, W, c = self._resample("upsample2", x, fmt, lambda h, w: (2 * h, 2 * w))
+        self._call("pg_upsample2", x.data_ptr(), out.data_ptr(), n, H, W, c, _dt(x), self._stream())
+        return out
+
+    def upsample2_bwd(self, dy, fmt="nhwc"):
+        out, n, H, W, c = self._resample("upsample2_bwd", dy, fmt, lambda h, w: (h // 2, w // 2))
+        self._call("pg_upsample2_bwd", dy.data_ptr(), out.data_ptr(), n, H // 2, W // 2, c, _dt(dy),
+                   self._stream())
+        return out
+
+    # ---------------------------------------------------------- elementwise
+    def blend(self, a, b, alpha_dev):
+        _chk(a, "a")
+        _chk(b, "b", a.dtype)
+        _chk(alpha_dev, "alpha_dev", torch.float32)
+        if a.shape != b.shape:
+            raise RuntimeError("progan_b200: blend shape mismatch %s vs %s" % (tuple(a.shape), tuple(b.shape)))
+        out = torch.empty_like(a)
+        self._call("pg_blend", a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(),
+                   alpha_dev.data_ptr(), _dt(a), self._stream())
+        return out
+
+    def scale(self, x, c0, c1, alpha_dev):
+        _chk(x, "x")
+        out = torch.empty_like(x)
+        self._call("pg_scale", x.data_ptr(), out.data_ptr(), x.numel(), float(c0), float(c1),
+                   _ptr(alpha_dev), _dt(x), self._stream())
+        return out
+
+    def tanh_fwd(self, x):
+        _chk(x, "x", torch.float32)
+        y = torch.empty_like(x)
+        self._call("pg_tanh_fwd", x.data_ptr(), y.data_ptr(), x.numel(), self._stream())
+        return y
+
+    def tanh_bwd(self, dy, y):
+        _chk(dy, "dy", torch.float32)
+        _chk(y, "y", torch.float32)
+        dx = torch.empty_like(y)
+        self._call("pg_tanh_bwd", dy.data_ptr(), y.data_ptr(), dx.data_ptr(), y.numel(), self._stream())
+        return dx
+
+    # --------------------------------------------------------------- mbstd
+    def mbstd_fwd(self, x, Cp):
+        _chk(x, "x", ndim=4)
+        N, H, W, C = x.shape
+        if H != 4 or W != 4:
+            raise RuntimeError("progan_b200: minibatch-stddev expects a 4x4 map, got %dx%d" % (H, W))
+        out = torch.empty((N, 4, 4, Cp), device=x.device, dtype=x.dtype)
+        self._call("pg_mbstd_fwd", x.data_ptr(), out.data_ptr(), N, C, Cp, _dt(x), self._stream())
+        return out
+
+    def mbstd_bwd(self, dout, x):
+        _chk(dout, "dout", x.dtype, 4)
+        N, _, _, C = x.shape
+        dx = torch.empty_like(x)
+        self._call("pg_mbstd_bwd", dout.data_ptr(), x.data_ptr(), dx.data_ptr(), N, C,
+                   dout.shape[-1], _dt(x), self._stream())
+        return dx
+
+    def mbstd_bwd_bwd(self, t, dout, x):
+        _chk(t, "t", x.dtype, 4)
+        _chk(dout, "dout", x.dtype, 4)
+        N, _, _, C = x.shape
+        cot_dout, cot_x = torch.empty_like(dout), torch.empty_like(x)
+        self._call("pg_mbstd_bwd_bwd", t.data_ptr(), dout.data_ptr(), x.data_ptr(),
+                   cot_dout.data_ptr(), cot_x.data_ptr(), N, C, dout.shape[-1], _dt(x), self._stream())
+        return cot_dout, cot_x
+
+    # ------------------------------------------------------------- WGAN-GP
+    def interp_xhat(self, real, fake, eps):
+        _chk(real, "real", torch.float32)
+        _chk(fake, "fake", torch.float32)
+        _chk(eps, "eps", torch.float32)
+        N = real.shape[0]
+        if fake.shape != real.shape or eps.numel() != N:
+            raise RuntimeError("progan_b200: interp_xhat shape mismatch")
+        out = torch.empty_like(real)
+        self._call("pg_interp_xhat", real.data_ptr(), fake.data_ptr(), eps.data_ptr(), out.data_ptr(),
+                   N, real.numel() // N, self._stream())
+        return out
+
+    def gp_fwd(self, g, lam):
+        _chk(g, "g", torch.float32)
+        N = g.shape[0]
+        norms = torch.empty(N, device=g.device, dtype=torch.float32)
+        gp = torch.empty((), device=g.device, dtype=torch.float32)
+        self._call("pg_gp_fwd", g.data_ptr(), norms.data_ptr(), gp.data_ptr(), N, g.numel() // N,
+                   float(lam), self._stream())
+        self.launches += 1
+        return gp, norms
+
+    def gp_bwd(self, g, norms, upstream, lam):
+        _chk(g, "g", torch.float32)
+        N = g.shape[0]
+        v = torch.empty_like(g)
+        self._call("pg_gp_bwd", g.data_ptr(), norms.data_ptr(), _ptr(upstream), v.data_ptr(), N,
+                   g.numel() // N, float(lam), self._stream())
+        return v
+
+    # ----------------------------------------------------------- optimiser
+    def adam_step(self, p, g, m, v, lr, beta1, beta2, eps, step_dev, grad_scale=1.0):
+        for t, n in ((p, "p"), (g, "g"), (v, "v"), (step_dev, "step")):
+            _chk(t, n, torch.float32)
+        self._call("pg_adam_step", p.data_ptr(), g.data_ptr(), _ptr(m), v.data_ptr(), p.numel(),
+                   float(lr), float(beta1), float(beta2), float(eps), step_dev.data_ptr(),
+                   float(grad_scale), self._stream())
+
+    def ema(self, ema, p, decay):
+        _chk(ema, "ema", torch.float32)
+        _chk(p, "p", torch.float32)
+        self._call("pg_ema", ema.data_ptr(), p.data_ptr(), p.numel(), float(decay), self._stream())
+
+
+_backend = None
+
+
+def get_kernels():
+    """The process-wide kernel backend (loads the shared library on first use)."""
+    global _backend
+    if _backend is None:
+        _backend = CudaKernels()
+    return _backend
+
+
+def set_kernels(backend):
+    """Install a different backend object (tests install a torch emulation of the kernel
+    semantics to check the host/autograd logic on machines without a GPU)."""
+    global _backend
+    prev = _backend
+    _backend = backend
+    return prev

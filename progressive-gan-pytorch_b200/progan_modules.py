@@ -1,0 +1,255 @@
+"""Host-side mirror of the reference's progan_modules.py for the training hot path.
+
+Same class names, constructor arguments, attribute names, forward signatures
+(`Generator(...).forward(input, step=0, alpha=-1)`, progan_modules.py:172,219;
+`Discriminator(...).forward(input, step=0, alpha=-1)`, :258,282) and state-dict keys
+(`...conv.weight_orig`, `...conv.bias`, `linear.linear.weight_orig`; SURVEY.md Appx A),
+so the reference's train scripts and checkpoints work unchanged.  Everything below the
+signatures is different: activations live in NHWC (bf16 in product mode, fp32 in check
+mode), the equalized-LR scale sqrt(2/fan_in) (EqualLR.compute_weight, :22-27) is folded
+into kernel epilogues instead of a per-forward weight multiply, and every op is an
+explicit sm_100a kernel behind the C-ABI (see functions.py / include/progan_b200.h).
+"""
+from math import sqrt
+
+import torch
+from torch import nn
+
+from . import functions as F_
+from .kernels import ConvOp
+
+_DEFAULT_PRECISION = "bf16"
+
+
+def set_default_precision(p):
+    """'bf16' (product: bf16 activations, fp32 accumulate) or 'fp32' (check mode)."""
+    global _DEFAULT_PRECISION
+    if p not in ("bf16", "fp32"):
+        raise ValueError("precision must be 'bf16' or 'fp32'")
+    _DEFAULT_PRECISION = p
+
+
+def _act_dtype(p):
+    # 'fp64' exists for the CPU test double only; the CUDA kernels take bf16 / fp32.
+    return {"bf16": torch.bfloat16, "fp32": torch.float32, "fp64": torch.float64}[p]
+
+
+def _img_dtype(p):
+    return torch.float64 if p == "fp64" else torch.float32
+
+
+class _Holder(nn.Module):
+    """Holds weight_orig/bias under the name `.conv` / `.linear` like equal_lr() does."""
+
+    def __init__(self, wshape, bias_n):
+        super().__init__()
+        # registration order (bias, weight_orig) matches the reference after equal_lr()
+        self.bias = nn.Parameter(torch.zeros(bias_n))           # conv.bias.data.zero_()
+        self.weight_orig = nn.Parameter(torch.randn(*wshape))   # conv.weight.data.normal_()
+
+
+class EqualConv2d(nn.Module):
+    """nn.Conv2d with equalized LR (progan_modules.py:63-73); kernel 1, 3 (pad 1) or 4 (pad 0)."""
+
+    def __init__(self, in_channel, out_channel, kernel_size, padding=0):
+        super().__init__()
+        self.cin, self.cout, self.k, self.pad = in_channel, out_channel, kernel_size, padding
+        self.conv = _Holder((out_channel, in_channel, kernel_size, kernel_size), out_channel)
+        self.scale = sqrt(2 / (in_channel * kernel_size * kernel_size))
+        self.op = ConvOp(kernel_size, padding, False, False)
+
+
+class EqualConvTranspose2d(nn.Module):
+    """nn.ConvTranspose2d(stride 1) with equalized LR (:76-92).  fan_in follows the
+    reference quirk: weight is IOHW so size(1)*k*k = Cout*k*k (:24)."""
+
+    def __init__(self, in_channel, out_channel, kernel_size, stride=1, padding=0):
+        super().__init__()
+        if stride != 1:
+            raise NotImplementedError("only stride-1 ConvTranspose2d is on the hot path")
+        self.cin, self.cout, self.k = in_channel, out_channel, kernel_size
+        self.conv = _Holder((in_channel, out_channel, kernel_size, kernel_size), out_channel)
+        self.scale = sqrt(2 / (out_channel * kernel_size * kernel_size))
+        self.op = ConvOp(kernel_size, kernel_size - 1 - padding, True, True)
+
+
+class EqualLinear(nn.Module):
+    def __init__(self, in_dim, out_dim):
+        super().__init__()
+        self.linear = _Holder((out_dim, in_dim), out_dim)
+        self.in_dim, self.out_dim = in_dim, out_dim
+        self.scale = sqrt(2 / in_dim)
+
+
+class PixelNorm(nn.Module):
+    """Marker only: PixelNorm (:54-60) is fused into the preceding conv's epilogue."""
+
+
+class _LeakyMarker(nn.Module):
+    def __init__(self, slope):
+        super().__init__()
+        self.negative_slope = slope
+
+
+def _fused_layer(x, conv, slope, use_pn):
+    h = conv.conv
+    return F_.conv_act(x, h.weight_orig, h.bias, conv.op, conv.scale, slope, use_pn)
+
+
+class ConvBlock(nn.Module):
+    """conv -> [PixelNorm] -> LeakyReLU(0.2) -> conv -> [PixelNorm] -> LeakyReLU(0.2)
+    (progan_modules.py:120-148); each conv+PN+LReLU is ONE fused kernel."""
+
+    def __init__(self, in_channel, out_channel, kernel_size, padding, kernel_size2=None,
+                 padding2=None, pixel_norm=True):
+        super().__init__()
+        pad2 = padding if padding2 is None else padding2
+        k2 = kernel_size if kernel_size2 is None else kernel_size2
+        mods = [EqualConv2d(in_channel, out_channel, kernel_size, padding=padding)]
+        if pixel_norm:
+            mods.append(PixelNorm())
+        mods.append(_LeakyMarker(0.2))
+        mods.append(EqualConv2d(out_channel, out_channel, k2, padding=pad2))
+        if pixel_norm:
+            mods.append(PixelNorm())
+        mods.append(_LeakyMarker(0.2))
+        self.conv = nn.Sequential(*mods)   # same indices as the reference: conv.0 / conv.3 (or conv.2)
+        self.pixel_norm = pixel_norm
+        self._c1 = 0
+        self._c2 = 3 if pixel_norm else 2
+
+    def forward(self, x):
+        x = _fused_layer(x, self.conv[self._c1], 0.2, self.pixel_norm)
+        return _fused_layer(x, self.conv[self._c2], 0.2, self.pixel_norm)
+
+
+class _AlphaMixin:
+    @staticmethod
+    def _alpha(alpha, device):
+        """alpha lives in device memory so blend kernels (and captured graphs) read the
+        current value; `alpha` may be a python float or an fp32 device tensor."""
+        if torch.is_tensor(alpha):
+            return alpha
+        return torch.full((), float(alpha), device=device, dtype=torch.float32)
+
+
+def _to_rgb(feat, m, act_dtype):
+    h = m.conv
+    C = feat.shape[-1]
+    return F_.PwFwd.apply(feat, h.weight_orig, h.bias, "reduce", C, 3, 1, C, m.scale, act_dtype)
+
+
+def _from_rgb(img, m, act_dtype):
+    h = m.conv
+    Kc = img.shape[1]
+    return F_.PwFwd.apply(img, h.weight_orig, h.bias, "expand", m.cout, Kc, Kc, 1, m.scale, act_dtype)
+
+
+class Generator(nn.Module, _AlphaMixin):
+    def __init__(self, input_code_dim=128, in_channel=128, pixel_norm=True, tanh=True, max_step=6,
+                 precision=None):
+        super().__init__()
+        self.input_dim = input_code_dim
+        self.in_channel = in_channel
+        self.tanh = tanh
+        self.pixel_norm = pixel_norm
+        self.precision = precision or _DEFAULT_PRECISION
+        c = in_channel
+        self.input_layer = nn.Sequential(EqualConvTranspose2d(input_code_dim, c, 4, 1, 0),
+                                         PixelNorm(), _LeakyMarker(0.2))
+        self.progression_4 = ConvBlock(c, c, 3, 1, pixel_norm=pixel_norm)
+        self.progression_8 = ConvBlock(c, c, 3, 1, pixel_norm=pixel_norm)
+        self.progression_16 = ConvBlock(c, c, 3, 1, pixel_norm=pixel_norm)
+        self.progression_32 = ConvBlock(c, c, 3, 1, pixel_norm=pixel_norm)
+        self.progression_64 = ConvBlock(c, c // 2, 3, 1, pixel_norm=pixel_norm)
+        self.progression_128 = ConvBlock(c // 2, c // 4, 3, 1, pixel_norm=pixel_norm)
+        self.progression_256 = ConvBlock(c // 4, c // 4, 3, 1, pixel_norm=pixel_norm)
+        self.to_rgb_8 = EqualConv2d(c, 3, 1)
+        self.to_rgb_16 = EqualConv2d(c, 3, 1)
+        self.to_rgb_32 = EqualConv2d(c, 3, 1)
+        self.to_rgb_64 = EqualConv2d(c // 2, 3, 1)
+        self.to_rgb_128 = EqualConv2d(c // 4, 3, 1)
+        self.to_rgb_256 = EqualConv2d(c // 4, 3, 1)
+        self.max_step = max_step
+
+    def _blocks(self):
+        return [self.progression_8, self.progression_16, self.progression_32,
+                self.progression_64, self.progression_128, self.progression_256]
+
+    def _heads(self):
+        return [self.to_rgb_8, self.to_rgb_16, self.to_rgb_32, self.to_rgb_64,
+                self.to_rgb_128, self.to_rgb_256]
+
+    def forward(self, input, step=0, alpha=-1):
+        if step > self.max_step:
+            step = self.max_step
+        if step < 1:
+            return None                      # reference falls through every `if` (:231-254)
+        dt = _act_dtype(self.precision)
+        fading = (not torch.is_tensor(alpha)) and 0 <= alpha < 1
+        if torch.is_tensor(alpha):
+            fading = True
+        z = input.reshape(-1, 1, 1, self.input_dim).to(dt).contiguous()
+        # input layer always applies PixelNorm (:181-184), independent of `pixel_norm`
+        feat = _fused_layer(z, self.input_layer[0], 0.2, True)
+        feat = self.progression_4(feat)
+        prev = None
+        blocks, heads = self._blocks(), self._heads()
+        for s in range(1, step + 1):
+            prev = feat
+            feat = blocks[s - 1](F_.upsample2(feat))
+        out = _to_rgb(feat, heads[step - 1], dt)
+        if step >= 2 and fading:
+            skip = F_.upsample2(_to_rgb(prev, heads[step - 2], dt), "nchw")
+            out = F_.Blend.apply(skip, out, self._alpha(alpha, out.device))
+        if self.tanh:
+            out = F_.Tanh.apply(out)
+        return out
+
+
+class Discriminator(nn.Module, _AlphaMixin):
+    def __init__(self, feat_dim=128, precision=None):
+        super().__init__()
+        self.feat_dim = feat_dim
+        self.precision = precision or _DEFAULT_PRECISION
+        f = feat_dim
+        self.progression = nn.ModuleList([ConvBlock(f // 4, f // 4, 3, 1),
+                                          ConvBlock(f // 4, f // 2, 3, 1),
+                                          ConvBlock(f // 2, f, 3, 1),
+                                          ConvBlock(f, f, 3, 1),
+                                          ConvBlock(f, f, 3, 1),
+                                          ConvBlock(f, f, 3, 1),
+                                          ConvBlock(f + 1, f, 3, 1, 4, 0)])
+        self.from_rgb = nn.ModuleList([EqualConv2d(3, f // 4, 1),
+                                       EqualConv2d(3, f // 4, 1),
+                                       EqualConv2d(3, f // 2, 1),
+                                       EqualConv2d(3, f, 1),
+                                       EqualConv2d(3, f, 1),
+                                       EqualConv2d(3, f, 1),
+                                       EqualConv2d(3, f, 1)])
+        self.n_layer = len(self.progression)
+        self.linear = EqualLinear(f, 1)
+
+    def forward(self, input, step=0, alpha=-1):
+        dt = _act_dtype(self.precision)
+        fading = torch.is_tensor(alpha) or (0 <= alpha < 1)
+        x = input.contiguous()
+        if x.dtype != _img_dtype(self.precision):
+            x = x.to(_img_dtype(self.precision))
+        out = None
+        for i in range(step, -1, -1):
+            index = self.n_layer - i - 1
+            if i == step:
+                out = _from_rgb(x, self.from_rgb[index], dt)
+            if i == 0:
+                out = F_.Mbstd.apply(out, out.shape[-1] + 1)
+            out = self.progression[index](out)
+            if i > 0:
+                out = F_.avgpool2(out)
+                if i == step and fading:
+                    skip = _from_rgb(F_.avgpool2(x, "nchw"), self.from_rgb[index + 1], dt)
+                    out = F_.Blend.apply(skip, out, self._alpha(alpha, out.device))
+        lin = self.linear.linear
+        C = out.shape[-1]
+        d = F_.PwFwd.apply(out, lin.weight_orig, lin.bias, "reduce", C, 1, 1, C, self.linear.scale, dt)
+        return d.view(-1, 1)

@@ -1,0 +1,76 @@
+"""Shared between make_golden.py (runs the REAL reference, only where /root/reference
+exists) and the tests (which never need the reference): seeded inputs and the compact
+summaries stored in the fixtures."""
+import os
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# name: (channel, z_dim, step, alpha, batch, tanh, pixel_norm)
+CASES = {
+    "s1_a1.0": (32, 32, 1, 1.0, 4, False, True),
+    "s1_a0.5": (32, 32, 1, 0.5, 4, False, True),
+    "s2_a0.5": (32, 32, 2, 0.5, 4, False, True),
+    "s2_a1.0_tanh": (32, 32, 2, 1.0, 4, True, True),
+    "s3_a0.25": (32, 32, 3, 0.25, 4, False, True),
+    "s3_a-1_nopn": (32, 32, 3, -1, 4, False, False),
+    "s5_a0.5": (32, 16, 5, 0.5, 2, False, True),
+}
+
+
+def model_shapes(channel, z_dim, pixel_norm):
+    """state-dict key -> shape, taken from the host mirror (identical to the reference's;
+    make_golden.py asserts that)."""
+    import progan_b200
+    G = progan_b200.Generator(input_code_dim=z_dim, in_channel=channel, pixel_norm=pixel_norm)
+    D = progan_b200.Discriminator(feat_dim=channel)
+    return ({k: tuple(v.shape) for k, v in G.state_dict().items()},
+            {k: tuple(v.shape) for k, v in D.state_dict().items()})
+
+
+def make_state(shapes, seed):
+    """weight_orig ~ N(0,1) (progan_modules.py:68), bias ~ 0.1*N(0,1) so bias paths are live."""
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for k in sorted(shapes):
+        t = torch.randn(shapes[k], generator=g)
+        out[k] = t * 0.1 if k.endswith("bias") else t
+    return out
+
+
+def make_inputs(name):
+    ch, zd, step, alpha, B, tanh, pn = CASES[name]
+    gs, ds = model_shapes(ch, zd, pn)
+    G_state, D_state = make_state(gs, 100), make_state(ds, 200)
+    g = torch.Generator().manual_seed(1234)
+    R = 4 * 2 ** step
+    real = torch.rand(B, 3, R, R, generator=g) * 2 - 1
+    z = torch.randn(B, zd, generator=g)
+    eps = torch.rand(B, 1, 1, 1, generator=g)
+    return dict(G=G_state, D=D_state, real=real, z=z, eps=eps, step=step, alpha=alpha,
+                tanh=tanh, pixel_norm=pn, channel=ch, z_dim=zd)
+
+
+def summarize(t, key):
+    """[l2 norm, sum, <t,p1>, <t,p2>] with projections seeded by the key."""
+    t = t.detach().double().flatten().cpu()
+    g = torch.Generator().manual_seed(abs(hash_str(key)) % (2 ** 31))
+    p1 = torch.randn(t.numel(), generator=g, dtype=torch.float64)
+    p2 = torch.randn(t.numel(), generator=g, dtype=torch.float64)
+    return torch.stack([t.norm(), t.sum(), t @ p1, t @ p2])
+
+
+def hash_str(s):
+    h = 0
+    for ch in s:
+        h = (h * 131 + ord(ch)) % 1000000007
+    return h
+
+
+def summarize_dict(d):
+    return {k: summarize(v, k) for k, v in d.items()}

@@ -1,0 +1,90 @@
+"""Host logic on CPU: the product's modules + autograd Function families, driven through
+the torch emulation of the kernels (tests/emul_kernels.py) in fp64, must reproduce the
+oracle (and hence the reference, see test_oracle_golden.py) to ~1e-9 — forward,
+first-order grads, and the WGAN-GP double backward with the hand-derived PixelNorm and
+minibatch-stddev second-order terms."""
+import pytest
+import torch
+
+import common
+import helpers
+import progan_b200
+from emul_kernels import EmulKernels
+from oracle import progan_oracle as O
+
+
+@pytest.fixture(autouse=True)
+def emul_backend():
+    prev = progan_b200.set_kernels(EmulKernels())
+    yield
+    progan_b200.set_kernels(prev)
+
+
+def _to64(d):
+    return {k: (v.double() if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in d.items()}
+
+
+@pytest.mark.parametrize("name", [n for n in common.CASES if not n.startswith("s5")])
+def test_train_step_matches_oracle_fp64(name):
+    inp = common.make_inputs(name)
+    step, alpha = inp["step"], inp["alpha"]
+    G, D = helpers.build_models(inp, "fp64", dtype=torch.float64)
+    real, z, eps = inp["real"].double(), inp["z"].double(), inp["eps"].double()
+    res, fake = helpers.product_train_step(G, D, real, z, eps, step, alpha)
+    gen_loss, g_grads = helpers.product_g_phase(G, D, fake, step, alpha)
+
+    PG, PD = O.params_of(_to64(inp["G"])), O.params_of(_to64(inp["D"]))
+    ref, rfake = O.train_step(PG, PD, real, z, eps, step, alpha, inp["tanh"], inp["pixel_norm"])
+    rloss, rg = O.g_phase(PG, PD, rfake, step, alpha)
+
+    tol = 1e-9
+    for k in ("real_predict", "fake", "hat_predict", "grad_x_hat", "grad_penalty", "disc_loss"):
+        assert helpers.rel(res[k], ref[k]) < tol, k
+    assert set(res["d_grads"]) == set(ref["d_grads"])
+    for k, v in ref["d_grads"].items():
+        assert helpers.rel(res["d_grads"][k], v) < 1e-8, k
+    assert helpers.rel(gen_loss, rloss) < tol
+    assert set(g_grads) == set(rg)
+    for k, v in rg.items():
+        assert helpers.rel(g_grads[k], v) < 1e-8, k
+
+
+def test_unfused_gp_chain_also_works():
+    """The reference script's own torch expression for the penalty (train.py:148-150) must
+    keep working on the product modules (drop-in)."""
+    inp = common.make_inputs("s2_a0.5")
+    G, D = helpers.build_models(inp, "fp64", dtype=torch.float64)
+    real, z, eps = inp["real"].double(), inp["z"].double(), inp["eps"].double()
+    a, _ = helpers.product_train_step(G, D, real, z, eps, 2, 0.5, fused_gp=True)
+    b, _ = helpers.product_train_step(G, D, real, z, eps, 2, 0.5, fused_gp=False)
+    assert helpers.rel(a["grad_penalty"], b["grad_penalty"]) < 1e-12
+    for k in a["d_grads"]:
+        assert helpers.rel(a["d_grads"][k], b["d_grads"][k]) < 1e-10, k
+
+
+def test_weight_grads_skipped_when_not_requested():
+    """autograd.grad(inputs=[x_hat]) must not run weight-gradient kernels (the reference's
+    ATen conv backward skips them through its output mask)."""
+    inp = common.make_inputs("s1_a1.0")
+    G, D = helpers.build_models(inp, "fp64", dtype=torch.float64)
+    x = inp["real"].double().requires_grad_(True)
+    K = progan_b200.get_kernels()
+    calls = []
+    orig = K.conv_wgrad
+    K.conv_wgrad = lambda *a, **k: (calls.append(1), orig(*a, **k))[1]
+    out = D(x, step=1, alpha=1.0)
+    torch.autograd.grad(out.sum(), x, create_graph=True)
+    assert not calls
+    out.sum().backward()
+    assert calls
+
+
+def test_generator_step0_returns_none_and_state_dict_keys():
+    G = progan_b200.Generator(input_code_dim=8, in_channel=32)
+    assert G(torch.zeros(2, 8), step=0) is None
+    keys = list(G.state_dict().keys())
+    assert keys[0] == "input_layer.0.conv.bias" and keys[1] == "input_layer.0.conv.weight_orig"
+    D = progan_b200.Discriminator(feat_dim=32)
+    assert "linear.linear.weight_orig" in D.state_dict()
+    assert D.state_dict()["progression.6.conv.0.conv.weight_orig"].shape == (32, 33, 3, 3)
+    assert D.state_dict()["progression.6.conv.3.conv.weight_orig"].shape == (32, 32, 4, 4)
