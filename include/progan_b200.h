@@ -84,11 +84,11 @@ int pg_conv_wgrad_simt(const void *x, const void *dy, float *dw, int N, int H,
 int pg_conv_tc(const void *x, const void *wp, const float *bias, void *y,
                float *r_out, int N, int H, int W, int Cin, int Cout, int taps,
                float scale, int epi, float slope, void *stream);
-/* weight gradient on tcgen05: dw fp32 [d0][d1][3][3] (zero-initialised by the
- * caller), accumulated with red.global.add.f32.                             */
-int pg_conv_wgrad_tc(const void *x, const void *dy, float *dw, int N, int H, int W,
-                     int Cin, int Cout, int taps, float scale, int swap_io,
-                     int flip, void *stream);
+/* weight gradient on tcgen05: dw fp32 [d0][d1][3][3] is overwritten; workspace is
+ * 9*Cin*Cout floats (partial sums reduced with coalesced red.global.add.f32). */
+int pg_conv_wgrad_tc(const void *x, const void *dy, float *dw, float *workspace, int N,
+                     int H, int W, int Cin, int Cout, int taps, float scale,
+                     int swap_io, int flip, void *stream);
 
 /* ---- PixelNorm + LeakyReLU derivatives: progan_modules.py:54-60,138 ------
  * y is the stored post-activation, r the stored per-pixel rsqrt.            */
@@ -164,6 +164,12 @@ int pg_gp_bwd(const float *g, const float *norms, const float *upstream, float *
 int pg_adam_step(float *p, const float *g, float *m, float *v, long long n, float lr,
                  float beta1, float beta2, float eps, const float *step_dev,
                  float grad_scale, void *stream);
+/* multi-tensor form: chunks is an int4 table {start, length, segment, 0} over the flat
+ * bucket, steps_dev[segment] the per-parameter-group step count (torch.optim.Adam keeps
+ * one step per parameter and skips parameters without a gradient).                  */
+int pg_adam_multi(float *p, const float *g, float *m, float *v, const void *chunks,
+                  int nchunks, const float *steps_dev, float lr, float beta1, float beta2,
+                  float eps, float grad_scale, void *stream);
 /* ema = decay*ema + (1-decay)*p   (accumulate(), train.py:17-22)              */
 int pg_ema(float *ema, const float *p, long long n, float decay, void *stream);
 

@@ -26,7 +26,7 @@ SIGNATURES = {
                            c_int, c_int, c_int, P],
     "pg_conv_tc": [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int,
                    c_float, P],
-    "pg_conv_wgrad_tc": [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int,
+    "pg_conv_wgrad_tc": [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int,
                          P],
     "pg_pn_lrelu_bwd": [P, P, P, P, c_ll, c_int, c_float, c_int, c_int, P],
     "pg_pn_lrelu_bwd_bwd": [P, P, P, P, P, P, c_ll, c_int, c_float, c_int, c_int, P],
@@ -50,6 +50,7 @@ SIGNATURES = {
     "pg_gp_fwd": [P, P, P, c_int, c_ll, c_float, P],
     "pg_gp_bwd": [P, P, P, P, c_int, c_ll, c_float, P],
     "pg_adam_step": [P, P, P, P, c_ll, c_float, c_float, c_float, c_float, P, c_float, P],
+    "pg_adam_multi": [P, P, P, P, P, c_int, P, c_float, c_float, c_float, c_float, c_float, P],
     "pg_ema": [P, P, c_ll, c_float, P],
 }
 

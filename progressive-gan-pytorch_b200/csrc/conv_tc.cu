@@ -1,0 +1,392 @@
+// 3x3 pad-1 (and 1x1) implicit-GEMM convolution on the 5th-gen tensor cores.
+//
+// Replaces aten::convolution (cuDNN fprop / dgrad) for the EqualConv2d 3x3 layers of
+// ConvBlock (reference progan_modules.py:63-73,120-148) and their data-gradients (the
+// data-gradient of a 3x3 pad-1 conv is the same conv with flipped/transposed weights, so
+// one kernel serves forward, dgrad and the GP tangent conv).  The equalized-LR scale
+// (:22-27), bias, PixelNorm (:54-60) and LeakyReLU(0.2) are fused into the epilogue.
+//
+// GEMM view: M = N*H*W output pixels (tile = 128 pixels = a bw x bh x bn spatial box),
+//            N = Cout (whole channel vector in one tile -> PixelNorm is thread-local),
+//            K = taps*Cin, walked as (tap, 64- or 32-channel block).
+// A tiles : TMA tiled-mode 4-D boxes over the NHWC activation, shifted by the tap offset;
+//           out-of-bounds coordinates are zero-filled by the TMA unit == conv padding.
+// B tiles : TMA 2-D boxes over the K-major packed weight matrix [Cout][taps*Cin].
+// MMA     : tcgen05.mma.cta_group::1.kind::f16, M=128, N=Cout, K=16, fp32 accumulators in
+//           TMEM, double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Roles   : warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+//           warps 4-7 = epilogue (tcgen05.ld -> scale/bias/PN/LReLU -> bf16 -> swizzled
+//           smem -> TMA store).  Persistent: grid = min(#tiles, #SMs).
+#include "tc_common.cuh"
+#include <mutex>
+
+namespace pg {
+
+PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) ==
+            cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  });
+  return fn;
+}
+
+int make_tmap_bf16(CUtensorMap *out, const void *base, int rank, const uint64_t *dims,
+                   const uint64_t *strides_bytes, const uint32_t *box, int swizzle_bytes,
+                   const char *what) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) {
+    set_error("%s: cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)", what);
+    return PG_ERR_CUDA;
+  }
+  cuuint64_t gdim[5], gstr[5];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+  }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  CUtensorMapSwizzle sw = swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                          : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, (void *)base, gdim,
+                   gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("%s: cuTensorMapEncodeTiled failed with CUresult %d", what, (int)r);
+    return PG_ERR_CUDA;
+  }
+  return PG_OK;
+}
+
+namespace tc {
+
+struct ConvTcParams {
+  int N, H, W, Cin, Cout, taps;
+  int bw, bh, bn;            // spatial box of one 128-pixel tile
+  int tiles_w, tiles_h, tiles_n, num_tiles;
+  int BK, kb_per_tap, num_kb;  // K block (channels) and counts
+  int stages;
+  int a_bytes, b_bytes;      // per-stage operand tile sizes
+  int out_chunk;             // channels per output TMA box (<=64)
+  int tmem_cols;             // allocated TMEM columns (2 accumulator stages)
+  int epi;
+  float scale, slope;
+  const float *bias;
+  float *r_out;
+};
+
+constexpr int kThreads = 256;
+constexpr int kEpiWarp0 = 4;
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+               const __grid_constant__ CUtensorMap tmap_y, const ConvTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve (base is 1024-aligned by the launch: dynamic smem starts aligned; enforce anyway)
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t stage_bytes = (uint32_t)(p.a_bytes + p.b_bytes);
+  const uint32_t smem_a0 = base;
+  const uint32_t smem_out = base + (uint32_t)p.stages * stage_bytes;
+  const uint32_t out_bytes = 128u * (uint32_t)p.Cout * 2u;
+  const uint32_t bar_base = smem_out + out_bytes;           // 8-byte aligned (multiple of 1024)
+  auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(p.stages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (uint32_t)(2 * p.stages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (uint32_t)(2 * p.stages + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (uint32_t)(2 * p.stages + 4);
+  const uint32_t bias_s = tmem_slot + 16u;
+  // generic pointers for plain smem accesses
+  uint8_t *gbase = smem_raw + (base - smem_u32(smem_raw));
+  volatile uint32_t *tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t *>(gbase + (tmem_slot - base));
+  float *bias_ptr = reinterpret_cast<float *>(gbase + (bias_s - base));
+  uint8_t *out_ptr = gbase + (smem_out - base);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_x);
+    prefetch_tmap(&tmap_w);
+    prefetch_tmap(&tmap_y);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  for (int c = threadIdx.x; c < p.Cout; c += kThreads) bias_ptr[c] = p.bias ? p.bias[c] : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int tw = tile % p.tiles_w;
+        const int th = (tile / p.tiles_w) % p.tiles_h;
+        const int tn = tile / (p.tiles_w * p.tiles_h);
+        const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          const int tap = kb / p.kb_per_tap;
+          const int cb = kb - tap * p.kb_per_tap;
+          int dh = 0, dw = 0;
+          if (p.taps == 9) {
+            dh = tap / 3 - 1;
+            dw = tap % 3 - 1;
+          }
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx(full_bar(stage), stage_bytes);
+          const uint32_t sa = smem_a0 + (uint32_t)stage * stage_bytes;
+          tma_load_4d(sa, &tmap_x, full_bar(stage), cb * p.BK, w0 + dw, h0 + dh, n0);
+          tma_load_2d(sa + (uint32_t)p.a_bytes, &tmap_w, full_bar(stage),
+                      tap * p.Cin + cb * p.BK, 0);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, p.Cout, 0, 0);
+      const uint32_t row_bytes = (uint32_t)p.BK * 2u;            // 128 or 64
+      const uint32_t layout = row_bytes == 128 ? 2u : 4u;         // SWIZZLE_128B / SWIZZLE_64B
+      const uint32_t sbo = 8u * row_bytes;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.Cout);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_a0 + (uint32_t)stage * stage_bytes;
+          const uint32_t sb = sa + (uint32_t)p.a_bytes;
+          const int nk = p.BK / 16;
+          for (int k = 0; k < nk; ++k) {
+            const uint64_t ad = make_smem_desc(sa + (uint32_t)k * 32u, 16u, sbo, layout);
+            const uint64_t bd = make_smem_desc(sb + (uint32_t)k * 32u, 16u, sbo, layout);
+            umma_bf16(d_tmem, ad, bd, idesc, (uint32_t)((kb | k) != 0));
+          }
+          umma_commit(empty_bar(stage));               // frees the smem slot when MMAs retire
+          if (kb == p.num_kb - 1) umma_commit(tfull_bar(acc));
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;                     // TMEM lane quadrant of this warp
+    const int row = q * 32 + lane;              // tile row == TMEM lane
+    const int et = threadIdx.x - kEpiWarp0 * 32;  // 0..127
+    const int chunk_rows_bytes = p.out_chunk * 2;  // 128 or 64
+    const int swz_bits = chunk_rows_bytes == 128 ? 3 : 2;
+    const int n_chunks = p.Cout / p.out_chunk;
+    const float invC = 1.f / (float)p.Cout;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int tw = tile % p.tiles_w;
+      const int th = (tile / p.tiles_w) % p.tiles_h;
+      const int tn = tile / (p.tiles_w * p.tiles_h);
+      const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.Cout);
+      float r = 1.f;
+      if (p.epi == PG_EPI_PN_LRELU) {
+        float ss = 0.f;
+        for (int c0 = 0; c0 < p.Cout; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(t_addr + (uint32_t)c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float a = __uint_as_float(v[j]) * p.scale + bias_ptr[c0 + j];
+            ss = fmaf(a, a, ss);
+          }
+        }
+        r = rsqrtf(ss * invC + 1e-8f);
+      }
+      // the previous tile's TMA store must have finished reading the staging buffer
+      if (et == 0) tma_store_wait_read0();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int c0 = 0; c0 < p.Cout; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(t_addr + (uint32_t)c0, v);
+        tmem_ld_wait();
+        uint32_t packed[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float a0 = (__uint_as_float(v[j]) * p.scale + bias_ptr[c0 + j]) * r;
+          float a1 = (__uint_as_float(v[j + 1]) * p.scale + bias_ptr[c0 + j + 1]) * r;
+          if (p.epi != PG_EPI_LINEAR) {
+            a0 = a0 > 0.f ? a0 : a0 * p.slope;
+            a1 = a1 > 0.f ? a1 : a1 * p.slope;
+          }
+          __nv_bfloat162 h = __floats2bfloat162_rn(a0, a1);
+          packed[j >> 1] = *reinterpret_cast<uint32_t *>(&h);
+        }
+        // 32 channels = 64 bytes = four 16-byte chunks of this row, swizzled like the TMA box
+        const int chunk = c0 / p.out_chunk;
+        const int cin_chunk = c0 - chunk * p.out_chunk;  // channel offset inside the chunk
+        uint8_t *tile_base = out_ptr + (size_t)chunk * 128 * chunk_rows_bytes;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t off = (uint32_t)row * (uint32_t)chunk_rows_bytes +
+                               (uint32_t)cin_chunk * 2u + (uint32_t)i * 16u;
+          *reinterpret_cast<uint4 *>(tile_base + swz(off, swz_bits)) =
+              make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+        }
+      }
+      // accumulator stage is drained: hand it back to the MMA warp
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+      if (p.epi == PG_EPI_PN_LRELU) {
+        const int wl = row % p.bw, hl = (row / p.bw) % p.bh, nl = row / (p.bw * p.bh);
+        const int w = w0 + wl, h = h0 + hl, n = n0 + nl;
+        if (w < p.W && h < p.H && n < p.N) p.r_out[((long long)n * p.H + h) * p.W + w] = r;
+      }
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et == 0) {
+        for (int ch = 0; ch < n_chunks; ++ch)
+          tma_store_4d(&tmap_y, smem_out + (uint32_t)ch * 128u * (uint32_t)chunk_rows_bytes,
+                       ch * p.out_chunk, w0, h0, n0);
+        tma_store_commit();
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1u;
+      }
+    }
+    if (et == 0) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+}  // namespace tc
+}  // namespace pg
+
+using namespace pg;
+
+static int pow2_ge(int v) {
+  int p = 32;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+extern "C" int pg_conv_tc(const void *x, const void *wp, const float *bias, void *y, float *r_out,
+                          int N, int H, int W, int Cin, int Cout, int taps, float scale, int epi,
+                          float slope, void *stream) {
+  PG_CHECK_ARG(x && wp && y, "pg_conv_tc: null pointer");
+  PG_CHECK_ARG(taps == 9 || taps == 1, "pg_conv_tc: taps must be 9 (3x3 pad 1) or 1");
+  PG_CHECK_ARG(N > 0 && H > 0 && W > 0, "pg_conv_tc: bad dims");
+  PG_CHECK_ARG(Cin % 32 == 0 && Cin > 0, "pg_conv_tc: Cin %% 32 != 0 (Cin=%d)", Cin);
+  PG_CHECK_ARG(Cout == 32 || Cout == 64 || Cout == 128 || Cout == 256,
+               "pg_conv_tc: Cout must be 32/64/128/256 (Cout=%d)", Cout);
+  PG_CHECK_ARG(epi != PG_EPI_PN_LRELU || r_out, "pg_conv_tc: PN epilogue needs r_out");
+  PG_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)wp & 15) == 0 && ((uintptr_t)y & 15) == 0,
+               "pg_conv_tc: pointers must be 16-byte aligned");
+  tc::ConvTcParams p;
+  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.taps = taps;
+  p.bw = W < 16 ? W : 16;
+  {
+    int rem = 128 / p.bw;
+    p.bh = H < rem ? H : rem;
+    p.bn = 128 / (p.bw * p.bh);
+  }
+  PG_CHECK_ARG(p.bw * p.bh * p.bn == 128 && p.bn <= 256,
+               "pg_conv_tc: cannot tile %dx%d into 128-pixel boxes", H, W);
+  p.tiles_w = (W + p.bw - 1) / p.bw;
+  p.tiles_h = (H + p.bh - 1) / p.bh;
+  p.tiles_n = (N + p.bn - 1) / p.bn;
+  p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  p.BK = (Cin % 64 == 0) ? 64 : 32;
+  p.kb_per_tap = Cin / p.BK;
+  p.num_kb = taps * p.kb_per_tap;
+  p.a_bytes = 128 * p.BK * 2;
+  p.b_bytes = Cout * p.BK * 2;
+  p.out_chunk = Cout < 64 ? Cout : 64;
+  p.tmem_cols = pow2_ge(2 * Cout);
+  p.epi = epi; p.scale = scale; p.slope = slope; p.bias = bias; p.r_out = r_out;
+  const int out_bytes = 128 * Cout * 2;
+  const int misc = 1024 /*align slack*/ + 8 * (2 * 8 + 4) + 16 + Cout * 4 + 64;
+  const int budget = 227 * 1024;
+  int stages = (budget - out_bytes - misc) / (p.a_bytes + p.b_bytes);
+  if (stages > 8) stages = 8;
+  PG_CHECK_ARG(stages >= 2, "pg_conv_tc: not enough shared memory for the pipeline");
+  p.stages = stages;
+  const size_t smem = (size_t)stages * (p.a_bytes + p.b_bytes) + out_bytes + misc;
+
+  CUtensorMap tx, tw_, ty;
+  {
+    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+    uint32_t box[4] = {(uint32_t)p.BK, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+    if (int rc = make_tmap_bf16(&tx, x, 4, dims, str, box, p.BK * 2, "pg_conv_tc(x)")) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)taps * Cin, (uint64_t)Cout};
+    uint64_t str[1] = {(uint64_t)taps * Cin * 2};
+    uint32_t box[2] = {(uint32_t)p.BK, (uint32_t)Cout};
+    if (int rc = make_tmap_bf16(&tw_, wp, 2, dims, str, box, p.BK * 2, "pg_conv_tc(w)")) return rc;
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    uint64_t str[3] = {(uint64_t)Cout * 2, (uint64_t)W * Cout * 2, (uint64_t)H * W * Cout * 2};
+    uint32_t box[4] = {(uint32_t)p.out_chunk, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+    if (int rc = make_tmap_bf16(&ty, y, 4, dims, str, box, p.out_chunk * 2, "pg_conv_tc(y)"))
+      return rc;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tc::conv_tc_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) {
+      set_error("pg_conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return PG_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+  tc::conv_tc_kernel<<<grid, tc::kThreads, smem, (cudaStream_t)stream>>>(tx, tw_, ty, p);
+  PG_CHECK_LAUNCH("pg_conv_tc");
+}

@@ -18,12 +18,14 @@ interp_xhat_kernel(const float *__restrict__ real, const float *__restrict__ fak
     const float4 r = reinterpret_cast<const float4 *>(real + n * D)[j];
     const float4 f = reinterpret_cast<const float4 *>(fake + n * D)[j];
     float4 o;
-    // same association as the reference expression eps*x + (1-eps)*G(z)
-    const float e1 = 1.f - e;
-    o.x = e * r.x + e1 * f.x;
-    o.y = e * r.y + e1 * f.y;
-    o.z = e * r.z + e1 * f.z;
-    o.w = e * r.w + e1 * f.w;
+    // same association and roundings as the reference expression eps*x + (1-eps)*G(z)
+    // (train.py:143): two rounded products and one rounded sum, no FMA contraction,
+    // so x_hat is bit-identical to torch's.
+    const float e1 = __fsub_rn(1.f, e);
+    o.x = __fadd_rn(__fmul_rn(e, r.x), __fmul_rn(e1, f.x));
+    o.y = __fadd_rn(__fmul_rn(e, r.y), __fmul_rn(e1, f.y));
+    o.z = __fadd_rn(__fmul_rn(e, r.z), __fmul_rn(e1, f.z));
+    o.w = __fadd_rn(__fmul_rn(e, r.w), __fmul_rn(e1, f.w));
     reinterpret_cast<float4 *>(out + n * D)[j] = o;
   }
 }
@@ -154,4 +156,46 @@ extern "C" int pg_ema(float *ema, const float *p, long long n, float decay, void
   PG_CHECK_ARG(ema && p && n > 0, "pg_ema: bad args");
   ema_kernel<<<bw_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(ema, p, n, decay);
   PG_CHECK_LAUNCH("pg_ema");
+}
+
+// ---- multi-tensor Adam over a flat bucket ------------------------------------------
+// torch.optim.Adam keeps one step counter per parameter and skips parameters whose grad is
+// None (inactive resolutions, SURVEY.md §7 "unused parameters per step").  The flat bucket
+// is cut into chunks; chunk c belongs to segment seg[c] (a group of parameters that became
+// active together) whose 1-based step count lives in steps_dev[seg] on the device.
+namespace pg {
+__global__ void __launch_bounds__(256)
+adam_multi_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
+                  float *__restrict__ v, const int4 *__restrict__ chunks,
+                  const float *__restrict__ steps_dev, float lr, float b1, float b2, float eps,
+                  float grad_scale) {
+  const int4 c = chunks[blockIdx.x];   // x = start, y = length, z = segment
+  const float t = steps_dev[c.z];
+  const float bc1 = 1.f - powf(b1, t);
+  const float bc2_sqrt = sqrtf(1.f - powf(b2, t));
+  const float step_size = lr / bc1;
+  for (int i = threadIdx.x; i < c.y; i += blockDim.x) {
+    const long long j = (long long)c.x + i;
+    const float gi = g[j] * grad_scale;
+    float mi = gi;
+    if (m) {
+      mi = b1 * m[j] + (1.f - b1) * gi;
+      m[j] = mi;
+    }
+    const float vi = b2 * v[j] + (1.f - b2) * gi * gi;
+    v[j] = vi;
+    p[j] = p[j] - step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+  }
+}
+}  // namespace pg
+
+extern "C" int pg_adam_multi(float *p, const float *g, float *m, float *v, const void *chunks,
+                             int nchunks, const float *steps_dev, float lr, float beta1,
+                             float beta2, float eps, float grad_scale, void *stream) {
+  PG_CHECK_ARG(p && g && v && chunks && steps_dev, "pg_adam_multi: null pointer");
+  PG_CHECK_ARG(m || beta1 == 0.f, "pg_adam_multi: beta1 != 0 needs a first-moment buffer");
+  PG_CHECK_ARG(nchunks > 0, "pg_adam_multi: nchunks must be > 0");
+  pg::adam_multi_kernel<<<nchunks, 256, 0, (cudaStream_t)stream>>>(
+      p, g, m, v, (const int4 *)chunks, steps_dev, lr, beta1, beta2, eps, grad_scale);
+  PG_CHECK_LAUNCH("pg_adam_multi");
 }

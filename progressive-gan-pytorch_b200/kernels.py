@@ -82,6 +82,7 @@ class CudaKernels:
     def __init__(self):
         self.lib = _lib.load()
         self.conv_impl = "tc"          # "tc": tcgen05 where the shape allows; "simt": always CUDA cores
+        self.wgrad_tc = False          # tcgen05 weight-gradient kernel (enabled once validated)
         self.launches = 0              # kernels launched through this shim (bench `gpu_launches`)
         self._packs = {}               # id(param) -> (weakref, version, {variant: tensor})
 
@@ -166,11 +167,14 @@ class CudaKernels:
         cout = dy.shape[-1]
         if cin != op.cin(wshape) or cout != op.cout(wshape):
             raise RuntimeError("progan_b200: wgrad shape mismatch")
-        dw = torch.zeros(tuple(wshape), device=x.device, dtype=torch.float32)
-        if self.tc_eligible(x, wshape, op):
-            self._call("pg_conv_wgrad_tc", x.data_ptr(), dy.data_ptr(), dw.data_ptr(), N, H, W, cin,
-                       cout, 9, float(scale), int(op.swap), int(op.flip), self._stream())
+        if self.wgrad_tc and self.tc_eligible(x, wshape, op) and cin <= 128:
+            dw = torch.empty(tuple(wshape), device=x.device, dtype=torch.float32)
+            ws = torch.empty(9 * cin * cout, device=x.device, dtype=torch.float32)
+            self._call("pg_conv_wgrad_tc", x.data_ptr(), dy.data_ptr(), dw.data_ptr(), ws.data_ptr(),
+                       N, H, W, cin, cout, 9, float(scale), int(op.swap), int(op.flip), self._stream())
+            self.launches += 2          # memset + unpack
         else:
+            dw = torch.zeros(tuple(wshape), device=x.device, dtype=torch.float32)
             self._call("pg_conv_wgrad_simt", x.data_ptr(), dy.data_ptr(), dw.data_ptr(), N, H, W,
                        cin, cout, op.k, op.pad, float(scale), int(op.swap), int(op.flip), _dt(x),
                        self._stream())
@@ -371,6 +375,14 @@ class CudaKernels:
         self._call("pg_adam_step", p.data_ptr(), g.data_ptr(), _ptr(m), v.data_ptr(), p.numel(),
                    float(lr), float(beta1), float(beta2), float(eps), step_dev.data_ptr(),
                    float(grad_scale), self._stream())
+
+    def adam_multi(self, p, g, m, v, chunks, steps_dev, lr, beta1, beta2, eps, grad_scale=1.0):
+        for t, n in ((p, "p"), (g, "g"), (v, "v"), (steps_dev, "steps")):
+            _chk(t, n, torch.float32)
+        _chk(chunks, "chunks", torch.int32, 2)
+        self._call("pg_adam_multi", p.data_ptr(), g.data_ptr(), _ptr(m), v.data_ptr(),
+                   chunks.data_ptr(), chunks.shape[0], steps_dev.data_ptr(), float(lr), float(beta1),
+                   float(beta2), float(eps), float(grad_scale), self._stream())
 
     def ema(self, ema, p, decay):
         _chk(ema, "ema", torch.float32)

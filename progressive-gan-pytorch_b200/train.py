@@ -1,0 +1,267 @@
+"""The training hot loop body of the reference (train.py:97-169) on the B200 kernels.
+
+`Trainer.step(real, z, eps, step, alpha)` performs exactly one iteration of the reference
+loop with n_critic = 1:
+
+    D.zero_grad; D(real) loss with 0.001 drift, backward          train.py:98,126-130
+    fake = G(z); D(fake.detach()).mean().backward                 train.py:133-139
+    x_hat = eps*real + (1-eps)*fake; grad(D(x_hat).sum(), x_hat, create_graph=True)
+    gp = 10*mean((||g||-1)^2); gp.backward                        train.py:142-151
+    d_optimizer.step()                                            train.py:155
+    G.zero_grad; loss = -D(fake).mean(); backward; g_optimizer.step(); EMA   :158-169
+
+What is different from the reference (all host-side, numerics unchanged):
+  * parameters / gradients / Adam state of each net live in ONE flat fp32 bucket, ordered so
+    the parameters that are live at a given (step, fading) form at most two contiguous
+    ranges; Adam is one multi-tensor launch per net, EMA one launch, zero_grad one memset;
+  * torch.optim.Adam semantics are kept per parameter group (own step counter, parameters
+    without gradient untouched — the reference relies on `grad is None` skipping);
+  * data parallel: one process per GPU, gradients of the live ranges are all-reduced (NCCL)
+    and averaged inside the Adam kernel (grad_scale = 1/world); minibatch-stddev stays
+    per-rank;
+  * losses are accumulated on the device (no .item() sync per iteration, train.py:152-165);
+  * the D weight-gradients of the G phase — which the reference computes and then throws
+    away (train.py:159-167) — are not computed: backward(inputs=G.parameters()).
+  * optionally the whole iteration is captured in a CUDA graph per (step, fading, batch).
+"""
+import torch
+import torch.distributed as dist
+
+from . import functions as F_
+from .kernels import get_kernels
+
+_CHUNK = 8192
+
+
+def _d_groups(D):
+    """(name, [params]) in flat-bucket order: trunk from the top of the network down, then
+    the from_rgb heads, so the live set at any step is a trunk prefix + adjacent heads."""
+    groups = [("linear", list(D.linear.parameters()))]
+    n = D.n_layer
+    for k in range(n - 1, -1, -1):
+        groups.append(("progression.%d" % k, list(D.progression[k].parameters())))
+    for k in range(n - 1, -1, -1):
+        groups.append(("from_rgb.%d" % k, list(D.from_rgb[k].parameters())))
+    return groups
+
+
+def _d_active(D, step, fading):
+    n = D.n_layer
+    names = ["linear"] + ["progression.%d" % k for k in range(n - 1, n - 2 - step, -1)]
+    names.append("from_rgb.%d" % (n - 1 - step))
+    if fading and step >= 1:
+        names.append("from_rgb.%d" % (n - step))
+    return names
+
+
+_G_RES = [8, 16, 32, 64, 128, 256]
+
+
+def _g_groups(G):
+    groups = [("input_layer", list(G.input_layer.parameters()) + list(G.progression_4.parameters()))]
+    for r in _G_RES:
+        groups.append(("progression_%d" % r, list(getattr(G, "progression_%d" % r).parameters())))
+    for r in _G_RES:
+        groups.append(("to_rgb_%d" % r, list(getattr(G, "to_rgb_%d" % r).parameters())))
+    return groups
+
+
+def _g_active(G, step, fading):
+    step = min(step, G.max_step)
+    names = ["input_layer"] + ["progression_%d" % r for r in _G_RES[:step]]
+    names.append("to_rgb_%d" % _G_RES[step - 1])
+    if fading and step >= 2:
+        names.append("to_rgb_%d" % _G_RES[step - 2])
+    return names
+
+
+class FlatBucket:
+    """Flat fp32 storage for the parameters, gradients and Adam state of one network."""
+
+    def __init__(self, groups, beta1):
+        self.group_params = {name: ps for name, ps in groups}
+        params = [p for _, ps in groups for p in ps]
+        dev = params[0].device
+        total = sum(p.numel() for p in params)
+        self.p = torch.empty(total, device=dev, dtype=torch.float32)
+        self.g = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.v = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.m = torch.zeros(total, device=dev, dtype=torch.float32) if beta1 != 0.0 else None
+        self.steps = torch.zeros(len(groups), device=dev, dtype=torch.float32)
+        self.group_index = {}
+        self.group_range = {}
+        off = 0
+        for gi, (name, ps) in enumerate(groups):
+            start = off
+            for p in ps:
+                n = p.numel()
+                self.p[off:off + n].copy_(p.detach().reshape(-1))
+                p.data = self.p[off:off + n].view(p.shape)
+                p.grad = self.g[off:off + n].view(p.shape)
+                off += n
+            self.group_index[name] = gi
+            self.group_range[name] = (start, off)
+        self._plans = {}
+
+    def plan(self, active_names):
+        """Per live-set: merged contiguous ranges (for all-reduce), the chunk table and the
+        step-increment mask (for multi-tensor Adam)."""
+        key = tuple(active_names)
+        pl = self._plans.get(key)
+        if pl is None:
+            dev = self.p.device
+            rs = sorted(self.group_range[n] for n in active_names)
+            merged = []
+            for a, b in rs:
+                if merged and merged[-1][1] == a:
+                    merged[-1][1] = b
+                else:
+                    merged.append([a, b])
+            chunks = []
+            for n in active_names:
+                a, b = self.group_range[n]
+                gi = self.group_index[n]
+                for s in range(a, b, _CHUNK):
+                    chunks.append((s, min(_CHUNK, b - s), gi, 0))
+            mask = torch.zeros(len(self.group_index), dtype=torch.float32)
+            for n in active_names:
+                mask[self.group_index[n]] = 1.0
+            pl = dict(params=[p for n in active_names for p in self.group_params[n]],
+                      ranges=[tuple(r) for r in merged],
+                      chunks=torch.tensor(chunks, dtype=torch.int32, device=dev),
+                      mask=mask.to(dev))
+            self._plans[key] = pl
+        return pl
+
+
+class Trainer:
+    def __init__(self, generator, discriminator, g_running=None, lr=1e-3, betas=(0.0, 0.99),
+                 eps=1e-8, ema_decay=0.999, gp_lambda=10.0, drift=0.001, process_group=None,
+                 use_graph=False):
+        self.G, self.D, self.G_run = generator, discriminator, g_running
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.ema_decay, self.gp_lambda, self.drift = ema_decay, gp_lambda, drift
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.use_graph = use_graph
+        self.bD = FlatBucket(_d_groups(discriminator), betas[0])
+        self.bG = FlatBucket(_g_groups(generator), betas[0])
+        self.bR = None
+        if g_running is not None:
+            self.bR = FlatBucket(_g_groups(g_running), 0.0)
+            for p in g_running.parameters():
+                p.requires_grad_(False)
+                p.grad = None
+        dev = self.bD.p.device
+        self.alpha_dev = torch.zeros((), device=dev, dtype=torch.float32)
+        self.metrics = {k: torch.zeros((), device=dev, dtype=torch.float32)
+                        for k in ("disc_loss", "grad_penalty", "gen_loss")}
+        self.iterations = 0
+        self._graphs = {}
+        self._g_params = list(generator.parameters())
+
+    # ------------------------------------------------------------------ pieces
+    def _allreduce(self, bucket, plan):
+        if self.world > 1:
+            for a, b in plan["ranges"]:
+                dist.all_reduce(bucket.g[a:b], group=self.pg)
+
+    def _adam(self, bucket, plan):
+        bucket.steps.add_(plan["mask"])
+        get_kernels().adam_multi(bucket.p, bucket.g, bucket.m, bucket.v, plan["chunks"], bucket.steps,
+                                 self.lr, self.betas[0], self.betas[1], self.eps, 1.0 / self.world)
+        get_kernels().invalidate_packs()
+
+    def _iteration(self, real, z, eps, step, alpha, fading):
+        """alpha: fp32 device scalar tensor when fading else the python number."""
+        K = get_kernels()
+        G, D = self.G, self.D
+        planD = self.bD.plan(_d_active(D, step, fading))
+        planG = self.bG.plan(_g_active(G, step, fading))
+        # ---- D phase
+        self.bD.g.zero_()
+        real_raw = D(real, step=step, alpha=alpha)
+        real_predict = real_raw.mean() - self.drift * (real_raw ** 2).mean()
+        (-real_predict).backward()
+        fake = G(z, step=step, alpha=alpha)
+        fake_predict = D(fake.detach(), step=step, alpha=alpha).mean()
+        fake_predict.backward()
+        x_hat = K.interp_xhat(real, fake.detach(), eps.reshape(-1)).requires_grad_(True)
+        hat = D(x_hat, step=step, alpha=alpha)
+        (g,) = torch.autograd.grad(outputs=hat.sum(), inputs=x_hat, create_graph=True)
+        gp = F_.gradient_penalty(g, self.gp_lambda)
+        gp.backward()
+        self._allreduce(self.bD, planD)
+        self._adam(self.bD, planD)
+        self.metrics["grad_penalty"].add_(gp.detach())
+        self.metrics["disc_loss"].add_((real_predict - fake_predict).detach())
+        # ---- G phase (D already updated, train.py:158-169)
+        self.bG.g.zero_()
+        loss = -D(fake, step=step, alpha=alpha).mean()
+        loss.backward(inputs=planG["params"])
+        self._allreduce(self.bG, planG)
+        self._adam(self.bG, planG)
+        if self.bR is not None:
+            K.ema(self.bR.p, self.bG.p, self.ema_decay)
+        self.metrics["gen_loss"].add_(loss.detach())
+
+    # ------------------------------------------------------------------ public
+    def step(self, real, z, eps, step, alpha):
+        """One full iteration on device-resident inputs: real [B,3,R,R] fp32, z [B,zdim],
+        eps [B,1,1,1] (drawn by the caller on the CPU generator, train.py:133,142)."""
+        fading = 0 <= alpha < 1
+        if fading:
+            self.alpha_dev.fill_(float(alpha))
+        a = self.alpha_dev if fading else alpha
+        if not self.use_graph:
+            self._iteration(real, z, eps, step, a, fading)
+        else:
+            self._graph_step(real, z, eps, step, a, fading)
+        self.iterations += 1
+
+    def _graph_step(self, real, z, eps, step, a, fading):
+        key = (step, fading, tuple(real.shape))
+        ent = self._graphs.get(key)
+        K = get_kernels()
+        if ent is None:
+            sreal, sz, seps = real.clone(), z.clone(), eps.clone()
+            # warm up on a side stream (allocator + lazy init), restoring state afterwards
+            state = [self.bD.p, self.bD.v, self.bD.steps, self.bG.p, self.bG.v, self.bG.steps]
+            state += [b.m for b in (self.bD, self.bG) if b.m is not None]
+            state += list(self.metrics.values())
+            snap = [b.clone() for b in state]
+            snapR = self.bR.p.clone() if self.bR is not None else None
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(2):
+                    K.invalidate_packs()
+                    self._iteration(sreal, sz, seps, step, a, fading)
+            torch.cuda.current_stream().wait_stream(s)
+            for dst, src in zip(state, snap):
+                dst.copy_(src)
+            if snapR is not None:
+                self.bR.p.copy_(snapR)
+            K.invalidate_packs()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._iteration(sreal, sz, seps, step, a, fading)
+            ent = (graph, sreal, sz, seps)
+            self._graphs[key] = ent
+            # the capture itself did not execute anything
+        graph, sreal, sz, seps = ent
+        sreal.copy_(real, non_blocking=True)
+        sz.copy_(z, non_blocking=True)
+        seps.copy_(eps, non_blocking=True)
+        graph.replay()
+        K.invalidate_packs()
+
+    def read_metrics(self, reset=True):
+        """One host sync for all three running sums (the reference syncs three times per
+        iteration with .item(), train.py:152,153,165)."""
+        vals = torch.stack(list(self.metrics.values())).tolist()
+        out = dict(zip(self.metrics.keys(), vals))
+        if reset:
+            for m in self.metrics.values():
+                m.zero_()
+        return out

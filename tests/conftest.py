@@ -9,6 +9,16 @@ for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golden
         sys.path.insert(0, p)
 
 
+@pytest.fixture(autouse=True)
+def _strict_fp32_references():
+    """torch's own convs/matmuls default to TF32 on GPU; every reference computed with torch
+    ops in these tests is true fp32."""
+    import torch
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 

@@ -41,7 +41,7 @@ class EmulKernels:
     def conv_fwd(self, x, w, bias, op, scale, epi=EPI_LINEAR, slope=0.2):
         self.launches += 1
         cd = torch.float64 if x.dtype == torch.float64 else torch.float32
-        wl = logical_weight(w, op).to(cd)
+        wl = logical_weight(w, op).to(x.dtype).to(cd)   # packed operands carry the activation dtype
         a = F.conv2d(_nchw(x).to(cd), wl, None, padding=op.pad) * scale
         if bias is not None:
             a = a + bias.to(cd).view(1, -1, 1, 1)
@@ -278,6 +278,14 @@ class EmulKernels:
         v.mul_(beta2).addcmul_(gi, gi, value=1 - beta2)
         denom = v.sqrt() / (1 - beta2 ** t) ** 0.5 + eps
         p.sub_(lr / (1 - beta1 ** t) * mi / denom)
+
+    def adam_multi(self, p, g, m, v, chunks, steps_dev, lr, beta1, beta2, eps, grad_scale=1.0):
+        self.launches += 1
+        for start, length, seg, _ in chunks.tolist():
+            sl = slice(start, start + length)
+            self.adam_step(p[sl], g[sl], None if m is None else m[sl], v[sl], lr, beta1, beta2, eps,
+                           steps_dev[seg], grad_scale)
+            self.launches -= 1
 
     def ema(self, ema, p, decay):
         self.launches += 1

@@ -1,0 +1,246 @@
+"""GPU unit tests: every C-ABI kernel against the torch specification of its semantics
+(tests/emul_kernels.py, running plain fp32 torch ops on the same device).
+Tolerances: fp32 kernels 1e-4 relative (l2), bf16 kernels 1e-2 (north_star)."""
+import pytest
+import torch
+
+import helpers
+import progan_b200
+from emul_kernels import EmulKernels
+from progan_b200.kernels import ConvOp, EPI_LINEAR, EPI_LRELU, EPI_PN_LRELU, CudaKernels
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def KE():
+    return CudaKernels(), EmulKernels()
+
+
+def tol(dtype):
+    return 1e-4 if dtype == torch.float32 else 1e-2
+
+
+def rnd(*shape, dtype=torch.float32, seed=0, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed + sum(shape))
+    return (torch.randn(*shape, generator=g) * scale).to(DEV).to(dtype).contiguous()
+
+
+DT = [torch.float32, torch.bfloat16]
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("cfg", [
+    # N, H, W, Cin, Cout, k, pad, swap, flip
+    (2, 8, 8, 32, 64, 3, 1, False, False),
+    (3, 4, 4, 33, 32, 3, 1, False, False),      # mbstd layer shape (C+1 input channels)
+    (4, 4, 4, 32, 32, 4, 0, False, False),      # D last conv 4x4 valid
+    (4, 1, 1, 16, 32, 4, 3, True, True),        # G input ConvTranspose 4x4 on 1x1
+    (2, 8, 8, 64, 32, 3, 1, True, True),        # data-gradient form
+])
+@pytest.mark.parametrize("epi", [EPI_LINEAR, EPI_PN_LRELU, EPI_LRELU])
+def test_conv_fwd_simt(KE, dtype, cfg, epi):
+    K, E = KE
+    K.conv_impl = "simt"
+    N, H, W, Cin, Cout, k, pad, swap, flip = cfg
+    op = ConvOp(k, pad, swap, flip)
+    x = rnd(N, H, W, Cin, dtype=dtype)
+    w = rnd(*((Cin, Cout, k, k) if swap else (Cout, Cin, k, k)), seed=1)
+    b = rnd(Cout, seed=2, scale=0.1)
+    scale = (2.0 / (Cin * k * k)) ** 0.5
+    y, r = K.conv_fwd(x, w, b, op, scale, epi, 0.2)
+    # spec sees the same rounded operands
+    wq = w.to(dtype).float() if dtype == torch.bfloat16 else w
+    ye, re_ = E.conv_fwd(x, wq, b, op, scale, epi, 0.2)
+    assert helpers.rel(y, ye) < tol(dtype)
+    if epi == EPI_PN_LRELU:
+        assert helpers.rel(r, re_) < 1e-4
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("cfg", [
+    (2, 8, 8, 32, 64, 3, 1, False, False),
+    (3, 4, 4, 33, 32, 3, 1, False, False),
+    (4, 4, 4, 32, 32, 4, 0, False, False),
+    (4, 1, 1, 16, 32, 4, 3, True, True),
+    (2, 16, 16, 64, 32, 3, 1, True, True),
+])
+def test_conv_wgrad_simt(KE, dtype, cfg):
+    K, E = KE
+    K.conv_impl = "simt"
+    N, H, W, Cin, Cout, k, pad, swap, flip = cfg
+    op = ConvOp(k, pad, swap, flip)
+    Ho = H + 2 * pad - k + 1
+    x = rnd(N, H, W, Cin, dtype=dtype)
+    dy = rnd(N, Ho, Ho, Cout, dtype=dtype, seed=3)
+    wshape = (Cin, Cout, k, k) if swap else (Cout, Cin, k, k)
+    dw = K.conv_wgrad(x, dy, wshape, op, 0.37)
+    dwe = E.conv_wgrad(x, dy, wshape, op, 0.37)
+    assert dw.shape == dwe.shape
+    assert helpers.rel(dw, dwe) < 1e-4
+
+
+@pytest.mark.parametrize("cfg", [
+    # N, H, W, Cin, Cout
+    (2, 16, 16, 64, 64), (1, 32, 32, 32, 64), (2, 16, 16, 128, 128), (4, 8, 8, 64, 128),
+    (16, 4, 4, 128, 128), (3, 4, 4, 64, 32), (1, 64, 64, 64, 32), (1, 32, 32, 32, 32),
+    (2, 32, 32, 128, 64), (5, 8, 8, 32, 128),
+])
+@pytest.mark.parametrize("epi", [EPI_LINEAR, EPI_PN_LRELU, EPI_LRELU])
+@pytest.mark.parametrize("flip", [False, True])
+def test_conv_tc_matches_spec(KE, cfg, epi, flip):
+    """tcgen05 implicit-GEMM conv vs the torch spec on identical bf16-rounded operands."""
+    K, E = KE
+    K.conv_impl = "tc"
+    N, H, W, Cin, Cout = cfg
+    op = ConvOp(3, 1, flip, flip)
+    x = rnd(N, H, W, Cin, dtype=torch.bfloat16)
+    w = rnd(*((Cin, Cout, 3, 3) if flip else (Cout, Cin, 3, 3)), seed=1)
+    b = rnd(Cout, seed=2, scale=0.1)
+    scale = (2.0 / (Cin * 9)) ** 0.5
+    assert K.tc_eligible(x, w.shape, op)
+    y, r = K.conv_fwd(x, w, b, op, scale, epi, 0.2)
+    ye, re_ = E.conv_fwd(x, w.to(torch.bfloat16).float(), b, op, scale, epi, 0.2)
+    torch.cuda.synchronize()
+    err = helpers.rel(y, ye)
+    assert err < 5e-3, "rel err %g" % err
+    if epi == EPI_PN_LRELU:
+        assert helpers.rel(r, re_) < 1e-4
+    K.conv_impl = "simt"
+
+
+@pytest.mark.parametrize("cfg", [
+    # N, H, W, Cin, Cout
+    (2, 16, 16, 64, 64), (1, 32, 32, 32, 64), (2, 16, 16, 128, 128), (4, 8, 8, 64, 128),
+    (16, 4, 4, 128, 128), (3, 4, 4, 64, 32), (1, 64, 64, 64, 32), (1, 32, 32, 32, 32),
+    (2, 32, 32, 128, 64), (5, 8, 8, 32, 128), (40, 16, 16, 128, 128),
+])
+@pytest.mark.parametrize("flip", [False, True])
+def test_conv_wgrad_tc_matches_spec(KE, cfg, flip):
+    """tcgen05 weight gradient (MN-major operands, TMEM-resident accumulators) vs the spec."""
+    K, E = KE
+    K.conv_impl, K.wgrad_tc = "tc", True
+    N, H, W, Cin, Cout = cfg
+    op = ConvOp(3, 1, flip, flip)
+    x = rnd(N, H, W, Cin, dtype=torch.bfloat16)
+    dy = rnd(N, H, W, Cout, dtype=torch.bfloat16, seed=3)
+    wshape = (Cin, Cout, 3, 3) if flip else (Cout, Cin, 3, 3)
+    dw = K.conv_wgrad(x, dy, wshape, op, 0.37)
+    dwe = E.conv_wgrad(x, dy, wshape, op, 0.37)
+    torch.cuda.synchronize()
+    err = helpers.rel(dw, dwe)
+    K.conv_impl = "simt"
+    assert err < 1e-3, "rel err %g" % err
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("C", [32, 64, 128, 512])
+@pytest.mark.parametrize("use_pn", [True, False])
+def test_pn_lrelu_grads(KE, dtype, C, use_pn):
+    K, E = KE
+    P = (3, 5, 7)
+    a = rnd(*P, C, seed=4)
+    r = torch.rsqrt((a * a).mean(-1) + 1e-8).contiguous()
+    y = torch.nn.functional.leaky_relu(a * r.unsqueeze(-1) if use_pn else a, 0.2).to(dtype)
+    dy, t = rnd(*P, C, dtype=dtype, seed=5), rnd(*P, C, dtype=dtype, seed=6)
+    da = K.pn_lrelu_bwd(dy, y, r, 0.2, use_pn)
+    assert helpers.rel(da, E.pn_lrelu_bwd(dy, y, r, 0.2, use_pn)) < tol(dtype)
+    c1, c2 = K.pn_lrelu_bwd_bwd(t, dy, y, r, 0.2, use_pn)
+    e1, e2 = E.pn_lrelu_bwd_bwd(t, dy, y, r, 0.2, use_pn)
+    assert helpers.rel(c1, e1) < tol(dtype)
+    if use_pn:
+        assert helpers.rel(c2, e2) < tol(dtype)
+    else:
+        assert float(c2.float().abs().max()) == 0.0
+    assert helpers.rel(K.colsum(dy), E.colsum(dy)) < 1e-4
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("Kc,C,HW", [(3, 32, (16, 16)), (3, 128, (8, 8)), (1, 128, (1, 1)), (4, 64, (4, 4))])
+@pytest.mark.parametrize("ck", [True, False])
+def test_pointwise_heads(KE, dtype, Kc, C, HW, ck):
+    K, E = KE
+    N = 5
+    w = rnd(C, Kc) if ck else rnd(Kc, C)
+    w_sc, w_sk = (Kc, 1) if ck else (1, C)
+    img = rnd(N, Kc, *HW, seed=7)
+    act = rnd(N, *HW, C, dtype=dtype, seed=8)
+    bc, bk = rnd(C, seed=9), rnd(Kc, seed=10)
+    assert helpers.rel(K.pw_expand(img, w, bc, C, w_sc, w_sk, 0.7, dtype),
+                       E.pw_expand(img, w, bc, C, w_sc, w_sk, 0.7, dtype)) < tol(dtype)
+    assert helpers.rel(K.pw_reduce(act, w, bk, Kc, w_sc, w_sk, 0.7),
+                       E.pw_reduce(act, w, bk, Kc, w_sc, w_sk, 0.7)) < 1e-4
+    assert helpers.rel(K.pw_wgrad(act, img, w.shape, w_sc, w_sk, 0.7),
+                       E.pw_wgrad(act, img, w.shape, w_sc, w_sk, 0.7)) < 1e-4
+    assert helpers.rel(K.img_chansum(img), E.img_chansum(img)) < 1e-4
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("shape,fmt", [((2, 8, 8, 32), "nhwc"), ((3, 4, 4, 129), "nhwc"),
+                                       ((2, 3, 16, 16), "nchw"), ((1, 32, 32, 64), "nhwc")])
+def test_resample(KE, dtype, shape, fmt):
+    K, E = KE
+    if fmt == "nchw" and dtype != torch.float32:
+        pytest.skip("images are fp32")
+    x = rnd(*shape, dtype=dtype, seed=11)
+    for name in ("avgpool2", "avgpool2_bwd", "upsample2", "upsample2_bwd"):
+        a, b = getattr(K, name)(x, fmt), getattr(E, name)(x, fmt)
+        assert a.shape == b.shape, name
+        assert helpers.rel(a, b) < tol(dtype), name
+    al = torch.tensor(0.3, device=DEV)
+    y = rnd(*shape, dtype=dtype, seed=12)
+    assert helpers.rel(K.blend(x, y, al), E.blend(x, y, al)) < tol(dtype)
+    assert helpers.rel(K.scale(x, 1.0, -1.0, al), E.scale(x, 1.0, -1.0, al)) < tol(dtype)
+    assert helpers.rel(K.scale(x, 0.5, 0.0, None), E.scale(x, 0.5, 0.0, None)) < tol(dtype)
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("N,C", [(4, 32), (64, 128), (7, 512)])
+def test_mbstd(KE, dtype, N, C):
+    K, E = KE
+    x = rnd(N, 4, 4, C, dtype=dtype, seed=13)
+    Cp = C + 1
+    o, oe = K.mbstd_fwd(x, Cp), E.mbstd_fwd(x, Cp)
+    assert helpers.rel(o, oe) < tol(dtype)
+    dout, t = rnd(N, 4, 4, Cp, dtype=dtype, seed=14), rnd(N, 4, 4, C, dtype=dtype, seed=15)
+    assert helpers.rel(K.mbstd_bwd(dout, x), E.mbstd_bwd(dout, x)) < tol(dtype)
+    a1, a2 = K.mbstd_bwd_bwd(t, dout, x)
+    b1, b2 = E.mbstd_bwd_bwd(t, dout, x)
+    assert helpers.rel(a1, b1) < tol(dtype)
+    assert helpers.rel(a2, b2) < (1e-3 if dtype == torch.float32 else 2e-2)
+
+
+def test_gp_and_optim(KE):
+    K, E = KE
+    N, D = 6, 3 * 16 * 16
+    real, fake = rnd(N, 3, 16, 16, seed=16), rnd(N, 3, 16, 16, seed=17)
+    eps = torch.rand(N, 1, 1, 1, device=DEV)
+    xh = K.interp_xhat(real, fake, eps)
+    assert torch.equal(xh, eps * real + (1 - eps) * fake)      # bit-exact eps indexing
+    g = rnd(N, 3, 16, 16, seed=18, scale=0.05)
+    gp, norms = K.gp_fwd(g, 10.0)
+    gpe, ne = E.gp_fwd(g, 10.0)
+    assert helpers.rel(gp, gpe) < 1e-5 and helpers.rel(norms, ne) < 1e-5
+    up = torch.tensor(0.7, device=DEV)
+    assert helpers.rel(K.gp_bwd(g, norms, up, 10.0), E.gp_bwd(g, ne, up, 10.0)) < 1e-5
+    # Adam (beta1 = 0) + EMA against torch.optim.Adam
+    p = torch.nn.Parameter(rnd(1000, seed=19))
+    opt = torch.optim.Adam([p], lr=1e-3, betas=(0.0, 0.99))
+    p2, v = p.detach().clone(), torch.zeros(1000, device=DEV)
+    step = torch.zeros((), device=DEV)
+    ema, ema_ref = p.detach().clone(), p.detach().clone()
+    for it in range(3):
+        grad = rnd(1000, seed=20 + it)
+        p.grad = grad.clone()
+        opt.step()
+        step += 1
+        K.adam_step(p2, grad, None, v, 1e-3, 0.0, 0.99, 1e-8, step)
+        K.ema(ema, p2, 0.999)
+        ema_ref.mul_(0.999).add_(p.detach(), alpha=0.001)
+    assert helpers.rel(p2, p) < 1e-6
+    assert helpers.rel(ema, ema_ref) < 1e-6
+    x = rnd(4, 3, 8, 8, seed=30)
+    y = K.tanh_fwd(x)
+    assert helpers.rel(y, torch.tanh(x)) < 1e-6
+    assert helpers.rel(K.tanh_bwd(x, y), x * (1 - y * y)) < 1e-6
