@@ -43,7 +43,8 @@ extern "C" {
 
 /* packed-weight layouts */
 #define PG_WL_TAP_CI_CO 0 /* [tap][ci][co]      — SIMT kernels                    */
-#define PG_WL_CO_TAP_CI 1 /* [co][tap][ci_pad]  — K-major rows for tcgen05        */
+#define PG_WL_CO_TAP_CI 1 /* [co][tap][ci]      — K-major rows for tcgen05        */
+#define PG_WL_TAP_CO_CI 2 /* [tap][co][ci]      — GEMM form of a full conv on 1x1 */
 
 const char *pg_last_error(void);
 int pg_abi_version(void);
@@ -57,8 +58,10 @@ int pg_device_info(int *sm_count, int *cc_major, int *cc_minor);
  * "logical" cross-correlation  y[co] = sum Wl[co][ci][tap] x[ci]:
  *   swap_io=0: co=d0, ci=d1 (nn.Conv2d OIHW)   swap_io=1: co=d1, ci=d0
  *   flip=1   : tap -> kh*kw-1-tap (data-gradient / ConvTranspose forms)     */
+/* ci_pad / co_pad >= logical Cin / Cout: extra rows/columns are zero-filled (activation
+ * tensors whose channel count is padded to a multiple of 32 for the tensor-core path). */
 int pg_pack_conv_weight(const float *w, void *out, int d0, int d1, int kh, int kw,
-                        int swap_io, int flip, int out_layout, int ci_pad,
+                        int swap_io, int flip, int out_layout, int ci_pad, int co_pad,
                         int out_dtype, void *stream);
 
 /* ---- generic kxk stride-1 conv, SIMT fp32-accumulate ----------------------
@@ -77,18 +80,26 @@ int pg_conv_wgrad_simt(const void *x, const void *dy, float *dw, int N, int H,
                        int W, int Cin, int Cout, int k, int pad, float scale,
                        int swap_io, int flip, int dtype, void *stream);
 
-/* ---- 3x3 pad-1 implicit-GEMM conv on tcgen05 (bf16 in, fp32 accumulate) ---
- * x:[N,H,W,Cin] bf16 (Cin % 32 == 0), wp: PG_WL_CO_TAP_CI bf16 with
- * ci_pad == Cin, y:[N,H,W,Cout] bf16 (Cout in {32,64,128,256}).  Same
- * epilogues as above.  taps==1 runs it as a 1x1 conv / plain GEMM.          */
+/* ---- implicit-GEMM conv on tcgen05 (bf16 in, fp32 accumulate) -------------
+ * x:[N,H,W,Cin] bf16 (Cin % 32 == 0), wp: K-major bf16 [Cout_total][taps*Cin],
+ * y:[N,H,W,Cout_total] bf16, tiled over N in tiles of Cout_tile (multiple of 32,
+ * <= 256).  taps == 9: 3x3 pad 1.  taps == 1: 1x1 conv / plain GEMM — the 4x4
+ * valid conv of D's last block (x viewed as [N,1,1,16*C]) and the 4x4
+ * ConvTranspose of G's input layer (y viewed as [N,1,1,16*C]) run through this
+ * form.  Same epilogues as the SIMT kernel; PixelNorm is taken over one N tile;
+ * bias[c % bias_mod]; r_out:[N*H*W*n_tiles].                                  */
 int pg_conv_tc(const void *x, const void *wp, const float *bias, void *y,
-               float *r_out, int N, int H, int W, int Cin, int Cout, int taps,
-               float scale, int epi, float slope, void *stream);
-/* weight gradient on tcgen05: dw fp32 [d0][d1][3][3] is overwritten; workspace is
- * 9*Cin*Cout floats (partial sums reduced with coalesced red.global.add.f32). */
+               float *r_out, int N, int H, int W, int Cin, int Cout_total,
+               int Cout_tile, int taps, int bias_mod, float scale, int epi,
+               float slope, void *stream);
+/* weight gradient on tcgen05: dw fp32 (logical dims Cin_log/Cout_log, parameter
+ * layout by swap_io/flip) is overwritten; workspace is taps*Cin*Cout floats.
+ * flat == 0: 3x3 pad 1 (taps == 9).  flat == 1: x is [N,1,1,taps*Cin] and tap t
+ * addresses channel block t (weight gradient of the GEMM forms above).        */
 int pg_conv_wgrad_tc(const void *x, const void *dy, float *dw, float *workspace, int N,
-                     int H, int W, int Cin, int Cout, int taps, float scale,
-                     int swap_io, int flip, void *stream);
+                     int H, int W, int Cin, int Cout, int Cin_log, int Cout_log,
+                     int taps, int flat, float scale, int swap_io, int flip,
+                     void *stream);
 
 /* ---- PixelNorm + LeakyReLU derivatives: progan_modules.py:54-60,138 ------
  * y is the stored post-activation, r the stored per-pixel rsqrt.            */

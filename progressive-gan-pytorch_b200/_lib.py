@@ -19,15 +19,15 @@ P = c_void_p
 SIGNATURES = {
     "pg_abi_version": [],
     "pg_device_info": [ctypes.POINTER(c_int)] * 3,
-    "pg_pack_conv_weight": [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P],
+    "pg_pack_conv_weight": [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P],
     "pg_conv_fwd_simt": [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
                          c_int, c_float, c_int, P],
     "pg_conv_wgrad_simt": [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
                            c_int, c_int, c_int, P],
-    "pg_conv_tc": [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int,
-                   c_float, P],
-    "pg_conv_wgrad_tc": [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int,
-                         P],
+    "pg_conv_tc": [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
+                   c_int, c_float, P],
+    "pg_conv_wgrad_tc": [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                         c_float, c_int, c_int, P],
     "pg_pn_lrelu_bwd": [P, P, P, P, c_ll, c_int, c_float, c_int, c_int, P],
     "pg_pn_lrelu_bwd_bwd": [P, P, P, P, P, P, c_ll, c_int, c_float, c_int, c_int, P],
     "pg_colsum": [P, P, c_ll, c_int, c_int, P],

@@ -11,24 +11,28 @@ namespace pg {
 template <typename T>
 __global__ void pack_weight_kernel(const float *__restrict__ w, T *__restrict__ out,
                                    int d0, int d1, int taps, int swap_io, int flip,
-                                   int layout, int ci_pad) {
+                                   int layout, int ci_pad, int co_pad) {
   const int Cout = swap_io ? d1 : d0;
   const int Cin = swap_io ? d0 : d1;
-  const long long total = (long long)Cout * taps * ci_pad;
+  const long long total = (long long)co_pad * taps * ci_pad;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     int co, ci, tap;
     if (layout == PG_WL_TAP_CI_CO) {
-      co = (int)(i % Cout);
-      ci = (int)((i / Cout) % ci_pad);
-      tap = (int)(i / ((long long)Cout * ci_pad));
-    } else {
+      co = (int)(i % co_pad);
+      ci = (int)((i / co_pad) % ci_pad);
+      tap = (int)(i / ((long long)co_pad * ci_pad));
+    } else if (layout == PG_WL_CO_TAP_CI) {
       ci = (int)(i % ci_pad);
       tap = (int)((i / ci_pad) % taps);
       co = (int)(i / ((long long)ci_pad * taps));
+    } else {  // PG_WL_TAP_CO_CI
+      ci = (int)(i % ci_pad);
+      co = (int)((i / ci_pad) % co_pad);
+      tap = (int)(i / ((long long)ci_pad * co_pad));
     }
     float v = 0.f;
-    if (ci < Cin) {
+    if (ci < Cin && co < Cout) {
       const int st = flip ? (taps - 1 - tap) : tap;
       const long long src = swap_io ? ((long long)ci * d1 + co) * taps + st
                                     : ((long long)co * d1 + ci) * taps + st;
@@ -131,20 +135,21 @@ __global__ void conv_wgrad_simt_kernel(const T *__restrict__ x, const T *__restr
 using namespace pg;
 
 extern "C" int pg_pack_conv_weight(const float *w, void *out, int d0, int d1, int kh, int kw,
-                                   int swap_io, int flip, int out_layout, int ci_pad,
+                                   int swap_io, int flip, int out_layout, int ci_pad, int co_pad,
                                    int out_dtype, void *stream) {
   const int Cin = swap_io ? d0 : d1;
   PG_CHECK_ARG(w && out, "pg_pack_conv_weight: null pointer");
   PG_CHECK_ARG(d0 > 0 && d1 > 0 && kh > 0 && kw > 0, "pg_pack_conv_weight: bad dims");
   PG_CHECK_ARG(ci_pad >= Cin, "pg_pack_conv_weight: ci_pad %d < Cin %d", ci_pad, Cin);
-  PG_CHECK_ARG(out_layout == PG_WL_TAP_CI_CO || out_layout == PG_WL_CO_TAP_CI,
+  PG_CHECK_ARG(out_layout >= PG_WL_TAP_CI_CO && out_layout <= PG_WL_TAP_CO_CI,
                "pg_pack_conv_weight: bad layout %d", out_layout);
   const int Cout = swap_io ? d1 : d0;
-  const long long total = (long long)Cout * kh * kw * ci_pad;
+  PG_CHECK_ARG(co_pad >= Cout, "pg_pack_conv_weight: co_pad %d < Cout %d", co_pad, Cout);
+  const long long total = (long long)co_pad * kh * kw * ci_pad;
   const int grid = bw_grid(total, 256);
   PG_DISPATCH_DTYPE(out_dtype, T,
                     pack_weight_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
-                        w, (T *)out, d0, d1, kh * kw, swap_io, flip, out_layout, ci_pad));
+                        w, (T *)out, d0, d1, kh * kw, swap_io, flip, out_layout, ci_pad, co_pad));
   PG_CHECK_LAUNCH("pg_pack_conv_weight");
 }
 

@@ -69,7 +69,8 @@ int make_tmap_bf16(CUtensorMap *out, const void *base, int rank, const uint64_t 
 namespace tc {
 
 struct ConvTcParams {
-  int N, H, W, Cin, Cout, taps;
+  int N, H, W, Cin, Cout, taps;   // Cout = channels of ONE N tile (<= 256)
+  int n_tiles;                    // N tiles (Cout_total / Cout); GEMM mode for wide outputs
   int bw, bh, bn;            // spatial box of one 128-pixel tile
   int tiles_w, tiles_h, tiles_n, num_tiles;
   int BK, kb_per_tap, num_kb;  // K block (channels) and counts
@@ -80,6 +81,7 @@ struct ConvTcParams {
   int epi;
   float scale, slope;
   const float *bias;
+  int bias_mod;              // bias[c % bias_mod]
   float *r_out;
 };
 
@@ -129,7 +131,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
-  for (int c = threadIdx.x; c < p.Cout; c += kThreads) bias_ptr[c] = p.bias ? p.bias[c] : 0.f;
+  for (int c = threadIdx.x; c < p.Cout; c += kThreads)
+    bias_ptr[c] = p.bias ? p.bias[c % p.bias_mod] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -141,9 +144,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int tw = tile % p.tiles_w;
-        const int th = (tile / p.tiles_w) % p.tiles_h;
-        const int tn = tile / (p.tiles_w * p.tiles_h);
+        const int nt = tile % p.n_tiles;          // N tile fastest: neighbours share the A tile in L2
+        const int pt = tile / p.n_tiles;
+        const int tw = pt % p.tiles_w;
+        const int th = (pt / p.tiles_w) % p.tiles_h;
+        const int tn = pt / (p.tiles_w * p.tiles_h);
         const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           const int tap = kb / p.kb_per_tap;
@@ -158,7 +163,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
           const uint32_t sa = smem_a0 + (uint32_t)stage * stage_bytes;
           tma_load_4d(sa, &tmap_x, full_bar(stage), cb * p.BK, w0 + dw, h0 + dh, n0);
           tma_load_2d(sa + (uint32_t)p.a_bytes, &tmap_w, full_bar(stage),
-                      tap * p.Cin + cb * p.BK, 0);
+                      tap * p.Cin + cb * p.BK, nt * p.Cout);
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;
@@ -180,7 +185,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.Cout);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * (p.tmem_cols / 2));
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
@@ -217,13 +222,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int tw = tile % p.tiles_w;
-      const int th = (tile / p.tiles_w) % p.tiles_h;
-      const int tn = tile / (p.tiles_w * p.tiles_h);
+      const int nt = tile % p.n_tiles;
+      const int pt = tile / p.n_tiles;
+      const int tw = pt % p.tiles_w;
+      const int th = (pt / p.tiles_w) % p.tiles_h;
+      const int tn = pt / (p.tiles_w * p.tiles_h);
       const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.Cout);
+      const uint32_t t_addr =
+          tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * (p.tmem_cols / 2));
       float r = 1.f;
       if (p.epi == PG_EPI_PN_LRELU) {
         float ss = 0.f;
@@ -276,14 +284,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       if (p.epi == PG_EPI_PN_LRELU) {
         const int wl = row % p.bw, hl = (row / p.bw) % p.bh, nl = row / (p.bw * p.bh);
         const int w = w0 + wl, h = h0 + hl, n = n0 + nl;
-        if (w < p.W && h < p.H && n < p.N) p.r_out[((long long)n * p.H + h) * p.W + w] = r;
+        if (w < p.W && h < p.H && n < p.N)
+          p.r_out[(((long long)n * p.H + h) * p.W + w) * p.n_tiles + nt] = r;
       }
       fence_proxy_async_smem();
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (et == 0) {
         for (int ch = 0; ch < n_chunks; ++ch)
           tma_store_4d(&tmap_y, smem_out + (uint32_t)ch * 128u * (uint32_t)chunk_rows_bytes,
-                       ch * p.out_chunk, w0, h0, n0);
+                       nt * p.Cout + ch * p.out_chunk, w0, h0, n0);
         tma_store_commit();
       }
       if (++acc == 2) {
@@ -314,19 +323,25 @@ static int pow2_ge(int v) {
 }
 
 extern "C" int pg_conv_tc(const void *x, const void *wp, const float *bias, void *y, float *r_out,
-                          int N, int H, int W, int Cin, int Cout, int taps, float scale, int epi,
-                          float slope, void *stream) {
+                          int N, int H, int W, int Cin, int Cout_total, int Cout_tile, int taps,
+                          int bias_mod, float scale, int epi, float slope, void *stream) {
   PG_CHECK_ARG(x && wp && y, "pg_conv_tc: null pointer");
   PG_CHECK_ARG(taps == 9 || taps == 1, "pg_conv_tc: taps must be 9 (3x3 pad 1) or 1");
   PG_CHECK_ARG(N > 0 && H > 0 && W > 0, "pg_conv_tc: bad dims");
   PG_CHECK_ARG(Cin % 32 == 0 && Cin > 0, "pg_conv_tc: Cin %% 32 != 0 (Cin=%d)", Cin);
-  PG_CHECK_ARG(Cout == 32 || Cout == 64 || Cout == 128 || Cout == 256,
-               "pg_conv_tc: Cout must be 32/64/128/256 (Cout=%d)", Cout);
+  const int Cout = Cout_tile;
+  PG_CHECK_ARG(Cout % 32 == 0 && Cout >= 32 && Cout <= 256,
+               "pg_conv_tc: N tile must be a multiple of 32 in [32,256] (%d)", Cout);
+  PG_CHECK_ARG(Cout_total % Cout == 0, "pg_conv_tc: Cout_total %d not a multiple of the tile %d",
+               Cout_total, Cout);
+  const int n_tiles = Cout_total / Cout;
+  PG_CHECK_ARG(!bias || (bias_mod > 0 && (n_tiles == 1 ? bias_mod == Cout : Cout % bias_mod == 0)),
+               "pg_conv_tc: bias_mod %d incompatible with the N tiling", bias_mod);
   PG_CHECK_ARG(epi != PG_EPI_PN_LRELU || r_out, "pg_conv_tc: PN epilogue needs r_out");
   PG_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)wp & 15) == 0 && ((uintptr_t)y & 15) == 0,
                "pg_conv_tc: pointers must be 16-byte aligned");
   tc::ConvTcParams p;
-  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.taps = taps;
+  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.taps = taps; p.n_tiles = n_tiles;
   p.bw = W < 16 ? W : 16;
   {
     int rem = 128 / p.bw;
@@ -338,15 +353,16 @@ extern "C" int pg_conv_tc(const void *x, const void *wp, const float *bias, void
   p.tiles_w = (W + p.bw - 1) / p.bw;
   p.tiles_h = (H + p.bh - 1) / p.bh;
   p.tiles_n = (N + p.bn - 1) / p.bn;
-  p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * n_tiles;
   p.BK = (Cin % 64 == 0) ? 64 : 32;
   p.kb_per_tap = Cin / p.BK;
   p.num_kb = taps * p.kb_per_tap;
   p.a_bytes = 128 * p.BK * 2;
   p.b_bytes = Cout * p.BK * 2;
-  p.out_chunk = Cout < 64 ? Cout : 64;
+  p.out_chunk = (Cout % 64 == 0) ? 64 : 32;
   p.tmem_cols = pow2_ge(2 * Cout);
-  p.epi = epi; p.scale = scale; p.slope = slope; p.bias = bias; p.r_out = r_out;
+  p.epi = epi; p.scale = scale; p.slope = slope; p.bias = bias; p.bias_mod = bias_mod > 0 ? bias_mod : 1;
+  p.r_out = r_out;
   const int out_bytes = 128 * Cout * 2;
   const int misc = 1024 /*align slack*/ + 8 * (2 * 8 + 4) + 16 + Cout * 4 + 64;
   const int budget = 227 * 1024;
@@ -364,14 +380,15 @@ extern "C" int pg_conv_tc(const void *x, const void *wp, const float *bias, void
     if (int rc = make_tmap_bf16(&tx, x, 4, dims, str, box, p.BK * 2, "pg_conv_tc(x)")) return rc;
   }
   {
-    uint64_t dims[2] = {(uint64_t)taps * Cin, (uint64_t)Cout};
+    uint64_t dims[2] = {(uint64_t)taps * Cin, (uint64_t)Cout_total};
     uint64_t str[1] = {(uint64_t)taps * Cin * 2};
     uint32_t box[2] = {(uint32_t)p.BK, (uint32_t)Cout};
     if (int rc = make_tmap_bf16(&tw_, wp, 2, dims, str, box, p.BK * 2, "pg_conv_tc(w)")) return rc;
   }
   {
-    uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-    uint64_t str[3] = {(uint64_t)Cout * 2, (uint64_t)W * Cout * 2, (uint64_t)H * W * Cout * 2};
+    uint64_t dims[4] = {(uint64_t)Cout_total, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    uint64_t str[3] = {(uint64_t)Cout_total * 2, (uint64_t)W * Cout_total * 2,
+                       (uint64_t)H * W * Cout_total * 2};
     uint32_t box[4] = {(uint32_t)p.out_chunk, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
     if (int rc = make_tmap_bf16(&ty, y, 4, dims, str, box, p.out_chunk * 2, "pg_conv_tc(y)"))
       return rc;

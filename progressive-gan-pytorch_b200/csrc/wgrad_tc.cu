@@ -23,7 +23,9 @@ namespace pg {
 namespace tc {
 
 struct WgradTcParams {
-  int N, H, W, Cin, Cout;
+  int N, H, W, Cin, Cout;      // physical channel counts of x (per tap) and dy
+  int taps, flat;              // flat: taps address channel blocks of x ([N,1,1,taps*Cin]), no shift
+  int group_stride;            // TMEM columns reserved per tap group (>= Cout)
   int bw, bh, bn, tiles_w, tiles_h, num_tiles;
   int atomM, atomN;            // channels per swizzle atom on the x / dy side (64 or 32)
   int n_atoms_m, n_atoms_n;    // atoms per 128-row x slot / per dy tile
@@ -32,7 +34,7 @@ struct WgradTcParams {
   int x_slots;                 // pipeline depth of the x ring
   int atom_m_bytes, atom_n_bytes;
   int tmem_cols;
-  float *dwp;                  // [9][Cout][Cin] fp32 partial-sum workspace (zeroed)
+  float *dwp;                  // [taps][Cout][Cin] fp32 partial-sum workspace (zeroed)
 };
 
 constexpr int kWgThreads = 256;
@@ -110,16 +112,19 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           int nvalid = 0;
           for (int a = 0; a < p.n_atoms_m; ++a) {
             const int tap = (g * p.n_atoms_m + a) / p.atoms_per_tap;
-            if (tap < 9) ++nvalid;
+            if (tap < p.taps) ++nvalid;
           }
           mbar_expect_tx(xfull(xs), (uint32_t)(nvalid * p.atom_m_bytes));
           for (int a = 0; a < p.n_atoms_m; ++a) {
             const int A = g * p.n_atoms_m + a;
             const int tap = A / p.atoms_per_tap;
-            if (tap >= 9) continue;             // dummy rows: smem left as is, lanes never read
+            if (tap >= p.taps) continue;        // dummy rows: smem left as is, lanes never read
             const int coff = (A - tap * p.atoms_per_tap) * p.atomM;
-            tma_load_4d(smem_x0 + (uint32_t)xs * slot_bytes + (uint32_t)(a * p.atom_m_bytes), &tmap_x,
-                        xfull(xs), coff, w0 + tap % 3 - 1, h0 + tap / 3 - 1, n0);
+            const uint32_t dst = smem_x0 + (uint32_t)xs * slot_bytes + (uint32_t)(a * p.atom_m_bytes);
+            if (p.flat)
+              tma_load_4d(dst, &tmap_x, xfull(xs), tap * p.Cin + coff, w0, h0, n0);
+            else
+              tma_load_4d(dst, &tmap_x, xfull(xs), coff, w0 + tap % 3 - 1, h0 + tap / 3 - 1, n0);
           }
           if (++xs == p.x_slots) {
             xs = 0;
@@ -145,7 +150,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           mbar_wait(xfull(xs), xphase);
           tc_fence_after();
           const uint32_t sa = smem_x0 + (uint32_t)xs * slot_bytes;
-          const uint32_t d_tmem = tmem_base + (uint32_t)(g * p.Cout);
+          const uint32_t d_tmem = tmem_base + (uint32_t)(g * p.group_stride);
 #pragma unroll
           for (int k = 0; k < 8; ++k) {          // 128 pixels = 8 x K16
             const uint64_t ad = make_smem_desc(sa + (uint32_t)k * 16u * rowA,
@@ -181,12 +186,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         const int A = (g0 + g) * p.n_atoms_m + m / p.atomM;
         const int tap = A / p.atoms_per_tap;
         const int ci = (A - tap * p.atoms_per_tap) * p.atomM + m % p.atomM;
-        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * p.Cout);
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * p.group_stride);
         for (int c0 = 0; c0 < p.Cout; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(t_addr + (uint32_t)c0, v);   // warp-collective: all lanes participate
           tmem_ld_wait();
-          if (tap < 9) {
+          if (tap < p.taps) {
             float *dst = p.dwp + ((size_t)tap * p.Cout + c0) * p.Cin + ci;
 #pragma unroll
             for (int j = 0; j < 32; ++j) atomicAdd(dst + (size_t)j * p.Cin, __uint_as_float(v[j]));
@@ -203,10 +208,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   }
 }
 
-// dw[param layout] = scale * dwp[tap][co][ci]
+// dw[param layout, logical dims] = scale * dwp[tap][co][ci] (physical, possibly padded dims)
 __global__ void __launch_bounds__(256)
 wgrad_unpack_kernel(const float *__restrict__ dwp, float *__restrict__ dw, int Cin, int Cout,
-                    int taps, float scale, int swap_io, int flip) {
+                    int Cin_p, int Cout_p, int taps, float scale, int swap_io, int flip) {
   const int total = Cin * Cout * taps;
   const int d1 = swap_io ? Cout : Cin;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -216,7 +221,7 @@ wgrad_unpack_kernel(const float *__restrict__ dwp, float *__restrict__ dw, int C
     const int i0 = i / (taps * d1);
     const int co = swap_io ? i1 : i0, ci = swap_io ? i0 : i1;
     const int tap = flip ? (taps - 1 - st) : st;
-    dw[i] = scale * dwp[((size_t)tap * Cout + co) * Cin + ci];
+    dw[i] = scale * dwp[((size_t)tap * Cout_p + co) * Cin_p + ci];
   }
 }
 
@@ -232,19 +237,23 @@ static int pow2_ge32(int v) {
 }
 
 extern "C" int pg_conv_wgrad_tc(const void *x, const void *dy, float *dw, float *workspace, int N,
-                                int H, int W, int Cin, int Cout, int taps, float scale,
-                                int swap_io, int flip, void *stream) {
+                                int H, int W, int Cin, int Cout, int Cin_log, int Cout_log,
+                                int taps, int flat, float scale, int swap_io, int flip,
+                                void *stream) {
   PG_CHECK_ARG(x && dy && dw && workspace, "pg_conv_wgrad_tc: null pointer");
-  PG_CHECK_ARG(taps == 9, "pg_conv_wgrad_tc: only 3x3 pad-1 (taps == 9)");
+  PG_CHECK_ARG(taps >= 1 && (flat || taps == 9), "pg_conv_wgrad_tc: 3x3 mode needs taps == 9");
   PG_CHECK_ARG(N > 0 && H > 0 && W > 0, "pg_conv_wgrad_tc: bad dims");
-  PG_CHECK_ARG(Cin == 32 || Cin == 64 || Cin == 128, "pg_conv_wgrad_tc: Cin must be 32/64/128 (%d)", Cin);
-  PG_CHECK_ARG(Cout == 32 || Cout == 64 || Cout == 128 || Cout == 256,
-               "pg_conv_wgrad_tc: Cout must be 32/64/128/256 (%d)", Cout);
+  PG_CHECK_ARG(!flat || (H == 1 && W == 1), "pg_conv_wgrad_tc: flat mode needs H == W == 1");
+  PG_CHECK_ARG(Cin % 32 == 0 && Cin >= 32, "pg_conv_wgrad_tc: Cin %% 32 != 0 (%d)", Cin);
+  PG_CHECK_ARG(Cout % 32 == 0 && Cout >= 32 && Cout <= 256,
+               "pg_conv_wgrad_tc: Cout must be a multiple of 32 in [32,256] (%d)", Cout);
+  PG_CHECK_ARG(Cin_log <= Cin && Cout_log <= Cout && Cin_log > 0 && Cout_log > 0,
+               "pg_conv_wgrad_tc: logical dims exceed physical dims");
   PG_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)dy & 15) == 0,
                "pg_conv_wgrad_tc: pointers must be 16-byte aligned");
   cudaStream_t s = (cudaStream_t)stream;
   tc::WgradTcParams p;
-  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
+  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.taps = taps; p.flat = flat;
   p.bw = W < 16 ? W : 16;
   {
     int rem = 128 / p.bw;
@@ -257,19 +266,20 @@ extern "C" int pg_conv_wgrad_tc(const void *x, const void *dy, float *dw, float 
   p.tiles_h = (H + p.bh - 1) / p.bh;
   const int tiles_n = (N + p.bn - 1) / p.bn;
   p.num_tiles = p.tiles_w * p.tiles_h * tiles_n;
-  p.atomM = Cin >= 64 ? 64 : 32;
-  p.atomN = Cout >= 64 ? 64 : 32;
+  p.atomM = (Cin % 64 == 0) ? 64 : 32;
+  p.atomN = (Cout % 64 == 0) ? 64 : 32;
   p.n_atoms_m = 128 / p.atomM;
   p.n_atoms_n = Cout / p.atomN;
   p.atoms_per_tap = Cin / p.atomM;
-  const int taps_per_group = 128 / Cin;                     // 4, 2 or 1
-  p.total_groups = (9 + taps_per_group - 1) / taps_per_group;
-  const int max_groups = 512 / Cout;
+  const int total_atoms = taps * p.atoms_per_tap;
+  p.total_groups = (total_atoms + p.n_atoms_m - 1) / p.n_atoms_m;
+  p.group_stride = (Cout & (Cout - 1)) == 0 ? Cout : ((Cout + 63) / 64) * 64;
+  const int max_groups = 512 / p.group_stride;
   const int passes = (p.total_groups + max_groups - 1) / max_groups;
   p.gpp = (p.total_groups + passes - 1) / passes;
   p.atom_m_bytes = 128 * p.atomM * 2;
   p.atom_n_bytes = 128 * p.atomN * 2;
-  p.tmem_cols = pow2_ge32(p.gpp * Cout);
+  p.tmem_cols = pow2_ge32(p.gpp * p.group_stride);
   p.dwp = workspace;
   const int slot_bytes = p.n_atoms_m * p.atom_m_bytes;
   const int dy_bytes = p.n_atoms_n * p.atom_n_bytes;
@@ -282,8 +292,9 @@ extern "C" int pg_conv_wgrad_tc(const void *x, const void *dy, float *dw, float 
 
   CUtensorMap tx, tdy;
   {
-    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-    uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+    const uint64_t cx = flat ? (uint64_t)taps * Cin : (uint64_t)Cin;
+    uint64_t dims[4] = {cx, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    uint64_t str[3] = {cx * 2, (uint64_t)W * cx * 2, (uint64_t)H * W * cx * 2};
     uint32_t box[4] = {(uint32_t)p.atomM, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
     if (int rc = make_tmap_bf16(&tx, x, 4, dims, str, box, p.atomM * 2, "pg_conv_wgrad_tc(x)")) return rc;
   }
@@ -303,7 +314,7 @@ extern "C" int pg_conv_wgrad_tc(const void *x, const void *dy, float *dw, float 
     }
     attr_set = true;
   }
-  cudaError_t e = cudaMemsetAsync(workspace, 0, (size_t)9 * Cin * Cout * sizeof(float), s);
+  cudaError_t e = cudaMemsetAsync(workspace, 0, (size_t)taps * Cin * Cout * sizeof(float), s);
   if (e != cudaSuccess) {
     set_error("pg_conv_wgrad_tc: cudaMemsetAsync: %s", cudaGetErrorString(e));
     return PG_ERR_CUDA;
@@ -313,8 +324,8 @@ extern "C" int pg_conv_wgrad_tc(const void *x, const void *dy, float *dw, float 
   if (gx < 1) gx = 1;
   dim3 grid(gx, passes);
   tc::wgrad_tc_kernel<<<grid, tc::kWgThreads, smem, s>>>(tx, tdy, p);
-  const int total = 9 * Cin * Cout;
-  tc::wgrad_unpack_kernel<<<(total + 255) / 256, 256, 0, s>>>(workspace, dw, Cin, Cout, 9, scale,
-                                                             swap_io, flip);
+  const int total = taps * Cin_log * Cout_log;
+  tc::wgrad_unpack_kernel<<<(total + 255) / 256, 256, 0, s>>>(workspace, dw, Cin_log, Cout_log, Cin,
+                                                             Cout, taps, scale, swap_io, flip);
   PG_CHECK_LAUNCH("pg_conv_wgrad_tc");
 }

@@ -17,7 +17,7 @@ import torch
 from . import _lib
 
 EPI_LINEAR, EPI_PN_LRELU, EPI_LRELU = 0, 1, 2
-WL_TAP_CI_CO, WL_CO_TAP_CI = 0, 1
+WL_TAP_CI_CO, WL_CO_TAP_CI, WL_TAP_CO_CI = 0, 1, 2
 
 _DT = {torch.float32: 0, torch.bfloat16: 1}
 
@@ -36,15 +36,23 @@ class ConvOp:
     pad: int
     swap: bool = False
     flip: bool = False
+    xpad: int = 0      # physical channel count of x when zero-padded beyond Cin (0 = not padded)
+    ypad: int = 0      # physical channel count of y when zero-padded beyond Cout
 
     def adjoint(self):
-        return ConvOp(self.k, self.k - 1 - self.pad, not self.swap, not self.flip)
+        return ConvOp(self.k, self.k - 1 - self.pad, not self.swap, not self.flip, self.ypad, self.xpad)
 
     def cout(self, wshape):
         return wshape[1] if self.swap else wshape[0]
 
     def cin(self, wshape):
         return wshape[0] if self.swap else wshape[1]
+
+    def cin_phys(self, wshape):
+        return self.xpad or self.cin(wshape)
+
+    def cout_phys(self, wshape):
+        return self.ypad or self.cout(wshape)
 
 
 def _dt(t):
@@ -97,21 +105,37 @@ class CudaKernels:
             _lib.check(rc, name)
         self.launches += 1
 
+    def tc_mode(self, dtype, H, W, wshape, op):
+        """Which tcgen05 form serves this conv: 'conv3' (3x3 pad 1 implicit GEMM), 'valid'
+        (kxk valid conv of a kxk map == GEMM with K = k*k*Cin), 'full' (kxk full conv of a 1x1
+        map == GEMM with N = k*k*Cout), or None (SIMT kernels)."""
+        if self.conv_impl != "tc" or dtype != torch.bfloat16:
+            return None
+        cin, cout = op.cin_phys(wshape), op.cout_phys(wshape)
+        if cin % 32 or cout % 32:
+            return None
+        if op.k == 3 and op.pad == 1 and cout <= 256:
+            return "conv3"
+        if op.xpad or op.ypad:
+            return None
+        if op.pad == 0 and H == op.k and W == op.k and cout <= 256:
+            return "valid"
+        if op.pad == op.k - 1 and H == 1 and W == 1 and cout <= 256 and cin <= 256:
+            return "full"
+        return None
+
     def tc_eligible(self, x, wshape, op):
-        if self.conv_impl != "tc" or x.dtype != torch.bfloat16:
-            return False
-        cin, cout = op.cin(wshape), op.cout(wshape)
-        return (op.k == 3 and op.pad == 1 and cin % 32 == 0 and cout in (32, 64, 128, 256)
-                and x.shape[-1] == cin)
+        return self.tc_mode(x.dtype, x.shape[1], x.shape[2], wshape, op) is not None
 
     # --------------------------------------------------------------- packing
     def invalidate_packs(self):
         self._packs.clear()
 
-    def packed(self, w, op, layout, dtype):
+    def packed(self, w, op, layout, dtype, flip=None):
         """Operand-layout copy of weight_orig for (op, layout, dtype); cached per parameter
         version (in-place optimizer updates bump Tensor._version)."""
-        key = (op.swap, op.flip, layout, dtype)
+        flip = op.flip if flip is None else flip
+        key = (op.swap, flip, layout, dtype, op.xpad, op.ypad)
         cacheable = isinstance(w, torch.nn.Parameter)
         if cacheable:
             ent = self._packs.get(id(w))
@@ -124,10 +148,10 @@ class CudaKernels:
                 self._packs[id(w)] = ent
         _chk(w, "weight", torch.float32, 4)
         d0, d1, kh, kw = w.shape
-        cout, cin = op.cout(w.shape), op.cin(w.shape)
+        cout, cin = op.cout_phys(w.shape), op.cin_phys(w.shape)
         out = torch.empty(cout * kh * kw * cin, device=w.device, dtype=dtype)
         self._call("pg_pack_conv_weight", w.data_ptr(), out.data_ptr(), d0, d1, kh, kw,
-                   int(op.swap), int(op.flip), layout, cin, _DT[dtype], self._stream())
+                   int(op.swap), int(flip), layout, cin, cout, _DT[dtype], self._stream())
         if cacheable:
             ent[2][key] = out
         return out
@@ -141,22 +165,34 @@ class CudaKernels:
         if bias is not None:
             _chk(bias, "bias", torch.float32, 1)
         N, H, W, C = x.shape
-        cin, cout = op.cin(w.shape), op.cout(w.shape)
-        if C != cin or w.shape[2] != op.k or w.shape[3] != op.k:
+        k = op.k
+        cin, cout = op.cin_phys(w.shape), op.cout_phys(w.shape)
+        if C != cin or w.shape[2] != k or w.shape[3] != k:
             raise RuntimeError("progan_b200: conv shape mismatch x=%s w=%s op=%s"
                                % (tuple(x.shape), tuple(w.shape), op))
-        Ho, Wo = H + 2 * op.pad - op.k + 1, W + 2 * op.pad - op.k + 1
+        Ho, Wo = H + 2 * op.pad - k + 1, W + 2 * op.pad - k + 1
         y = torch.empty((N, Ho, Wo, cout), device=x.device, dtype=x.dtype)
         r = torch.empty((N, Ho, Wo), device=x.device, dtype=torch.float32) if epi == EPI_PN_LRELU else None
-        if self.tc_eligible(x, w.shape, op):
+        mode = self.tc_mode(x.dtype, H, W, w.shape, op)
+        nb = bias.numel() if bias is not None else 0
+        st = self._stream()
+        if mode == "conv3":
             wp = self.packed(w, op, WL_CO_TAP_CI, torch.bfloat16)
             self._call("pg_conv_tc", x.data_ptr(), wp.data_ptr(), _ptr(bias), y.data_ptr(), _ptr(r),
-                       N, H, W, cin, cout, 9, float(scale), epi, float(slope), self._stream())
+                       N, H, W, cin, cout, cout, 9, nb, float(scale), epi, float(slope), st)
+        elif mode == "valid":      # [N, k*k*cin] x [cout, k*k*cin]^T
+            wp = self.packed(w, op, WL_CO_TAP_CI, torch.bfloat16)
+            self._call("pg_conv_tc", x.data_ptr(), wp.data_ptr(), _ptr(bias), y.data_ptr(), _ptr(r),
+                       N, 1, 1, k * k * cin, cout, cout, 1, nb, float(scale), epi, float(slope), st)
+        elif mode == "full":       # [N, cin] x [(pos, cout), cin]^T ; output position = flipped tap
+            wp = self.packed(w, op, WL_TAP_CO_CI, torch.bfloat16, flip=not op.flip)
+            self._call("pg_conv_tc", x.data_ptr(), wp.data_ptr(), _ptr(bias), y.data_ptr(), _ptr(r),
+                       N, 1, 1, cin, k * k * cout, cout, 1, nb, float(scale), epi, float(slope), st)
         else:
             wp = self.packed(w, op, WL_TAP_CI_CO, x.dtype)
             self._call("pg_conv_fwd_simt", x.data_ptr(), wp.data_ptr(), _ptr(bias), y.data_ptr(),
-                       _ptr(r), N, H, W, cin, cout, op.k, op.pad, float(scale), epi, float(slope),
-                       _dt(x), self._stream())
+                       _ptr(r), N, H, W, cin, cout, k, op.pad, float(scale), epi, float(slope),
+                       _dt(x), st)
         return y, r
 
     def conv_wgrad(self, x, dy, wshape, op, scale):
@@ -165,20 +201,42 @@ class CudaKernels:
         _chk(dy, "dy", x.dtype, 4)
         N, H, W, cin = x.shape
         cout = dy.shape[-1]
-        if cin != op.cin(wshape) or cout != op.cout(wshape):
+        k = op.k
+        if cin != op.cin_phys(wshape) or cout != op.cout_phys(wshape):
             raise RuntimeError("progan_b200: wgrad shape mismatch")
-        if self.wgrad_tc and self.tc_eligible(x, wshape, op) and cin <= 128:
+        cin_l, cout_l = op.cin(wshape), op.cout(wshape)
+        mode = self.tc_mode(x.dtype, H, W, wshape, op) if self.wgrad_tc else None
+        st = self._stream()
+        if mode is not None:
             dw = torch.empty(tuple(wshape), device=x.device, dtype=torch.float32)
-            ws = torch.empty(9 * cin * cout, device=x.device, dtype=torch.float32)
-            self._call("pg_conv_wgrad_tc", x.data_ptr(), dy.data_ptr(), dw.data_ptr(), ws.data_ptr(),
-                       N, H, W, cin, cout, 9, float(scale), int(op.swap), int(op.flip), self._stream())
+            ws = torch.empty(k * k * cin * cout, device=x.device, dtype=torch.float32)
+            if mode == "conv3":
+                self._call("pg_conv_wgrad_tc", x.data_ptr(), dy.data_ptr(), dw.data_ptr(), ws.data_ptr(),
+                           N, H, W, cin, cout, cin_l, cout_l, 9, 0, float(scale), int(op.swap),
+                           int(op.flip), st)
+            elif mode == "valid":
+                self._call("pg_conv_wgrad_tc", x.data_ptr(), dy.data_ptr(), dw.data_ptr(), ws.data_ptr(),
+                           N, 1, 1, cin, cout, cin, cout, k * k, 1, float(scale), int(op.swap),
+                           int(op.flip), st)
+            else:   # "full": the same quantity as the valid-form weight gradient of the adjoint op
+                self._call("pg_conv_wgrad_tc", dy.data_ptr(), x.data_ptr(), dw.data_ptr(), ws.data_ptr(),
+                           N, 1, 1, cout, cin, cout, cin, k * k, 1, float(scale), int(not op.swap),
+                           int(not op.flip), st)
             self.launches += 2          # memset + unpack
         else:
+            if op.xpad or op.ypad:
+                raise RuntimeError("progan_b200: padded channels are only used on the tcgen05 path")
             dw = torch.zeros(tuple(wshape), device=x.device, dtype=torch.float32)
             self._call("pg_conv_wgrad_simt", x.data_ptr(), dy.data_ptr(), dw.data_ptr(), N, H, W,
-                       cin, cout, op.k, op.pad, float(scale), int(op.swap), int(op.flip), _dt(x),
-                       self._stream())
+                       cin, cout, k, op.pad, float(scale), int(op.swap), int(op.flip), _dt(x), st)
         return dw
+
+    def mbstd_channels(self, C, dtype):
+        """Physical channel count of the minibatch-stddev output (C real + 1 statistic):
+        padded to a multiple of 32 on the tensor-core path."""
+        if self.conv_impl == "tc" and dtype == torch.bfloat16:
+            return ((C + 1 + 31) // 32) * 32
+        return C + 1
 
     # ------------------------------------------------- PixelNorm + LeakyReLU
     def pn_lrelu_bwd(self, dy, y, r, slope, use_pn):

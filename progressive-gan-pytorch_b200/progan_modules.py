@@ -93,7 +93,10 @@ class _LeakyMarker(nn.Module):
 
 def _fused_layer(x, conv, slope, use_pn):
     h = conv.conv
-    return F_.conv_act(x, h.weight_orig, h.bias, conv.op, conv.scale, slope, use_pn)
+    op = conv.op
+    if x.shape[-1] != conv.cin:       # zero-padded input channels (after minibatch-stddev)
+        op = ConvOp(op.k, op.pad, op.swap, op.flip, x.shape[-1], 0)
+    return F_.conv_act(x, h.weight_orig, h.bias, op, conv.scale, slope, use_pn)
 
 
 class ConvBlock(nn.Module):
@@ -242,7 +245,7 @@ class Discriminator(nn.Module, _AlphaMixin):
             if i == step:
                 out = _from_rgb(x, self.from_rgb[index], dt)
             if i == 0:
-                out = F_.Mbstd.apply(out, out.shape[-1] + 1)
+                out = F_.Mbstd.apply(out, F_.K().mbstd_channels(out.shape[-1], out.dtype))
             out = self.progression[index](out)
             if i > 0:
                 out = F_.avgpool2(out)

@@ -37,11 +37,15 @@ class EmulKernels:
     def invalidate_packs(self):
         pass
 
+    def mbstd_channels(self, C, dtype):
+        return C + 1
+
     # ---- conv
     def conv_fwd(self, x, w, bias, op, scale, epi=EPI_LINEAR, slope=0.2):
         self.launches += 1
         cd = torch.float64 if x.dtype == torch.float64 else torch.float32
         wl = logical_weight(w, op).to(x.dtype).to(cd)   # packed operands carry the activation dtype
+        x = x[..., :op.cin(w.shape)]                    # padded channels carry zero weights
         a = F.conv2d(_nchw(x).to(cd), wl, None, padding=op.pad) * scale
         if bias is not None:
             a = a + bias.to(cd).view(1, -1, 1, 1)
@@ -52,6 +56,8 @@ class EmulKernels:
         if epi != EPI_LINEAR:
             a = torch.where(a > 0, a, a * slope)
         y = _nhwc(a).to(x.dtype)
+        if op.ypad and op.ypad > y.shape[-1]:
+            y = F.pad(y, (0, op.ypad - y.shape[-1]))
         if r is not None:
             r = r.contiguous().to(torch.float64 if cd == torch.float64 else torch.float32)
         return y, r
@@ -60,6 +66,7 @@ class EmulKernels:
         self.launches += 1
         cd = torch.float64 if x.dtype == torch.float64 else torch.float32
         cout, cin = op.cout(wshape), op.cin(wshape)
+        x, dy = x[..., :cin], dy[..., :cout]
         dwl = torch.nn.grad.conv2d_weight(_nchw(x).to(cd), (cout, cin, op.k, op.k),
                                           _nchw(dy).to(cd), padding=op.pad) * scale
         if op.flip:

@@ -134,6 +134,53 @@ def test_conv_wgrad_tc_matches_spec(KE, cfg, flip):
     assert err < 1e-3, "rel err %g" % err
 
 
+GEMM_CASES = [
+    # name, N, H, W, wshape, op, xC (physical x channels), epi
+    ("valid_fwd", 64, 4, 4, (128, 128, 4, 4), ConvOp(4, 0), 128, EPI_PN_LRELU),
+    ("valid_fwd_small_batch", 6, 4, 4, (64, 32, 4, 4), ConvOp(4, 0), 32, EPI_LRELU),
+    ("valid_dgrad(full)", 64, 1, 1, (128, 128, 4, 4), ConvOp(4, 3, True, True), 128, EPI_LINEAR),
+    ("convT_fwd(full)", 64, 1, 1, (128, 128, 4, 4), ConvOp(4, 3, True, True), 128, EPI_PN_LRELU),
+    ("convT_fwd(full)_z64", 10, 1, 1, (64, 128, 4, 4), ConvOp(4, 3, True, True), 64, EPI_PN_LRELU),
+    ("convT_dgrad(valid)", 64, 4, 4, (128, 128, 4, 4), ConvOp(4, 0, False, False), 128, EPI_LINEAR),
+    ("mbstd_conv_padded", 64, 4, 4, (128, 129, 3, 3), ConvOp(3, 1, False, False, 160, 0), 160, EPI_PN_LRELU),
+    ("mbstd_conv_dgrad_padded", 64, 4, 4, (128, 129, 3, 3), ConvOp(3, 1, True, True, 0, 160), 128, EPI_LINEAR),
+    ("mbstd_conv_padded_c32", 5, 4, 4, (32, 33, 3, 3), ConvOp(3, 1, False, False, 64, 0), 64, EPI_PN_LRELU),
+]
+
+
+@pytest.mark.parametrize("case", GEMM_CASES, ids=[c[0] for c in GEMM_CASES])
+def test_tc_gemm_and_padded_forms(KE, case):
+    """The 4x4 valid conv / 4x4 ConvTranspose-on-1x1 GEMM forms and the channel-padded 3x3 conv
+    after minibatch-stddev, forward + weight gradient, vs the spec."""
+    K, E = KE
+    K.conv_impl, K.wgrad_tc = "tc", True
+    name, N, H, W, wshape, op, xC, epi = case
+    w = rnd(*wshape, seed=1)
+    cin_l, cout_l = op.cin(wshape), op.cout(wshape)
+    x = rnd(N, H, W, xC, dtype=torch.bfloat16)
+    if xC > cin_l:
+        x[..., cin_l:] = 0
+    b = rnd(cout_l, seed=2, scale=0.1) if epi != EPI_LINEAR else None
+    scale = (2.0 / (cin_l * op.k * op.k)) ** 0.5
+    mode = K.tc_mode(x.dtype, H, W, wshape, op)
+    assert mode is not None, "expected a tensor-core form"
+    y, r = K.conv_fwd(x, w, b, op, scale, epi, 0.2)
+    ye, re_ = E.conv_fwd(x, w, b, op, scale, epi, 0.2)
+    torch.cuda.synchronize()
+    assert y.shape == ye.shape
+    assert helpers.rel(y, ye) < 5e-3, (mode, helpers.rel(y, ye))
+    if epi == EPI_PN_LRELU:
+        assert helpers.rel(r, re_) < 1e-4
+    dy = rnd(*y.shape, dtype=torch.bfloat16, seed=3)
+    if op.ypad:
+        dy[..., cout_l:] = 0
+    dw = K.conv_wgrad(x, dy, wshape, op, 0.37)
+    dwe = E.conv_wgrad(x, dy, wshape, op, 0.37)
+    torch.cuda.synchronize()
+    K.conv_impl = "simt"
+    assert helpers.rel(dw, dwe) < 1e-3, (mode, helpers.rel(dw, dwe))
+
+
 @pytest.mark.parametrize("dtype", DT)
 @pytest.mark.parametrize("C", [32, 64, 128, 512])
 @pytest.mark.parametrize("use_pn", [True, False])
@@ -200,10 +247,11 @@ def test_resample(KE, dtype, shape, fmt):
 def test_mbstd(KE, dtype, N, C):
     K, E = KE
     x = rnd(N, 4, 4, C, dtype=dtype, seed=13)
-    Cp = C + 1
+    Cp = C + 1 if N != 64 else ((C + 1 + 31) // 32) * 32      # also the channel-padded form
     o, oe = K.mbstd_fwd(x, Cp), E.mbstd_fwd(x, Cp)
     assert helpers.rel(o, oe) < tol(dtype)
     dout, t = rnd(N, 4, 4, Cp, dtype=dtype, seed=14), rnd(N, 4, 4, C, dtype=dtype, seed=15)
+    dout[..., C + 1:] = 0
     assert helpers.rel(K.mbstd_bwd(dout, x), E.mbstd_bwd(dout, x)) < tol(dtype)
     a1, a2 = K.mbstd_bwd_bwd(t, dout, x)
     b1, b2 = E.mbstd_bwd_bwd(t, dout, x)
