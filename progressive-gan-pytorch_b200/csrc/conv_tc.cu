@@ -19,6 +19,7 @@
 //           smem -> TMA store).  Persistent: grid = min(#tiles, #SMs).
 #include "tc_common.cuh"
 #include <mutex>
+#include <stdlib.h>
 
 namespace pg {
 
@@ -173,41 +174,52 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, p.Cout, 0, 0);
-      const uint32_t row_bytes = (uint32_t)p.BK * 2u;            // 128 or 64
-      const uint32_t layout = row_bytes == 128 ? 2u : 4u;         // SWIZZLE_128B / SWIZZLE_64B
-      const uint32_t sbo = 8u * row_bytes;
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+    // warp-uniform loop; tcgen05 ops issued by the elected lane; precomputed descriptors
+    const uint32_t idesc = make_idesc_bf16(128, p.Cout, 0, 0);
+    const uint32_t row_bytes = (uint32_t)p.BK * 2u;            // 128 or 64
+    const uint32_t layout = row_bytes == 128 ? 2u : 4u;         // SWIZZLE_128B / SWIZZLE_64B
+    const uint32_t desc_hi = (((8u * row_bytes) >> 4) & 0x3FFFu) | (1u << 14) | (layout << 29);
+    const int nk = p.BK / 16;
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * (p.tmem_cols / 2));
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * (p.tmem_cols / 2));
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-          const uint32_t sa = smem_a0 + (uint32_t)stage * stage_bytes;
-          const uint32_t sb = sa + (uint32_t)p.a_bytes;
-          const int nk = p.BK / 16;
-          for (int k = 0; k < nk; ++k) {
-            const uint64_t ad = make_smem_desc(sa + (uint32_t)k * 32u, 16u, sbo, layout);
-            const uint64_t bd = make_smem_desc(sb + (uint32_t)k * 32u, 16u, sbo, layout);
-            umma_bf16(d_tmem, ad, bd, idesc, (uint32_t)((kb | k) != 0));
+        const uint32_t sa = smem_a0 + (uint32_t)stage * stage_bytes;
+        const uint32_t a_lo = (sa >> 4) | (1u << 16);
+        const uint32_t b_lo = ((sa + (uint32_t)p.a_bytes) >> 4) | (1u << 16);
+        if (elect_one_sync()) {
+          if (nk == 4) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(d_tmem, ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + 2u * k),
+                        ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + 2u * k), idesc,
+                        (uint32_t)((kb | k) != 0));
+          } else {
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+              umma_bf16(d_tmem, ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + 2u * k),
+                        ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + 2u * k), idesc,
+                        (uint32_t)((kb | k) != 0));
           }
           umma_commit(empty_bar(stage));               // frees the smem slot when MMAs retire
           if (kb == p.num_kb - 1) umma_commit(tfull_bar(acc));
-          if (++stage == p.stages) {
-            stage = 0;
-            phase ^= 1u;
-          }
         }
-        if (++acc == 2) {
-          acc = 0;
-          acc_phase ^= 1u;
+        __syncwarp();
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1u;
         }
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1u;
       }
     }
   } else if (warp >= kEpiWarp0) {
@@ -340,6 +352,11 @@ extern "C" int pg_conv_tc(const void *x, const void *wp, const float *bias, void
   PG_CHECK_ARG(epi != PG_EPI_PN_LRELU || r_out, "pg_conv_tc: PN epilogue needs r_out");
   PG_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)wp & 15) == 0 && ((uintptr_t)y & 15) == 0,
                "pg_conv_tc: pointers must be 16-byte aligned");
+  if (taps == 9 && n_tiles == 1) {   // second-generation kernel where the shape allows
+    const int rc = conv3_tc_launch(x, wp, bias, y, r_out, N, H, W, Cin, Cout, scale, epi, slope,
+                                   (cudaStream_t)stream);
+    if (rc != PG_ERR_UNSUPPORTED) return rc;
+  }
   tc::ConvTcParams p;
   p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.taps = taps; p.n_tiles = n_tiles;
   p.bw = W < 16 ? W : 16;
@@ -368,6 +385,10 @@ extern "C" int pg_conv_tc(const void *x, const void *wp, const float *bias, void
   const int budget = 227 * 1024;
   int stages = (budget - out_bytes - misc) / (p.a_bytes + p.b_bytes);
   if (stages > 8) stages = 8;
+  if (const char *e = getenv("PG_TC_STAGES")) {   // tuning/experiment knob
+    int v = atoi(e);
+    if (v >= 2 && v < stages) stages = v;
+  }
   PG_CHECK_ARG(stages >= 2, "pg_conv_tc: not enough shared memory for the pipeline");
   p.stages = stages;
   const size_t smem = (size_t)stages * (p.a_bytes + p.b_bytes) + out_bytes + misc;

@@ -11,6 +11,18 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
 
+// exactly one lane of a converged warp (ptxas treats the elected region as single-threaded,
+// which lets it issue uniform-datapath instructions such as UTCHMMA without election loops)
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred px;\n\t"
+      "elect.sync _|px, 0xFFFFFFFF;\n\t"
+      "@px mov.s32 %0, 1;\n\t}"
+      : "+r"(pred));
+  return pred != 0;
+}
+
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
@@ -135,6 +147,39 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
 }
+// generic: N consecutive fp32 columns (N = 16, 32 or 64) of this warp's 32 lanes
+template <int N>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t *v);
+template <>
+__device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, uint32_t *v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+template <>
+__device__ __forceinline__ void tmem_ld<32>(uint32_t taddr, uint32_t *v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
+        "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]),
+        "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+template <>
+__device__ __forceinline__ void tmem_ld<64>(uint32_t taddr, uint32_t *v) {
+  tmem_ld<32>(taddr, v);
+  tmem_ld<32>(taddr + 32u, v + 32);
+}
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -185,5 +230,10 @@ PFN_encodeTiled get_encode_tiled();
 int make_tmap_bf16(CUtensorMap *out, const void *base, int rank, const uint64_t *dims,
                    const uint64_t *strides_bytes, const uint32_t *box, int swizzle_bytes,
                    const char *what);
+
+// second-generation 3x3 kernel (conv3_tc.cu); PG_ERR_UNSUPPORTED when the shape is not eligible
+int conv3_tc_launch(const void *x, const void *wp, const float *bias, void *y, float *r_out, int N,
+                    int H, int W, int Cin, int Cout, float scale, int epi, float slope,
+                    cudaStream_t stream);
 
 }  // namespace pg

@@ -135,45 +135,52 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, p.Cout, 1, 1);   // both operands MN-major
-      const uint32_t rowA = (uint32_t)p.atomM * 2u, rowB = (uint32_t)p.atomN * 2u;
-      const uint32_t layA = rowA == 128 ? 2u : 4u, layB = rowB == 128 ? 2u : 4u;
-      int xs = 0, ds = 0;
-      uint32_t xphase = 0, dphase = 0;
-      bool first = true;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        mbar_wait(dyfull(ds), dphase);
+    // warp-uniform loop, tcgen05 ops issued by the elected lane, descriptors = constant high
+    // word + (start>>4) low word advanced by adds (see conv3_tc.cu).
+    const uint32_t idesc = make_idesc_bf16(128, p.Cout, 1, 1);   // both operands MN-major
+    const uint32_t rowA = (uint32_t)p.atomM * 2u, rowB = (uint32_t)p.atomN * 2u;
+    const uint32_t layA = rowA == 128 ? 2u : 4u, layB = rowB == 128 ? 2u : 4u;
+    const uint32_t hiA = (((8u * rowA) >> 4) & 0x3FFFu) | (1u << 14) | (layA << 29);
+    const uint32_t hiB = (((8u * rowB) >> 4) & 0x3FFFu) | (1u << 14) | (layB << 29);
+    const uint32_t lboA = (((uint32_t)p.atom_m_bytes >> 4) & 0x3FFFu) << 16;
+    const uint32_t lboB = (((uint32_t)p.atom_n_bytes >> 4) & 0x3FFFu) << 16;
+    const uint32_t stepA = (16u * rowA) >> 4, stepB = (16u * rowB) >> 4;   // one K16 step
+    int xs = 0, ds = 0;
+    uint32_t xphase = 0, dphase = 0;
+    uint32_t first = 1;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      mbar_wait(dyfull(ds), dphase);
+      tc_fence_after();
+      const uint32_t b_lo = ((smem_dy0 + (uint32_t)ds * dy_bytes) >> 4) | lboB;
+      for (int g = 0; g < ngroups; ++g) {
+        mbar_wait(xfull(xs), xphase);
         tc_fence_after();
-        const uint32_t sb = smem_dy0 + (uint32_t)ds * dy_bytes;
-        for (int g = 0; g < ngroups; ++g) {
-          mbar_wait(xfull(xs), xphase);
-          tc_fence_after();
-          const uint32_t sa = smem_x0 + (uint32_t)xs * slot_bytes;
-          const uint32_t d_tmem = tmem_base + (uint32_t)(g * p.group_stride);
+        const uint32_t a_lo = ((smem_x0 + (uint32_t)xs * slot_bytes) >> 4) | lboA;
+        const uint32_t d_tmem = tmem_base + (uint32_t)(g * p.group_stride);
+        if (elect_one_sync()) {
 #pragma unroll
           for (int k = 0; k < 8; ++k) {          // 128 pixels = 8 x K16
-            const uint64_t ad = make_smem_desc(sa + (uint32_t)k * 16u * rowA,
-                                               (uint32_t)p.atom_m_bytes, 8u * rowA, layA);
-            const uint64_t bd = make_smem_desc(sb + (uint32_t)k * 16u * rowB,
-                                               (uint32_t)p.atom_n_bytes, 8u * rowB, layB);
-            umma_bf16(d_tmem, ad, bd, idesc, (uint32_t)(!(first && k == 0)));
+            const uint64_t ad = ((uint64_t)hiA << 32) | (uint64_t)(a_lo + (uint32_t)k * stepA);
+            const uint64_t bd = ((uint64_t)hiB << 32) | (uint64_t)(b_lo + (uint32_t)k * stepB);
+            umma_bf16(d_tmem, ad, bd, idesc, k ? 1u : (first ^ 1u));
           }
           umma_commit(xempty(xs));
-          if (++xs == p.x_slots) {
-            xs = 0;
-            xphase ^= 1u;
-          }
+          if (g == ngroups - 1) umma_commit(dyempty(ds));
         }
-        umma_commit(dyempty(ds));
-        if (++ds == 2) {
-          ds = 0;
-          dphase ^= 1u;
+        __syncwarp();
+        if (++xs == p.x_slots) {
+          xs = 0;
+          xphase ^= 1u;
         }
-        first = false;
       }
-      umma_commit(done_bar);
+      if (++ds == 2) {
+        ds = 0;
+        dphase ^= 1u;
+      }
+      first = 0;
     }
+    if (elect_one_sync()) umma_commit(done_bar);
+    __syncwarp();
   } else if (warp >= 4) {
     // ===================== final reduction =====================
     const bool has_work = (int)blockIdx.x < p.num_tiles;

@@ -86,6 +86,9 @@ def test_conv_wgrad_simt(KE, dtype, cfg):
     (2, 16, 16, 64, 64), (1, 32, 32, 32, 64), (2, 16, 16, 128, 128), (4, 8, 8, 64, 128),
     (16, 4, 4, 128, 128), (3, 4, 4, 64, 32), (1, 64, 64, 64, 32), (1, 32, 32, 32, 32),
     (2, 32, 32, 128, 64), (5, 8, 8, 32, 128),
+    # second-generation kernel: resident weights / streamed weights with two tiles per unit
+    (3, 32, 32, 64, 64), (2, 64, 64, 32, 64), (2, 32, 32, 64, 128), (4, 32, 32, 128, 128),
+    (1, 64, 32, 64, 32), (3, 32, 64, 32, 32), (1, 32, 32, 128, 32),
 ])
 @pytest.mark.parametrize("epi", [EPI_LINEAR, EPI_PN_LRELU, EPI_LRELU])
 @pytest.mark.parametrize("flip", [False, True])
