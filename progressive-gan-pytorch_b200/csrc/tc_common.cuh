@@ -236,4 +236,8 @@ int conv3_tc_launch(const void *x, const void *wp, const float *bias, void *y, f
                     int H, int W, int Cin, int Cout, float scale, int epi, float slope,
                     cudaStream_t stream);
 
+// second-generation weight-gradient kernel (wgrad3_tc.cu); workspace pre-zeroed by the caller
+int wgrad3_tc_launch(const void *x, const void *dy, float *workspace, int N, int H, int W, int Cin,
+                     int Cout, cudaStream_t stream);
+
 }  // namespace pg

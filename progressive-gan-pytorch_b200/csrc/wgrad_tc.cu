@@ -326,11 +326,17 @@ extern "C" int pg_conv_wgrad_tc(const void *x, const void *dy, float *dw, float 
     set_error("pg_conv_wgrad_tc: cudaMemsetAsync: %s", cudaGetErrorString(e));
     return PG_ERR_CUDA;
   }
-  int gx = sm_count() / passes;
-  if (gx > p.num_tiles) gx = p.num_tiles;
-  if (gx < 1) gx = 1;
-  dim3 grid(gx, passes);
-  tc::wgrad_tc_kernel<<<grid, tc::kWgThreads, smem, s>>>(tx, tdy, p);
+  int rc2 = PG_ERR_UNSUPPORTED;
+  if (!flat && taps == 9)   // second-generation kernel where the shape allows
+    rc2 = wgrad3_tc_launch(x, dy, workspace, N, H, W, Cin, Cout, s);
+  if (rc2 != PG_OK && rc2 != PG_ERR_UNSUPPORTED) return rc2;
+  if (rc2 == PG_ERR_UNSUPPORTED) {
+    int gx = sm_count() / passes;
+    if (gx > p.num_tiles) gx = p.num_tiles;
+    if (gx < 1) gx = 1;
+    dim3 grid(gx, passes);
+    tc::wgrad_tc_kernel<<<grid, tc::kWgThreads, smem, s>>>(tx, tdy, p);
+  }
   const int total = taps * Cin_log * Cout_log;
   tc::wgrad_unpack_kernel<<<(total + 255) / 256, 256, 0, s>>>(workspace, dw, Cin_log, Cout_log, Cin,
                                                              Cout, taps, scale, swap_io, flip);

@@ -118,6 +118,10 @@ def test_conv_tc_matches_spec(KE, cfg, epi, flip):
     (2, 16, 16, 64, 64), (1, 32, 32, 32, 64), (2, 16, 16, 128, 128), (4, 8, 8, 64, 128),
     (16, 4, 4, 128, 128), (3, 4, 4, 64, 32), (1, 64, 64, 64, 32), (1, 32, 32, 32, 32),
     (2, 32, 32, 128, 64), (5, 8, 8, 32, 128), (40, 16, 16, 128, 128),
+    # second-generation (column-halo) kernel: every Cin/Cout atom configuration
+    (3, 32, 32, 64, 64), (2, 64, 64, 32, 64), (2, 32, 32, 64, 128), (4, 32, 32, 128, 128),
+    (1, 64, 32, 64, 32), (3, 32, 64, 32, 32), (1, 32, 32, 128, 32), (2, 32, 32, 32, 128),
+    (6, 32, 32, 128, 64),
 ])
 @pytest.mark.parametrize("flip", [False, True])
 def test_conv_wgrad_tc_matches_spec(KE, cfg, flip):
