@@ -95,22 +95,27 @@ int pg_conv_tc(const void *x, const void *wp, const float *bias, void *y,
 /* weight gradient on tcgen05: dw fp32 (logical dims Cin_log/Cout_log, parameter
  * layout by swap_io/flip) is overwritten; workspace is taps*Cin*Cout floats.
  * flat == 0: 3x3 pad 1 (taps == 9).  flat == 1: x is [N,1,1,taps*Cin] and tap t
- * addresses channel block t (weight gradient of the GEMM forms above).        */
+ * addresses channel block t (weight gradient of the GEMM forms above).
+ * accumulate != 0: dw += result (gradient accumulation straight into the flat bucket). */
 int pg_conv_wgrad_tc(const void *x, const void *dy, float *dw, float *workspace, int N,
                      int H, int W, int Cin, int Cout, int Cin_log, int Cout_log,
                      int taps, int flat, float scale, int swap_io, int flip,
-                     void *stream);
+                     int accumulate, void *stream);
 
 /* ---- PixelNorm + LeakyReLU derivatives: progan_modules.py:54-60,138 ------
  * y is the stored post-activation, r the stored per-pixel rsqrt.            */
+/* pool_h/pool_w != 0: dy is the gradient of the 2x2-average-pooled activation
+ * ([N,H/2,W/2,C]); the x1/4 expansion (avgpool backward) is fused.  colsum (nullable, fp32
+ * [C], zero-initialised) += per-channel sum of da = bias gradient of the conv in front. */
 int pg_pn_lrelu_bwd(const void *dy, const void *y, const float *r, void *da,
-                    long long P, int C, float slope, int use_pn, int dtype,
-                    void *stream);
+                    long long P, int C, float slope, int use_pn, int pool_h, int pool_w,
+                    float *colsum, int dtype, void *stream);
 /* second order (WGAN-GP, train.py:146-151): given t = cotangent of da,
  * cot_dy = M Jpn t ;  cot_a = d/da <t, Jpn(a) M dy>                          */
 int pg_pn_lrelu_bwd_bwd(const void *t, const void *dy, const void *y, const float *r,
                         void *cot_dy, void *cot_a, long long P, int C,
-                        float slope, int use_pn, int dtype, void *stream);
+                        float slope, int use_pn, int pool_h, int pool_w, int dtype,
+                        void *stream);
 /* column sum over pixels (bias gradient): out[C] fp32 (zero-initialised) +=  */
 int pg_colsum(const void *x, float *out, long long P, int C, int dtype, void *stream);
 
@@ -151,12 +156,15 @@ int pg_tanh_bwd(const float *dy, const float *y, float *dx, long long n, void *s
 /* ---- minibatch-stddev: progan_modules.py:289-293 ---------------------------
  * x:[N,F] (F = 16*C features of the 4x4 map, NHWC so feature f = pos*C + c),
  * out:[N,16,Cp] = x with channel C set to mean_f sigma_f and channels
- * C+1..Cp-1 zero.                                                            */
-int pg_mbstd_fwd(const void *x, void *out, int N, int C, int Cp, int dtype, void *stream);
-int pg_mbstd_bwd(const void *dout, const void *x, void *dx, int N, int C, int Cp,
-                 int dtype, void *stream);
-int pg_mbstd_bwd_bwd(const void *t, const void *dout, const void *x, void *cot_dout,
-                     void *cot_x, int N, int C, int Cp, int dtype, void *stream);
+ * C+1..Cp-1 zero.  stats: fp32 workspace of 4*F + 64 floats written by fwd
+ * (mu, sigma per feature) and reused by bwd / bwd_bwd.                        */
+int pg_mbstd_fwd(const void *x, void *out, float *stats, int N, int C, int Cp, int dtype,
+                 void *stream);
+int pg_mbstd_bwd(const void *dout, const void *x, const float *stats, void *dx, int N, int C,
+                 int Cp, int dtype, void *stream);
+int pg_mbstd_bwd_bwd(const void *t, const void *dout, const void *x, float *stats,
+                     void *cot_dout, void *cot_x, int N, int C, int Cp, int dtype,
+                     void *stream);
 
 /* ---- WGAN-GP pieces: train.py:142-150 ---------------------------------------*/
 /* x_hat = eps[n]*real + (1-eps[n])*fake  (all fp32 [N,D])                    */

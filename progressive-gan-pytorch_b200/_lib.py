@@ -27,9 +27,9 @@ SIGNATURES = {
     "pg_conv_tc": [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
                    c_int, c_float, P],
     "pg_conv_wgrad_tc": [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
-                         c_float, c_int, c_int, P],
-    "pg_pn_lrelu_bwd": [P, P, P, P, c_ll, c_int, c_float, c_int, c_int, P],
-    "pg_pn_lrelu_bwd_bwd": [P, P, P, P, P, P, c_ll, c_int, c_float, c_int, c_int, P],
+                         c_float, c_int, c_int, c_int, P],
+    "pg_pn_lrelu_bwd": [P, P, P, P, c_ll, c_int, c_float, c_int, c_int, c_int, P, c_int, P],
+    "pg_pn_lrelu_bwd_bwd": [P, P, P, P, P, P, c_ll, c_int, c_float, c_int, c_int, c_int, c_int, P],
     "pg_colsum": [P, P, c_ll, c_int, c_int, P],
     "pg_pw_expand": [P, P, P, P, c_int, c_ll, c_int, c_int, c_int, c_int, c_float, c_int, P],
     "pg_pw_reduce": [P, P, P, P, c_int, c_ll, c_int, c_int, c_int, c_int, c_float, c_int, P],
@@ -43,9 +43,9 @@ SIGNATURES = {
     "pg_scale": [P, P, c_ll, c_float, c_float, P, c_int, P],
     "pg_tanh_fwd": [P, P, c_ll, P],
     "pg_tanh_bwd": [P, P, P, c_ll, P],
-    "pg_mbstd_fwd": [P, P, c_int, c_int, c_int, c_int, P],
-    "pg_mbstd_bwd": [P, P, P, c_int, c_int, c_int, c_int, P],
-    "pg_mbstd_bwd_bwd": [P, P, P, P, P, c_int, c_int, c_int, c_int, P],
+    "pg_mbstd_fwd": [P, P, P, c_int, c_int, c_int, c_int, P],
+    "pg_mbstd_bwd": [P, P, P, P, c_int, c_int, c_int, c_int, P],
+    "pg_mbstd_bwd_bwd": [P, P, P, P, P, P, c_int, c_int, c_int, c_int, P],
     "pg_interp_xhat": [P, P, P, P, c_int, c_ll, P],
     "pg_gp_fwd": [P, P, P, c_int, c_ll, c_float, P],
     "pg_gp_bwd": [P, P, P, P, c_int, c_ll, c_float, P],

@@ -16,99 +16,170 @@ __device__ __forceinline__ float subwarp_sum(float v) {
   return v;
 }
 
-// MAXI = chunks of 8 channels per lane (C <= 8*TPP*MAXI)
-template <typename T, int TPP, int MAXI, bool SECOND>
+// MAXI = chunks of 8 channels per lane (C <= 8*TPP*MAXI); U = pixels per sub-warp per
+// iteration whose loads are all issued before any arithmetic (bytes in flight).
+// pool_w > 0: dy is the gradient of the 2x2-average-pooled activation ([N,H/2,W/2,C], the
+// reference's bilinear x0.5, progan_modules.py:299) and is expanded on the fly (x 1/4), which
+// fuses avgpool2_bwd into this kernel.  colsum != nullptr (first order only): the per-channel
+// sum of the produced da — the bias gradient of the conv in front — is accumulated too.
+template <typename T, int TPP, int MAXI, bool SECOND, int U>
 __global__ void __launch_bounds__(256)
 pn_lrelu_grad_kernel(const T *__restrict__ t_in, const T *__restrict__ dy,
                      const T *__restrict__ y, const float *__restrict__ rr,
                      T *__restrict__ out0, T *__restrict__ out1, long long P, int C,
-                     float slope, int use_pn) {
+                     float slope, int use_pn, int pool_h, int pool_w,
+                     float *__restrict__ colsum) {
   // first order : out0 = da                 (t_in unused)
   // second order: out0 = cot_dy, out1 = cot_a
+  using Raw = typename RawOf<T>::type;
   const int sub = threadIdx.x % TPP;
   const long long ppb = blockDim.x / TPP;
   const int nch = C >> 3;
   const float invC = 1.f / (float)C;
   const float inv_slope = 1.f / slope;
-  for (long long pix = blockIdx.x * ppb + threadIdx.x / TPP;
-       pix < ((P + ppb - 1) / ppb) * ppb; pix += (long long)gridDim.x * ppb) {
-    const bool live = pix < P;
-    F8 pv[MAXI], uv[MAXI], tv[MAXI];
-    float mk[MAXI][8];
-    float s_pu = 0.f, s_pt = 0.f, s_tu = 0.f;
+  const long long stride = (long long)gridDim.x * ppb;
+  float csum[MAXI][8];
 #pragma unroll
-    for (int i = 0; i < MAXI; ++i) {
-      const int ch = sub + i * TPP;
-      if (live && ch < nch) {
-        const long long off = pix * C + (long long)ch * 8;
-        F8 yv = ld8(y + off);
-        F8 dv = ld8(dy + off);
-        if (SECOND) tv[i] = ld8(t_in + off);
+  for (int i = 0; i < MAXI; ++i)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const bool pos = yv.v[e] > 0.f;
-          const float m = pos ? 1.f : slope;
-          const float p = pos ? yv.v[e] : yv.v[e] * inv_slope;
-          mk[i][e] = m;
-          pv[i].v[e] = p;
-          uv[i].v[e] = m * dv.v[e];
-          s_pu += p * uv[i].v[e];
-          if (SECOND) {
-            s_pt += p * tv[i].v[e];
-            s_tu += tv[i].v[e] * uv[i].v[e];
+    for (int e = 0; e < 8; ++e) csum[i][e] = 0.f;
+  const long long Pr = ((P + ppb - 1) / ppb) * ppb;
+  for (long long pix0 = blockIdx.x * ppb + threadIdx.x / TPP; pix0 < Pr; pix0 += stride * U) {
+    Raw ry[U][MAXI], rd[U][MAXI], rt[U][MAXI];
+    float rv[U];
+    // ---- phase 1: issue every load of the U pixels
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long pix = pix0 + u * stride;
+      const bool live = pix < P;
+      rv[u] = 1.f;
+#pragma unroll
+      for (int i = 0; i < MAXI; ++i) {
+        const int ch = sub + i * TPP;
+        if (live && ch < nch) {
+          const long long off = pix * C + (long long)ch * 8;
+          ry[u][i] = ldraw8(y + off);
+          if (pool_w > 0) {
+            const unsigned upix = (unsigned)pix;
+            const unsigned lw = (unsigned)pool_w >> 16, lh = (unsigned)pool_h >> 16;
+            const unsigned W_ = (unsigned)pool_w & 0xFFFFu, H_ = (unsigned)pool_h & 0xFFFFu;
+            unsigned wq, hq, nq;
+            if (lw) { wq = upix & (W_ - 1); hq = (upix >> (lw - 1)) & (H_ - 1); nq = upix >> (lw + lh - 2); }
+            else { wq = upix % W_; hq = (upix / W_) % H_; nq = upix / (W_ * H_); }
+            const long long pp = ((long long)nq * (H_ >> 1) + (hq >> 1)) * (W_ >> 1) + (wq >> 1);
+            rd[u][i] = ldraw8(dy + pp * C + (long long)ch * 8);
+          } else {
+            rd[u][i] = ldraw8(dy + off);
           }
+          if (SECOND) rt[u][i] = ldraw8(t_in + off);
         }
       }
+      if (use_pn && live) rv[u] = rr[pix];
     }
-    float r = 1.f;
-    if (use_pn) {
-      s_pu = subwarp_sum<TPP>(s_pu);
-      if (SECOND) {
-        s_pt = subwarp_sum<TPP>(s_pt);
-        s_tu = subwarp_sum<TPP>(s_tu);
-      }
-      if (live) r = rr[pix];
-    }
+    // ---- phase 2: arithmetic + stores, one pixel at a time
 #pragma unroll
-    for (int i = 0; i < MAXI; ++i) {
-      const int ch = sub + i * TPP;
-      if (live && ch < nch) {
-        const long long off = pix * C + (long long)ch * 8;
-        F8 o0, o1;
+    for (int u = 0; u < U; ++u) {
+      const long long pix = pix0 + u * stride;
+      const bool live = pix < P;
+      const float dscale = pool_w > 0 ? 0.25f : 1.f;
+      F8 pv[MAXI], uv[MAXI], tv[MAXI];
+      float mk[MAXI][8];
+      float s_pu = 0.f, s_pt = 0.f, s_tu = 0.f;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float p = pv[i].v[e], u = uv[i].v[e];
-          if (!SECOND) {
-            o0.v[e] = use_pn ? r * (u - p * s_pu * invC) : u;
-          } else {
-            const float t = tv[i].v[e];
-            if (use_pn) {
-              o0.v[e] = mk[i][e] * r * (t - p * s_pt * invC);
-              o1.v[e] = r * r * invC *
-                        (3.f * invC * s_pt * s_pu * p - s_tu * p - s_pu * t - s_pt * u);
-            } else {
-              o0.v[e] = mk[i][e] * t;
-              o1.v[e] = 0.f;
+      for (int i = 0; i < MAXI; ++i) {
+        const int ch = sub + i * TPP;
+        if (live && ch < nch) {
+          const F8 yv = unpack8(ry[u][i]);
+          const F8 dv = unpack8(rd[u][i]);
+          if (SECOND) tv[i] = unpack8(rt[u][i]);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const bool pos = yv.v[e] > 0.f;
+            const float m = pos ? 1.f : slope;
+            const float p = pos ? yv.v[e] : yv.v[e] * inv_slope;
+            mk[i][e] = m;
+            pv[i].v[e] = p;
+            uv[i].v[e] = m * dv.v[e] * dscale;
+            s_pu += p * uv[i].v[e];
+            if (SECOND) {
+              s_pt += p * tv[i].v[e];
+              s_tu += tv[i].v[e] * uv[i].v[e];
             }
           }
         }
-        st8(out0 + off, o0);
-        if (SECOND) st8(out1 + off, o1);
       }
+      const float r = rv[u];
+      if (use_pn) {
+        s_pu = subwarp_sum<TPP>(s_pu);
+        if (SECOND) {
+          s_pt = subwarp_sum<TPP>(s_pt);
+          s_tu = subwarp_sum<TPP>(s_tu);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < MAXI; ++i) {
+        const int ch = sub + i * TPP;
+        if (live && ch < nch) {
+          const long long off = pix * C + (long long)ch * 8;
+          F8 o0, o1;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float p = pv[i].v[e], uu = uv[i].v[e];
+            if (!SECOND) {
+              o0.v[e] = use_pn ? r * (uu - p * s_pu * invC) : uu;
+              csum[i][e] += o0.v[e];
+            } else {
+              const float t = tv[i].v[e];
+              if (use_pn) {
+                o0.v[e] = mk[i][e] * r * (t - p * s_pt * invC);
+                o1.v[e] = r * r * invC *
+                          (3.f * invC * s_pt * s_pu * p - s_tu * p - s_pu * t - s_pt * uu);
+              } else {
+                o0.v[e] = mk[i][e] * t;
+                o1.v[e] = 0.f;
+              }
+            }
+          }
+          st8(out0 + off, o0);
+          if (SECOND) st8(out1 + off, o1);
+        }
+      }
+    }
+  }
+  if (!SECOND && colsum != nullptr) {
+    // block reduction over the pixel slots, then one atomic per channel per block
+    extern __shared__ float cs_sm[];              // [ppb][C]
+    const int slot = threadIdx.x / TPP;
+#pragma unroll
+    for (int i = 0; i < MAXI; ++i) {
+      const int ch = sub + i * TPP;
+      if (ch < nch) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) cs_sm[slot * C + ch * 8 + e] = csum[i][e];
+      }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float a = 0.f;
+      for (int sl = 0; sl < (int)ppb; ++sl) a += cs_sm[sl * C + c];
+      atomicAdd(colsum + c, a);
     }
   }
 }
 
 template <typename T, bool SECOND>
 static int launch_pn_grad(const T *t, const T *dy, const T *y, const float *r, T *o0, T *o1,
-                          long long P, int C, float slope, int use_pn, cudaStream_t s) {
+                          long long P, int C, float slope, int use_pn, int pool_h, int pool_w,
+                          float *colsum, cudaStream_t s) {
   const int nch = C / 8;
 #define PG_LAUNCH_PN(TPP, MAXI)                                                           \
   {                                                                                       \
     const long long ppb = 256 / TPP;                                                      \
-    const int grid = bw_grid(P, (int)ppb);                                                \
-    pn_lrelu_grad_kernel<T, TPP, MAXI, SECOND><<<grid, 256, 0, s>>>(t, dy, y, r, o0, o1, \
-                                                                     P, C, slope, use_pn); \
+    constexpr int U_ = (MAXI == 1) ? (SECOND ? 2 : 4) : 1;                                 \
+    const int grid = bw_grid(P, (int)ppb * U_);                                           \
+    const size_t sm = (!SECOND && colsum) ? (size_t)ppb * C * sizeof(float) : 0;          \
+    pn_lrelu_grad_kernel<T, TPP, MAXI, SECOND, U_><<<grid, 256, sm, s>>>(                 \
+        t, dy, y, r, o0, o1, P, C, slope, use_pn, pool_h, pool_w, colsum);                \
   }
   if (nch <= 4) PG_LAUNCH_PN(4, 1)
   else if (nch <= 8) PG_LAUNCH_PN(8, 1)
@@ -155,15 +226,31 @@ colsum_kernel(const T *__restrict__ x, float *__restrict__ out, long long P, int
 
 using namespace pg;
 
+// power-of-two H and W: put (log2 + 1) into the high 16 bits so the kernel can shift/mask
+static void pg_encode_pool(int *h, int *w) {
+  auto lg = [](int v) { int l = 0; while ((1 << l) < v) ++l; return ((1 << l) == v) ? l + 1 : 0; };
+  const int lh = lg(*h), lw = lg(*w);
+  if (*w > 0 && lh && lw) {
+    *h |= lh << 16;
+    *w |= lw << 16;
+  }
+}
+
 extern "C" int pg_pn_lrelu_bwd(const void *dy, const void *y, const float *r, void *da,
-                               long long P, int C, float slope, int use_pn, int dtype,
-                               void *stream) {
+                               long long P, int C, float slope, int use_pn, int pool_h,
+                               int pool_w, float *colsum, int dtype, void *stream) {
+  PG_CHECK_ARG((pool_h == 0) == (pool_w == 0) && pool_h % 2 == 0 && pool_w % 2 == 0,
+               "pg_pn_lrelu_bwd: pooled form needs even H and W");
+  PG_CHECK_ARG(pool_w == 0 || P % ((long long)pool_h * pool_w) == 0, "pg_pn_lrelu_bwd: P is not N*H*W");
+  PG_CHECK_ARG(pool_w == 0 || (P < (1ll << 31) && pool_h < 65536 && pool_w < 65536), "pg_pn_lrelu_bwd: too large");
+  pg_encode_pool(&pool_h, &pool_w);
   PG_CHECK_ARG(dy && y && da && (r || !use_pn), "pg_pn_lrelu_bwd: null pointer");
   PG_CHECK_ARG(P > 0 && C > 0 && C % 8 == 0, "pg_pn_lrelu_bwd: need C %% 8 == 0 (C=%d)", C);
   PG_CHECK_ARG(slope > 0.f, "pg_pn_lrelu_bwd: slope must be > 0");
   PG_DISPATCH_DTYPE(dtype, T, {
     int rc = launch_pn_grad<T, false>(nullptr, (const T *)dy, (const T *)y, r, (T *)da, nullptr,
-                                      P, C, slope, use_pn, (cudaStream_t)stream);
+                                      P, C, slope, use_pn, pool_h, pool_w, colsum,
+                                      (cudaStream_t)stream);
     if (rc) return rc;
   });
   PG_CHECK_LAUNCH("pg_pn_lrelu_bwd");
@@ -171,14 +258,19 @@ extern "C" int pg_pn_lrelu_bwd(const void *dy, const void *y, const float *r, vo
 
 extern "C" int pg_pn_lrelu_bwd_bwd(const void *t, const void *dy, const void *y, const float *r,
                                    void *cot_dy, void *cot_a, long long P, int C, float slope,
-                                   int use_pn, int dtype, void *stream) {
+                                   int use_pn, int pool_h, int pool_w, int dtype, void *stream) {
+  PG_CHECK_ARG((pool_h == 0) == (pool_w == 0) && pool_h % 2 == 0 && pool_w % 2 == 0,
+               "pg_pn_lrelu_bwd_bwd: pooled form needs even H and W");
+  PG_CHECK_ARG(pool_w == 0 || (P < (1ll << 31) && pool_h < 65536 && pool_w < 65536), "pg_pn_lrelu_bwd_bwd: too large");
+  pg_encode_pool(&pool_h, &pool_w);
   PG_CHECK_ARG(t && dy && y && cot_dy && cot_a && (r || !use_pn),
                "pg_pn_lrelu_bwd_bwd: null pointer");
   PG_CHECK_ARG(P > 0 && C > 0 && C % 8 == 0, "pg_pn_lrelu_bwd_bwd: need C %% 8 == 0 (C=%d)", C);
   PG_CHECK_ARG(slope > 0.f, "pg_pn_lrelu_bwd_bwd: slope must be > 0");
   PG_DISPATCH_DTYPE(dtype, T, {
     int rc = launch_pn_grad<T, true>((const T *)t, (const T *)dy, (const T *)y, r, (T *)cot_dy,
-                                     (T *)cot_a, P, C, slope, use_pn, (cudaStream_t)stream);
+                                     (T *)cot_a, P, C, slope, use_pn, pool_h, pool_w, nullptr,
+                                     (cudaStream_t)stream);
     if (rc) return rc;
   });
   PG_CHECK_LAUNCH("pg_pn_lrelu_bwd_bwd");

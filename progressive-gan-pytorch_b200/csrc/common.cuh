@@ -85,6 +85,38 @@ __device__ __forceinline__ void st8(__nv_bfloat16 *p, const F8 &o) {
   *reinterpret_cast<uint4 *>(p) = raw;
 }
 
+// raw (unconverted) 8-element vectors: issue the loads first, convert later (more bytes in flight)
+struct Raw8f { float4 a, b; };
+__device__ __forceinline__ Raw8f ldraw8(const float *p) {
+  Raw8f r;
+  r.a = *reinterpret_cast<const float4 *>(p);
+  r.b = *reinterpret_cast<const float4 *>(p + 4);
+  return r;
+}
+__device__ __forceinline__ uint4 ldraw8(const __nv_bfloat16 *p) {
+  return *reinterpret_cast<const uint4 *>(p);
+}
+__device__ __forceinline__ F8 unpack8(const Raw8f &r) {
+  F8 o;
+  o.v[0] = r.a.x; o.v[1] = r.a.y; o.v[2] = r.a.z; o.v[3] = r.a.w;
+  o.v[4] = r.b.x; o.v[5] = r.b.y; o.v[6] = r.b.z; o.v[7] = r.b.w;
+  return o;
+}
+__device__ __forceinline__ F8 unpack8(const uint4 &raw) {
+  F8 o;
+  const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&raw);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __bfloat1622float2(h[i]);
+    o.v[2 * i] = f.x;
+    o.v[2 * i + 1] = f.y;
+  }
+  return o;
+}
+template <typename T> struct RawOf;
+template <> struct RawOf<float> { using type = Raw8f; };
+template <> struct RawOf<__nv_bfloat16> { using type = uint4; };
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -218,7 +218,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
 // dw[param layout, logical dims] = scale * dwp[tap][co][ci] (physical, possibly padded dims)
 __global__ void __launch_bounds__(256)
 wgrad_unpack_kernel(const float *__restrict__ dwp, float *__restrict__ dw, int Cin, int Cout,
-                    int Cin_p, int Cout_p, int taps, float scale, int swap_io, int flip) {
+                    int Cin_p, int Cout_p, int taps, float scale, int swap_io, int flip,
+                    int accumulate) {
   const int total = Cin * Cout * taps;
   const int d1 = swap_io ? Cout : Cin;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -228,7 +229,8 @@ wgrad_unpack_kernel(const float *__restrict__ dwp, float *__restrict__ dw, int C
     const int i0 = i / (taps * d1);
     const int co = swap_io ? i1 : i0, ci = swap_io ? i0 : i1;
     const int tap = flip ? (taps - 1 - st) : st;
-    dw[i] = scale * dwp[((size_t)tap * Cout_p + co) * Cin_p + ci];
+    const float v = scale * dwp[((size_t)tap * Cout_p + co) * Cin_p + ci];
+    dw[i] = accumulate ? dw[i] + v : v;
   }
 }
 
@@ -246,7 +248,7 @@ static int pow2_ge32(int v) {
 extern "C" int pg_conv_wgrad_tc(const void *x, const void *dy, float *dw, float *workspace, int N,
                                 int H, int W, int Cin, int Cout, int Cin_log, int Cout_log,
                                 int taps, int flat, float scale, int swap_io, int flip,
-                                void *stream) {
+                                int accumulate, void *stream) {
   PG_CHECK_ARG(x && dy && dw && workspace, "pg_conv_wgrad_tc: null pointer");
   PG_CHECK_ARG(taps >= 1 && (flat || taps == 9), "pg_conv_wgrad_tc: 3x3 mode needs taps == 9");
   PG_CHECK_ARG(N > 0 && H > 0 && W > 0, "pg_conv_wgrad_tc: bad dims");
@@ -339,6 +341,6 @@ extern "C" int pg_conv_wgrad_tc(const void *x, const void *dy, float *dw, float 
   }
   const int total = taps * Cin_log * Cout_log;
   tc::wgrad_unpack_kernel<<<(total + 255) / 256, 256, 0, s>>>(workspace, dw, Cin_log, Cout_log, Cin,
-                                                             Cout, taps, scale, swap_io, flip);
+                                                             Cout, taps, scale, swap_io, flip, accumulate);
   PG_CHECK_LAUNCH("pg_conv_wgrad_tc");
 }

@@ -33,14 +33,24 @@ def K():
 
 
 def _acc_node(p):
-    node = getattr(p, "_pg_acc_node", None)
-    if node is None:
-        node = p.view_as(p).grad_fn.next_functions[0][0]
-        try:
-            p._pg_acc_node = node
-        except Exception:
-            pass
-    return node
+    """The AccumulateGrad node of a leaf parameter.  Deliberately NOT cached: a node kept alive
+    across iterations keeps the stream it was created on, which breaks CUDA-graph capture
+    (the engine would sync the capturing stream with that stale stream)."""
+    return p.view_as(p).grad_fn.next_functions[0][0]
+
+
+# Direct gradient accumulation (enabled by Trainer): weight/bias gradient kernels add straight
+# into the parameter's .grad (a view of the flat bucket) and the Function returns None, which
+# removes autograd's AccumulateGrad add kernels and the zero-initialised temporaries.  Only
+# for plain (non-create_graph) backward passes of leaf parameters that already own a .grad.
+DIRECT_GRADS = False
+
+
+def _direct_target(p):
+    if (DIRECT_GRADS and p is not None and not torch.is_grad_enabled() and p.is_leaf
+            and p.grad is not None and p.grad.is_contiguous() and p.grad.dtype == torch.float32):
+        return p.grad
+    return None
 
 
 def _wants_grad(ctx, idx, t):
@@ -77,7 +87,11 @@ class ConvFwd(Function):
         if ctx.needs_input_grad[0]:
             dx = ConvFwd.apply(dy, w, ctx.op.adjoint(), ctx.scale)
         if _wants_grad(ctx, 1, w):
-            dw = ConvWgrad.apply(x, dy, ctx.op, ctx.scale, tuple(w.shape))
+            tgt = _direct_target(w)
+            if tgt is not None:
+                K().conv_wgrad(x, dy, tuple(w.shape), ctx.op, ctx.scale, out=tgt)
+            else:
+                dw = ConvWgrad.apply(x, dy, ctx.op, ctx.scale, tuple(w.shape))
         return dx, dw, None, None
 
 
@@ -136,50 +150,87 @@ class ConvAct(Function):
         if ctx.needs_input_grad[0]:
             dx = ConvFwd.apply(dA, w, ctx.op.adjoint(), ctx.scale)
         if _wants_grad(ctx, 1, w):
-            dw = ConvWgrad.apply(x, dA, ctx.op, ctx.scale, tuple(w.shape))
+            tgt = _direct_target(w)
+            if tgt is not None:
+                K().conv_wgrad(x, dA, tuple(w.shape), ctx.op, ctx.scale, out=tgt)
+            else:
+                dw = ConvWgrad.apply(x, dA, ctx.op, ctx.scale, tuple(w.shape))
         if b is not None and _wants_grad(ctx, 2, b):
-            db = ColSum.apply(dA)
+            if _direct_target(b) is not None:
+                pass          # direct mode: accumulated by the Act/ActBwd kernels that produced dA
+            else:
+                db = ColSum.apply(dA)
         return dx, dw, db, None, None, None, None
 
 
+def _bias_wanted(bias):
+    if bias is None or not bias.requires_grad:
+        return False
+    if bias.is_leaf:
+        try:
+            return bool(torch._C._will_engine_execute_node(_acc_node(bias)))
+        except Exception:
+            return True
+    return True
+
+
 class Act(Function):
-    """Graph marker turning the 'pre-activation handle' A into the activation y (same data)."""
+    """Graph marker turning the 'pre-activation handle' A into the activation y (same data).
+    pool=True additionally applies the 2x2 average pool (bilinear x0.5 of the reference,
+    progan_modules.py:299) so that its backward can be fused with the activation backward.
+    `bias` is the bias parameter of the conv that produced A: every gradient that reaches A
+    comes from this node's backward chain (ActBwd.forward and ActBwd.backward), so the bias
+    gradient (column sum of dA) is produced there, fused into those kernels."""
 
     @staticmethod
-    def forward(ctx, A, r, slope, use_pn):
-        ctx.slope, ctx.use_pn = slope, use_pn
+    def forward(ctx, A, r, slope, use_pn, pool, bias):
+        ctx.slope, ctx.use_pn, ctx.pool, ctx.bias = slope, use_pn, pool, bias
         ctx.save_for_backward(A, r)
+        if pool:
+            return K().avgpool2(A, "nhwc")
         return A.view_as(A)
 
     @staticmethod
     def backward(ctx, dy):
         A, r = ctx.saved_tensors
-        return ActBwd.apply(dy.contiguous(), A, r, ctx.slope, ctx.use_pn), None, None, None
+        direct = DIRECT_GRADS and not torch.is_grad_enabled()
+        da = ActBwd.apply(dy.contiguous(), A, r, ctx.slope, ctx.use_pn, ctx.pool, ctx.bias, direct)
+        return da, None, None, None, None, None
 
 
 class ActBwd(Function):
-    """da = Jpn(a)^T (m * dy)  — first-order PixelNorm+LeakyReLU backward."""
+    """da = Jpn(a)^T (m * dy)  — first-order PixelNorm+LeakyReLU backward (with the average
+    pool's backward fused when pool=True) + the per-channel sum of da (bias gradient)."""
 
     @staticmethod
-    def forward(ctx, dy, A, r, slope, use_pn):
-        ctx.slope, ctx.use_pn = slope, use_pn
+    def forward(ctx, dy, A, r, slope, use_pn, pool, bias, direct):
+        ctx.slope, ctx.use_pn, ctx.pool, ctx.bias = slope, use_pn, pool, bias
         ctx.save_for_backward(dy, A, r)
-        return K().pn_lrelu_bwd(dy, A, r if use_pn else None, slope, use_pn)
+        tgt = None
+        want = _bias_wanted(bias)
+        if direct and want and bias.is_leaf and bias.grad is not None:
+            tgt = bias.grad
+        da, _ = K().pn_lrelu_bwd(dy, A, r if use_pn else None, slope, use_pn, pool, False, tgt)
+        return da
 
     @staticmethod
     @once_differentiable
     def backward(ctx, t):
         dy, A, r = ctx.saved_tensors
         cot_dy, cot_a = K().pn_lrelu_bwd_bwd(t.contiguous(), dy, A, r if ctx.use_pn else None,
-                                             ctx.slope, ctx.use_pn)
+                                             ctx.slope, ctx.use_pn, ctx.pool)
+        if ctx.pool:
+            cot_dy = K().avgpool2(cot_dy, "nhwc")
         if not ctx.needs_input_grad[1] or not ctx.use_pn:
             cot_a = None
-        return cot_dy, cot_a, None, None, None
+        elif DIRECT_GRADS and _bias_wanted(ctx.bias) and _direct_target(ctx.bias) is not None:
+            K().colsum(cot_a, out=ctx.bias.grad)    # Hessian-term share of the bias gradient
+        return cot_dy, cot_a, None, None, None, None, None, None
 
 
-def conv_act(x, w, b, op, scale, slope=0.2, use_pn=True):
+def conv_act(x, w, b, op, scale, slope=0.2, use_pn=True, pool=False):
     A, r = ConvAct.apply(x, w, b, op, scale, slope, use_pn)
-    return Act.apply(A, r, slope, use_pn)
+    return Act.apply(A, r, slope, use_pn, pool, b)
 
 
 # ---------------------------------------------------------------------- 1x1 heads
@@ -205,9 +256,17 @@ class PwFwd(Function):
             dx = PwFwd.apply(dy, w, None, other, C, Kc, w_sc, w_sk, scale, act_dtype)
         if _wants_grad(ctx, 1, w):
             act, img = (dy, x) if kind == "expand" else (x, dy)
-            dw = PwWgrad.apply(act, img, tuple(w.shape), C, Kc, w_sc, w_sk, scale, act_dtype)
+            tgt = _direct_target(w)
+            if tgt is not None:
+                K().pw_wgrad(act, img, tuple(w.shape), w_sc, w_sk, scale, out=tgt)
+            else:
+                dw = PwWgrad.apply(act, img, tuple(w.shape), C, Kc, w_sc, w_sk, scale, act_dtype)
         if b is not None and _wants_grad(ctx, 2, b):
-            db = ColSum.apply(dy) if kind == "expand" else ImgChanSum.apply(dy)
+            tgt = _direct_target(b)
+            if tgt is not None:
+                (K().colsum if kind == "expand" else K().img_chansum)(dy, out=tgt)
+            else:
+                db = ColSum.apply(dy) if kind == "expand" else ImgChanSum.apply(dy)
         return (dx, dw, db) + (None,) * 7
 
 
@@ -317,27 +376,30 @@ class Tanh(Function):
 class Mbstd(Function):
     @staticmethod
     def forward(ctx, x, Cp):
+        out, stats = K().mbstd_fwd(x, Cp)
+        ctx.stats = stats
         ctx.save_for_backward(x)
-        return K().mbstd_fwd(x, Cp)
+        return out
 
     @staticmethod
     def backward(ctx, dout):
         (x,) = ctx.saved_tensors
-        return MbstdBwd.apply(dout.contiguous(), x), None
+        return MbstdBwd.apply(dout.contiguous(), x, ctx.stats), None
 
 
 class MbstdBwd(Function):
     @staticmethod
-    def forward(ctx, dout, x):
+    def forward(ctx, dout, x, stats):
+        ctx.stats = stats
         ctx.save_for_backward(dout, x)
-        return K().mbstd_bwd(dout, x)
+        return K().mbstd_bwd(dout, x, stats)
 
     @staticmethod
     @once_differentiable
     def backward(ctx, t):
         dout, x = ctx.saved_tensors
-        cot_dout, cot_x = K().mbstd_bwd_bwd(t.contiguous(), dout, x)
-        return cot_dout, cot_x
+        cot_dout, cot_x = K().mbstd_bwd_bwd(t.contiguous(), dout, x, ctx.stats)
+        return cot_dout, cot_x, None
 
 
 # ---------------------------------------------------------------- gradient penalty

@@ -195,8 +195,9 @@ class CudaKernels:
                        _dt(x), st)
         return y, r
 
-    def conv_wgrad(self, x, dy, wshape, op, scale):
-        """dw[wshape] = scale * sum_pix dy (x) x for the conv `op` (fp32)."""
+    def conv_wgrad(self, x, dy, wshape, op, scale, out=None):
+        """dw[wshape] = scale * sum_pix dy (x) x for the conv `op` (fp32).  out: accumulate into
+        this fp32 tensor (a parameter's .grad view of the flat bucket) instead of allocating."""
         _chk(x, "x", ndim=4)
         _chk(dy, "dy", x.dtype, 4)
         N, H, W, cin = x.shape
@@ -207,26 +208,32 @@ class CudaKernels:
         cin_l, cout_l = op.cin(wshape), op.cout(wshape)
         mode = self.tc_mode(x.dtype, H, W, wshape, op) if self.wgrad_tc else None
         st = self._stream()
+        acc = 0
+        if out is not None:
+            _chk(out, "out", torch.float32)
+            if tuple(out.shape) != tuple(wshape):
+                raise RuntimeError("progan_b200: wgrad out shape mismatch")
+            acc = 1
         if mode is not None:
-            dw = torch.empty(tuple(wshape), device=x.device, dtype=torch.float32)
+            dw = out if out is not None else torch.empty(tuple(wshape), device=x.device, dtype=torch.float32)
             ws = torch.empty(k * k * cin * cout, device=x.device, dtype=torch.float32)
             if mode == "conv3":
                 self._call("pg_conv_wgrad_tc", x.data_ptr(), dy.data_ptr(), dw.data_ptr(), ws.data_ptr(),
                            N, H, W, cin, cout, cin_l, cout_l, 9, 0, float(scale), int(op.swap),
-                           int(op.flip), st)
+                           int(op.flip), acc, st)
             elif mode == "valid":
                 self._call("pg_conv_wgrad_tc", x.data_ptr(), dy.data_ptr(), dw.data_ptr(), ws.data_ptr(),
                            N, 1, 1, cin, cout, cin, cout, k * k, 1, float(scale), int(op.swap),
-                           int(op.flip), st)
+                           int(op.flip), acc, st)
             else:   # "full": the same quantity as the valid-form weight gradient of the adjoint op
                 self._call("pg_conv_wgrad_tc", dy.data_ptr(), x.data_ptr(), dw.data_ptr(), ws.data_ptr(),
                            N, 1, 1, cout, cin, cout, cin, k * k, 1, float(scale), int(not op.swap),
-                           int(not op.flip), st)
+                           int(not op.flip), acc, st)
             self.launches += 2          # memset + unpack
         else:
             if op.xpad or op.ypad:
                 raise RuntimeError("progan_b200: padded channels are only used on the tcgen05 path")
-            dw = torch.zeros(tuple(wshape), device=x.device, dtype=torch.float32)
+            dw = out if out is not None else torch.zeros(tuple(wshape), device=x.device, dtype=torch.float32)
             self._call("pg_conv_wgrad_simt", x.data_ptr(), dy.data_ptr(), dw.data_ptr(), N, H, W,
                        cin, cout, k, op.pad, float(scale), int(op.swap), int(op.flip), _dt(x), st)
         return dw
@@ -239,29 +246,39 @@ class CudaKernels:
         return C + 1
 
     # ------------------------------------------------- PixelNorm + LeakyReLU
-    def pn_lrelu_bwd(self, dy, y, r, slope, use_pn):
+    def pn_lrelu_bwd(self, dy, y, r, slope, use_pn, pool=False, want_colsum=False, colsum_out=None):
+        """da = Jpn(a)^T (m*dy).  pool: dy is the gradient of avgpool2(y).  Returns (da, colsum)
+        where colsum = per-channel sum of da (bias gradient) when requested, else None."""
         _chk(dy, "dy", y.dtype)
         _chk(y, "y")
-        C = y.shape[-1]
+        N, H, W, C = y.shape
+        if pool and tuple(dy.shape) != (N, H // 2, W // 2, C):
+            raise RuntimeError("progan_b200: pooled dy shape mismatch")
         da = torch.empty_like(y)
+        cs = colsum_out
+        if cs is None and want_colsum:
+            cs = torch.zeros(C, device=y.device, dtype=torch.float32)
         self._call("pg_pn_lrelu_bwd", dy.data_ptr(), y.data_ptr(), _ptr(r), da.data_ptr(),
-                   y.numel() // C, C, float(slope), int(use_pn), _dt(y), self._stream())
-        return da
+                   y.numel() // C, C, float(slope), int(use_pn), H if pool else 0, W if pool else 0,
+                   _ptr(cs), _dt(y), self._stream())
+        return da, cs
 
-    def pn_lrelu_bwd_bwd(self, t, dy, y, r, slope, use_pn):
+    def pn_lrelu_bwd_bwd(self, t, dy, y, r, slope, use_pn, pool=False):
+        """(cot_dy at full resolution, cot_a); pool: dy is the pooled-activation gradient."""
         _chk(t, "t", y.dtype)
         _chk(dy, "dy", y.dtype)
-        C = y.shape[-1]
+        N, H, W, C = y.shape
         cot_dy, cot_a = torch.empty_like(y), torch.empty_like(y)
         self._call("pg_pn_lrelu_bwd_bwd", t.data_ptr(), dy.data_ptr(), y.data_ptr(), _ptr(r),
                    cot_dy.data_ptr(), cot_a.data_ptr(), y.numel() // C, C, float(slope),
-                   int(use_pn), _dt(y), self._stream())
+                   int(use_pn), H if pool else 0, W if pool else 0, _dt(y), self._stream())
         return cot_dy, cot_a
 
-    def colsum(self, x):
+    def colsum(self, x, out=None):
         _chk(x, "x")
         C = x.shape[-1]
-        out = torch.zeros(C, device=x.device, dtype=torch.float32)
+        if out is None:
+            out = torch.zeros(C, device=x.device, dtype=torch.float32)
         self._call("pg_colsum", x.data_ptr(), out.data_ptr(), x.numel() // C, C, _dt(x), self._stream())
         return out
 
@@ -284,20 +301,21 @@ class CudaKernels:
                    Kc, C, w_sc, w_sk, float(scale), _dt(act), self._stream())
         return img
 
-    def pw_wgrad(self, act, img, wshape, w_sc, w_sk, scale):
+    def pw_wgrad(self, act, img, wshape, w_sc, w_sk, scale, out=None):
         _chk(act, "act", ndim=4)
         _chk(img, "img", torch.float32, 4)
         N, H, W, C = act.shape
         Kc = img.shape[1]
-        dw = torch.zeros(tuple(wshape), device=act.device, dtype=torch.float32)
+        dw = out if out is not None else torch.zeros(tuple(wshape), device=act.device, dtype=torch.float32)
         self._call("pg_pw_wgrad", act.data_ptr(), img.data_ptr(), dw.data_ptr(), N, H * W, Kc, C,
                    w_sc, w_sk, float(scale), _dt(act), self._stream())
         return dw
 
-    def img_chansum(self, img):
+    def img_chansum(self, img, out=None):
         _chk(img, "img", torch.float32, 4)
         N, Kc, H, W = img.shape
-        out = torch.zeros(Kc, device=img.device, dtype=torch.float32)
+        if out is None:
+            out = torch.zeros(Kc, device=img.device, dtype=torch.float32)
         self._call("pg_img_chansum", img.data_ptr(), out.data_ptr(), N, H * W, Kc, self._stream())
         return out
 
@@ -370,29 +388,36 @@ class CudaKernels:
 
     # --------------------------------------------------------------- mbstd
     def mbstd_fwd(self, x, Cp):
+        """Returns (out, stats): stats is the fp32 workspace (mu, sigma per feature) reused by
+        the backward kernels."""
         _chk(x, "x", ndim=4)
         N, H, W, C = x.shape
         if H != 4 or W != 4:
             raise RuntimeError("progan_b200: minibatch-stddev expects a 4x4 map, got %dx%d" % (H, W))
         out = torch.empty((N, 4, 4, Cp), device=x.device, dtype=x.dtype)
-        self._call("pg_mbstd_fwd", x.data_ptr(), out.data_ptr(), N, C, Cp, _dt(x), self._stream())
-        return out
+        stats = torch.empty(4 * 16 * C + 64, device=x.device, dtype=torch.float32)
+        self._call("pg_mbstd_fwd", x.data_ptr(), out.data_ptr(), stats.data_ptr(), N, C, Cp, _dt(x),
+                   self._stream())
+        self.launches += 1
+        return out, stats
 
-    def mbstd_bwd(self, dout, x):
+    def mbstd_bwd(self, dout, x, stats):
         _chk(dout, "dout", x.dtype, 4)
         N, _, _, C = x.shape
         dx = torch.empty_like(x)
-        self._call("pg_mbstd_bwd", dout.data_ptr(), x.data_ptr(), dx.data_ptr(), N, C,
-                   dout.shape[-1], _dt(x), self._stream())
+        self._call("pg_mbstd_bwd", dout.data_ptr(), x.data_ptr(), stats.data_ptr(), dx.data_ptr(), N,
+                   C, dout.shape[-1], _dt(x), self._stream())
         return dx
 
-    def mbstd_bwd_bwd(self, t, dout, x):
+    def mbstd_bwd_bwd(self, t, dout, x, stats):
         _chk(t, "t", x.dtype, 4)
         _chk(dout, "dout", x.dtype, 4)
         N, _, _, C = x.shape
         cot_dout, cot_x = torch.empty_like(dout), torch.empty_like(x)
-        self._call("pg_mbstd_bwd_bwd", t.data_ptr(), dout.data_ptr(), x.data_ptr(),
+        st2 = torch.empty_like(stats)       # (tbar, c_f) of this call; mu/sigma are recomputed
+        self._call("pg_mbstd_bwd_bwd", t.data_ptr(), dout.data_ptr(), x.data_ptr(), st2.data_ptr(),
                    cot_dout.data_ptr(), cot_x.data_ptr(), N, C, dout.shape[-1], _dt(x), self._stream())
+        self.launches += 1
         return cot_dout, cot_x
 
     # ------------------------------------------------------------- WGAN-GP

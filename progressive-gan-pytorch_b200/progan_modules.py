@@ -91,12 +91,12 @@ class _LeakyMarker(nn.Module):
         self.negative_slope = slope
 
 
-def _fused_layer(x, conv, slope, use_pn):
+def _fused_layer(x, conv, slope, use_pn, pool=False):
     h = conv.conv
     op = conv.op
     if x.shape[-1] != conv.cin:       # zero-padded input channels (after minibatch-stddev)
         op = ConvOp(op.k, op.pad, op.swap, op.flip, x.shape[-1], 0)
-    return F_.conv_act(x, h.weight_orig, h.bias, op, conv.scale, slope, use_pn)
+    return F_.conv_act(x, h.weight_orig, h.bias, op, conv.scale, slope, use_pn, pool)
 
 
 class ConvBlock(nn.Module):
@@ -121,9 +121,11 @@ class ConvBlock(nn.Module):
         self._c1 = 0
         self._c2 = 3 if pixel_norm else 2
 
-    def forward(self, x):
+    def forward(self, x, pool=False):
+        """pool=True: followed by the x0.5 bilinear (= 2x2 average) downsample of the
+        discriminator (progan_modules.py:299); its backward is fused with the activation's."""
         x = _fused_layer(x, self.conv[self._c1], 0.2, self.pixel_norm)
-        return _fused_layer(x, self.conv[self._c2], 0.2, self.pixel_norm)
+        return _fused_layer(x, self.conv[self._c2], 0.2, self.pixel_norm, pool)
 
 
 class _AlphaMixin:
@@ -246,9 +248,8 @@ class Discriminator(nn.Module, _AlphaMixin):
                 out = _from_rgb(x, self.from_rgb[index], dt)
             if i == 0:
                 out = F_.Mbstd.apply(out, F_.K().mbstd_channels(out.shape[-1], out.dtype))
-            out = self.progression[index](out)
+            out = self.progression[index](out, pool=(i > 0))
             if i > 0:
-                out = F_.avgpool2(out)
                 if i == step and fading:
                     skip = _from_rgb(F_.avgpool2(x, "nchw"), self.from_rgb[index + 1], dt)
                     out = F_.Blend.apply(skip, out, self._alpha(alpha, out.device))

@@ -173,6 +173,14 @@ class Trainer:
         get_kernels().invalidate_packs()
 
     def _iteration(self, real, z, eps, step, alpha, fading):
+        prev = F_.DIRECT_GRADS
+        F_.DIRECT_GRADS = True      # gradient kernels accumulate straight into the flat buckets
+        try:
+            self._iteration_impl(real, z, eps, step, alpha, fading)
+        finally:
+            F_.DIRECT_GRADS = prev
+
+    def _iteration_impl(self, real, z, eps, step, alpha, fading):
         """alpha: fp32 device scalar tensor when fading else the python number."""
         K = get_kernels()
         G, D = self.G, self.D

@@ -62,7 +62,7 @@ class EmulKernels:
             r = r.contiguous().to(torch.float64 if cd == torch.float64 else torch.float32)
         return y, r
 
-    def conv_wgrad(self, x, dy, wshape, op, scale):
+    def conv_wgrad(self, x, dy, wshape, op, scale, out=None):
         self.launches += 1
         cd = torch.float64 if x.dtype == torch.float64 else torch.float32
         cout, cin = op.cout(wshape), op.cin(wshape)
@@ -73,7 +73,11 @@ class EmulKernels:
             dwl = dwl.flip(2, 3)
         if op.swap:
             dwl = dwl.transpose(0, 1)
-        return dwl.contiguous().to(cd if cd == torch.float64 else torch.float32)
+        res = dwl.contiguous().to(cd if cd == torch.float64 else torch.float32)
+        if out is not None:
+            out.add_(res.to(out.dtype))
+            return out
+        return res
 
     # ---- PixelNorm + LeakyReLU
     @staticmethod
@@ -83,22 +87,34 @@ class EmulKernels:
         p = torch.where(pos, y, y / slope)
         return p, m
 
-    def pn_lrelu_bwd(self, dy, y, r, slope, use_pn):
-        self.launches += 1
-        cd = torch.float64 if y.dtype == torch.float64 else torch.float32
-        p, m = self._pm(y.to(cd), slope)
-        u = m * dy.to(cd)
-        if not use_pn:
-            return u.to(y.dtype)
-        C = y.shape[-1]
-        s = (p * u).sum(-1, keepdim=True)
-        return (r.to(cd).unsqueeze(-1) * (u - p * s / C)).to(y.dtype)
+    @staticmethod
+    def _unpool(dy):
+        return 0.25 * dy.repeat_interleave(2, 1).repeat_interleave(2, 2)
 
-    def pn_lrelu_bwd_bwd(self, t, dy, y, r, slope, use_pn):
+    def pn_lrelu_bwd(self, dy, y, r, slope, use_pn, pool=False, want_colsum=False, colsum_out=None):
         self.launches += 1
         cd = torch.float64 if y.dtype == torch.float64 else torch.float32
         p, m = self._pm(y.to(cd), slope)
-        u = m * dy.to(cd)
+        dyf = self._unpool(dy.to(cd)) if pool else dy.to(cd)
+        u = m * dyf
+        if use_pn:
+            C = y.shape[-1]
+            s = (p * u).sum(-1, keepdim=True)
+            u = r.to(cd).unsqueeze(-1) * (u - p * s / C)
+        cs = None
+        if want_colsum or colsum_out is not None:
+            cs = u.reshape(-1, y.shape[-1]).sum(0).to(cd if cd == torch.float64 else torch.float32)
+            if colsum_out is not None:
+                colsum_out.add_(cs.to(colsum_out.dtype))
+                cs = colsum_out
+        return u.to(y.dtype), cs
+
+    def pn_lrelu_bwd_bwd(self, t, dy, y, r, slope, use_pn, pool=False):
+        self.launches += 1
+        cd = torch.float64 if y.dtype == torch.float64 else torch.float32
+        p, m = self._pm(y.to(cd), slope)
+        dyf = self._unpool(dy.to(cd)) if pool else dy.to(cd)
+        u = m * dyf
         t = t.to(cd)
         if not use_pn:
             return (m * t).to(y.dtype), torch.zeros_like(y)
@@ -111,9 +127,13 @@ class EmulKernels:
         cot_a = rr * rr / C * (3.0 / C * s_pt * s_pu * p - s_tu * p - s_pu * t - s_pt * u)
         return cot_dy.to(y.dtype), cot_a.to(y.dtype)
 
-    def colsum(self, x):
+    def colsum(self, x, out=None):
         self.launches += 1
-        return x.reshape(-1, x.shape[-1]).to(torch.float64 if x.dtype == torch.float64 else torch.float32).sum(0)
+        res = x.reshape(-1, x.shape[-1]).to(torch.float64 if x.dtype == torch.float64 else torch.float32).sum(0)
+        if out is not None:
+            out.add_(res.to(out.dtype))
+            return out
+        return res
 
     # ---- 1x1 heads
     @staticmethod
@@ -142,7 +162,7 @@ class EmulKernels:
             out = out + bias.to(cd).view(1, -1, 1, 1)
         return out.contiguous()
 
-    def pw_wgrad(self, act, img, wshape, w_sc, w_sk, scale):
+    def pw_wgrad(self, act, img, wshape, w_sc, w_sk, scale, out=None):
         self.launches += 1
         C, Kc = act.shape[-1], img.shape[1]
         cd = img.dtype
@@ -151,11 +171,18 @@ class EmulKernels:
         idx = (torch.arange(C, device=img.device).view(C, 1) * w_sc
                + torch.arange(Kc, device=img.device).view(1, Kc) * w_sk)
         dw.view(-1)[idx.reshape(-1)] = dck.reshape(-1)
+        if out is not None:
+            out.add_(dw.to(out.dtype))
+            return out
         return dw
 
-    def img_chansum(self, img):
+    def img_chansum(self, img, out=None):
         self.launches += 1
-        return img.sum(dim=(0, 2, 3))
+        res = img.sum(dim=(0, 2, 3))
+        if out is not None:
+            out.add_(res.to(out.dtype))
+            return out
+        return res
 
     # ---- resampling
     @staticmethod
@@ -227,9 +254,9 @@ class EmulKernels:
         out = torch.zeros(N, 4, 4, Cp, dtype=xf.dtype, device=x.device)
         out[..., :C] = xf
         out[..., C] = sigma.mean()
-        return out.to(x.dtype)
+        return out.to(x.dtype), None
 
-    def mbstd_bwd(self, dout, x):
+    def mbstd_bwd(self, dout, x, stats=None):
         self.launches += 1
         xf, mu, sigma = self._mb_stats(x)
         N, _, _, C = x.shape
@@ -238,7 +265,7 @@ class EmulKernels:
         dm = g[..., C].sum()
         return (g[..., :C] + dm * (xf - mu) / (N * Fn * sigma)).contiguous().to(x.dtype)
 
-    def mbstd_bwd_bwd(self, t, dout, x):
+    def mbstd_bwd_bwd(self, t, dout, x, stats=None):
         self.launches += 1
         xf, mu, sigma = self._mb_stats(x)
         N, _, _, C = x.shape

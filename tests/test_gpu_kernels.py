@@ -198,8 +198,21 @@ def test_pn_lrelu_grads(KE, dtype, C, use_pn):
     r = torch.rsqrt((a * a).mean(-1) + 1e-8).contiguous()
     y = torch.nn.functional.leaky_relu(a * r.unsqueeze(-1) if use_pn else a, 0.2).to(dtype)
     dy, t = rnd(*P, C, dtype=dtype, seed=5), rnd(*P, C, dtype=dtype, seed=6)
-    da = K.pn_lrelu_bwd(dy, y, r, 0.2, use_pn)
-    assert helpers.rel(da, E.pn_lrelu_bwd(dy, y, r, 0.2, use_pn)) < tol(dtype)
+    da, cs = K.pn_lrelu_bwd(dy, y, r, 0.2, use_pn, False, True)
+    dae, cse = E.pn_lrelu_bwd(dy, y, r, 0.2, use_pn, False, True)
+    assert helpers.rel(da, dae) < tol(dtype)
+    assert helpers.rel(cs, cse) < 1e-3
+    # pooled form: dy is the gradient of avgpool2(y) (needs even H, W)
+    y2, r2 = y.reshape(3, 5, 7, C)[:, :4, :6].contiguous(), r.reshape(3, 5, 7)[:, :4, :6].contiguous()
+    dyp = rnd(3, 2, 3, C, dtype=dtype, seed=7)
+    dap, _ = K.pn_lrelu_bwd(dyp, y2, r2, 0.2, use_pn, True, False)
+    assert helpers.rel(dap, E.pn_lrelu_bwd(dyp, y2, r2, 0.2, use_pn, True)[0]) < tol(dtype)
+    t2 = t.reshape(3, 5, 7, C)[:, :4, :6].contiguous()
+    p1, p2 = K.pn_lrelu_bwd_bwd(t2, dyp, y2, r2, 0.2, use_pn, True)
+    q1, q2 = E.pn_lrelu_bwd_bwd(t2, dyp, y2, r2, 0.2, use_pn, True)
+    assert helpers.rel(p1, q1) < tol(dtype)
+    if use_pn:
+        assert helpers.rel(p2, q2) < tol(dtype)
     c1, c2 = K.pn_lrelu_bwd_bwd(t, dy, y, r, 0.2, use_pn)
     e1, e2 = E.pn_lrelu_bwd_bwd(t, dy, y, r, 0.2, use_pn)
     assert helpers.rel(c1, e1) < tol(dtype)
@@ -255,12 +268,12 @@ def test_mbstd(KE, dtype, N, C):
     K, E = KE
     x = rnd(N, 4, 4, C, dtype=dtype, seed=13)
     Cp = C + 1 if N != 64 else ((C + 1 + 31) // 32) * 32      # also the channel-padded form
-    o, oe = K.mbstd_fwd(x, Cp), E.mbstd_fwd(x, Cp)
+    (o, stats), (oe, _) = K.mbstd_fwd(x, Cp), E.mbstd_fwd(x, Cp)
     assert helpers.rel(o, oe) < tol(dtype)
     dout, t = rnd(N, 4, 4, Cp, dtype=dtype, seed=14), rnd(N, 4, 4, C, dtype=dtype, seed=15)
     dout[..., C + 1:] = 0
-    assert helpers.rel(K.mbstd_bwd(dout, x), E.mbstd_bwd(dout, x)) < tol(dtype)
-    a1, a2 = K.mbstd_bwd_bwd(t, dout, x)
+    assert helpers.rel(K.mbstd_bwd(dout, x, stats), E.mbstd_bwd(dout, x)) < tol(dtype)
+    a1, a2 = K.mbstd_bwd_bwd(t, dout, x, stats)
     b1, b2 = E.mbstd_bwd_bwd(t, dout, x)
     assert helpers.rel(a1, b1) < tol(dtype)
     assert helpers.rel(a2, b2) < (1e-3 if dtype == torch.float32 else 2e-2)

@@ -225,9 +225,10 @@ def test_per_layer_taps(precision):
         orig = F_.conv_act
 
         def tapped(*a, **k):
-            y = orig(*a, **k)
+            pool = k.pop("pool", False) or (len(a) > 7 and a[7])
+            y = orig(*a[:7], **k)                 # tap the activation before the fused pool
             taps.append(y.detach().float().permute(0, 3, 1, 2))
-            return y
+            return F_.avgpool2(y) if pool else y
         F_.conv_act = tapped
         try:
             D(inp["real"].to(DEV), step=3, alpha=0.25)
