@@ -35,8 +35,10 @@ def K():
 def _acc_node(p):
     """The AccumulateGrad node of a leaf parameter.  Deliberately NOT cached: a node kept alive
     across iterations keeps the stream it was created on, which breaks CUDA-graph capture
-    (the engine would sync the capturing stream with that stale stream)."""
-    return p.view_as(p).grad_fn.next_functions[0][0]
+    (the engine would sync the capturing stream with that stale stream).  Grad mode is forced
+    on: inside a plain backward it is off and view_as() would not record a node."""
+    with torch.enable_grad():
+        return p.view_as(p).grad_fn.next_functions[0][0]
 
 
 # Direct gradient accumulation (enabled by Trainer): weight/bias gradient kernels add straight
