@@ -14,6 +14,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--which", default="fwd,wgrad")
 ap.add_argument("--iters", type=int, default=10)
+ap.add_argument("--layers", default="", help="comma list like 128:64:64 to restrict")
 a = ap.parse_args()
 K = progan_b200.get_kernels()
 K.conv_impl, K.wgrad_tc = "tc", True
@@ -39,6 +40,8 @@ def timeit(fn, sets):
 
 
 print("%-22s %10s %10s %8s" % ("layer", "us", "TFLOP/s", "frac"))
+if a.layers:
+    LAYERS = [tuple(int(v) for v in l.split(":")) for l in a.layers.split(",")]
 for res, cin, cout in LAYERS:
     op = ConvOp(3, 1)
     w = torch.nn.Parameter(torch.randn(cout, cin, 3, 3, device=dev))

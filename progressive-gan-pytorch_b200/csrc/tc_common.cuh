@@ -100,6 +100,44 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// ------------------------------------------------------------------ clusters
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctaid_x() {   // clusters in the grid (x)
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// 2-D tile load multicast to every CTA of `mask`: data and the complete_tx land at the same
+// smem / mbarrier offsets in each destination CTA.
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap *m, uint32_t bar,
+                                               int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(m), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+// commit that arrives on the mbarrier at the same offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"(mask)
+      : "memory");
+}
+
 // ------------------------------------------------------------------- tcgen05
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst),
@@ -233,6 +271,12 @@ int make_tmap_bf16(CUtensorMap *out, const void *base, int rank, const uint64_t 
 
 // second-generation 3x3 kernel (conv3_tc.cu); PG_ERR_UNSUPPORTED when the shape is not eligible
 int conv3_tc_launch(const void *x, const void *wp, const float *bias, void *y, float *r_out, int N,
+                    int H, int W, int Cin, int Cout, float scale, int epi, float slope,
+                    cudaStream_t stream);
+
+// third-generation 3x3 kernel (conv4_tc.cu): one 10x18 halo box per channel block, weight ring,
+// cluster multicast of streamed weights; PG_ERR_UNSUPPORTED when the shape is not eligible
+int conv4_tc_launch(const void *x, const void *wp, const float *bias, void *y, float *r_out, int N,
                     int H, int W, int Cin, int Cout, float scale, int epi, float slope,
                     cudaStream_t stream);
 

@@ -89,6 +89,8 @@ def test_conv_wgrad_simt(KE, dtype, cfg):
     # second-generation kernel: resident weights / streamed weights with two tiles per unit
     (3, 32, 32, 64, 64), (2, 64, 64, 32, 64), (2, 32, 32, 64, 128), (4, 32, 32, 128, 128),
     (1, 64, 32, 64, 32), (3, 32, 64, 32, 32), (1, 32, 32, 128, 32),
+    # third-generation kernel: streamed weights, two tiles per stage, cluster multicast (2 and 4)
+    (10, 64, 64, 128, 128), (19, 32, 32, 128, 128), (5, 128, 128, 64, 64),
 ])
 @pytest.mark.parametrize("epi", [EPI_LINEAR, EPI_PN_LRELU, EPI_LRELU])
 @pytest.mark.parametrize("flip", [False, True])
