@@ -63,6 +63,15 @@ int pg_device_info(int *sm_count, int *cc_major, int *cc_minor);
 int pg_pack_conv_weight(const float *w, void *out, int d0, int d1, int kh, int kw,
                         int swap_io, int flip, int out_layout, int ci_pad, int co_pad,
                         int out_dtype, void *stream);
+/* The same re-layout for n weights in ONE launch (after an optimiser step every operand copy
+ * of a network is refreshed at once).  `table` is a DEVICE array of n entries. */
+typedef struct PgPackEntry {
+  const float *w;
+  void *out;
+  long long total; /* co_pad * taps * ci_pad */
+  int d0, d1, taps, swap_io, flip, layout, ci_pad, co_pad, dtype, reserved;
+} PgPackEntry;
+int pg_pack_conv_weight_multi(const PgPackEntry *table, int n, void *stream);
 
 /* ---- generic kxk stride-1 conv, SIMT fp32-accumulate ----------------------
  * replaces aten::convolution for nn.Conv2d / nn.ConvTranspose2d at
@@ -96,11 +105,24 @@ int pg_conv_tc(const void *x, const void *wp, const float *bias, void *y,
  * layout by swap_io/flip) is overwritten; workspace is taps*Cin*Cout floats.
  * flat == 0: 3x3 pad 1 (taps == 9).  flat == 1: x is [N,1,1,taps*Cin] and tap t
  * addresses channel block t (weight gradient of the GEMM forms above).
- * accumulate != 0: dw += result (gradient accumulation straight into the flat bucket). */
+ * accumulate == 1: dw += result (gradient accumulation straight into the flat bucket).
+ * accumulate == 2: deferred — the partial sums are ADDED to `workspace` (which the caller keeps
+ * zero-initialised and persistent) and dw is not touched; pg_wgrad_unpack_multi later folds
+ * every pending workspace into its gradient in one launch. */
 int pg_conv_wgrad_tc(const void *x, const void *dy, float *dw, float *workspace, int N,
                      int H, int W, int Cin, int Cout, int Cin_log, int Cout_log,
                      int taps, int flat, float scale, int swap_io, int flip,
                      int accumulate, void *stream);
+/* Deferred weight-gradient epilogue for n parameters in ONE launch: for each entry
+ * dw[param layout] += scale * ws[tap][co][ci], then ws is reset to zero.  `table` is a DEVICE
+ * array. */
+typedef struct PgUnpackEntry {
+  float *ws;
+  float *dw;
+  int Cin, Cout, Cin_p, Cout_p, taps, swap_io, flip, reserved;
+  float scale, reserved2;
+} PgUnpackEntry;
+int pg_wgrad_unpack_multi(const PgUnpackEntry *table, int n, void *stream);
 
 /* ---- PixelNorm + LeakyReLU derivatives: progan_modules.py:54-60,138 ------
  * y is the stored post-activation, r the stored per-pixel rsqrt.            */

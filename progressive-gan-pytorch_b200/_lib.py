@@ -20,6 +20,8 @@ SIGNATURES = {
     "pg_abi_version": [],
     "pg_device_info": [ctypes.POINTER(c_int)] * 3,
     "pg_pack_conv_weight": [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P],
+    "pg_pack_conv_weight_multi": [P, c_int, P],
+    "pg_wgrad_unpack_multi": [P, c_int, P],
     "pg_conv_fwd_simt": [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
                          c_int, c_float, c_int, P],
     "pg_conv_wgrad_simt": [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
@@ -53,6 +55,22 @@ SIGNATURES = {
     "pg_adam_multi": [P, P, P, P, P, c_int, P, c_float, c_float, c_float, c_float, c_float, P],
     "pg_ema": [P, P, c_ll, c_float, P],
 }
+
+
+
+class PackEntry(ctypes.Structure):
+    """PgPackEntry of include/progan_b200.h."""
+    _fields_ = [("w", c_void_p), ("out", c_void_p), ("total", c_ll)] + [
+        (n, c_int) for n in ("d0", "d1", "taps", "swap_io", "flip", "layout", "ci_pad", "co_pad",
+                             "dtype", "reserved")]
+
+
+class UnpackEntry(ctypes.Structure):
+    """PgUnpackEntry of include/progan_b200.h."""
+    _fields_ = [("ws", c_void_p), ("dw", c_void_p)] + [
+        (n, c_int) for n in ("Cin", "Cout", "Cin_p", "Cout_p", "taps", "swap_io", "flip", "reserved")
+    ] + [("scale", c_float), ("reserved2", c_float)]
+
 
 _lib = None
 _lock = threading.Lock()

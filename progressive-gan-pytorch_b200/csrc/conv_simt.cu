@@ -42,6 +42,40 @@ __global__ void pack_weight_kernel(const float *__restrict__ w, T *__restrict__ 
   }
 }
 
+// every (weight, operand layout) pair of a network in one launch: blockIdx.y = table entry
+__global__ void __launch_bounds__(256)
+pack_weight_multi_kernel(const PgPackEntry *__restrict__ table) {
+  const PgPackEntry e = table[blockIdx.y];
+  const int Cout = e.swap_io ? e.d1 : e.d0;
+  const int Cin = e.swap_io ? e.d0 : e.d1;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < e.total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int co, ci, tap;
+    if (e.layout == PG_WL_TAP_CI_CO) {
+      co = (int)(i % e.co_pad);
+      ci = (int)((i / e.co_pad) % e.ci_pad);
+      tap = (int)(i / ((long long)e.co_pad * e.ci_pad));
+    } else if (e.layout == PG_WL_CO_TAP_CI) {
+      ci = (int)(i % e.ci_pad);
+      tap = (int)((i / e.ci_pad) % e.taps);
+      co = (int)(i / ((long long)e.ci_pad * e.taps));
+    } else {
+      ci = (int)(i % e.ci_pad);
+      co = (int)((i / e.ci_pad) % e.co_pad);
+      tap = (int)(i / ((long long)e.ci_pad * e.co_pad));
+    }
+    float v = 0.f;
+    if (ci < Cin && co < Cout) {
+      const int st = e.flip ? (e.taps - 1 - tap) : tap;
+      const long long src = e.swap_io ? ((long long)ci * e.d1 + co) * e.taps + st
+                                      : ((long long)co * e.d1 + ci) * e.taps + st;
+      v = e.w[src];
+    }
+    if (e.dtype == PG_BF16) stf(reinterpret_cast<__nv_bfloat16 *>(e.out) + i, v);
+    else stf(reinterpret_cast<float *>(e.out) + i, v);
+  }
+}
+
 // ---------------------------------------------------------------- forward ----
 // one CTA per output pixel, one thread per output channel (loops if Cout > blockDim)
 template <typename T>
@@ -151,6 +185,13 @@ extern "C" int pg_pack_conv_weight(const float *w, void *out, int d0, int d1, in
                     pack_weight_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
                         w, (T *)out, d0, d1, kh * kw, swap_io, flip, out_layout, ci_pad, co_pad));
   PG_CHECK_LAUNCH("pg_pack_conv_weight");
+}
+
+extern "C" int pg_pack_conv_weight_multi(const PgPackEntry *table, int n, void *stream) {
+  PG_CHECK_ARG(table && n > 0 && n <= 65535, "pg_pack_conv_weight_multi: bad table");
+  dim3 grid(64, (unsigned)n);
+  pack_weight_multi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(table);
+  PG_CHECK_LAUNCH("pg_pack_conv_weight_multi");
 }
 
 extern "C" int pg_conv_fwd_simt(const void *x, const void *wp, const float *bias, void *y,

@@ -234,10 +234,39 @@ wgrad_unpack_kernel(const float *__restrict__ dwp, float *__restrict__ dw, int C
   }
 }
 
+// deferred epilogue of every pending weight gradient in one launch (blockIdx.y = entry):
+// dw += scale * ws, then ws = 0 for the next accumulation round
+__global__ void __launch_bounds__(256)
+wgrad_unpack_multi_kernel(const PgUnpackEntry *__restrict__ table) {
+  const PgUnpackEntry e = table[blockIdx.y];
+  const int total_p = e.Cin_p * e.Cout_p * e.taps;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total_p; i += gridDim.x * blockDim.x) {
+    // i indexes the workspace [tap][co][ci] (physical dims): coalesced read + reset
+    const int ci = i % e.Cin_p;
+    const int co = (i / e.Cin_p) % e.Cout_p;
+    const int tap = i / (e.Cin_p * e.Cout_p);
+    const float v = e.ws[i];
+    e.ws[i] = 0.f;
+    if (ci < e.Cin && co < e.Cout) {
+      const int st = e.flip ? (e.taps - 1 - tap) : tap;
+      const int i0 = e.swap_io ? ci : co, i1 = e.swap_io ? co : ci;
+      const int d1 = e.swap_io ? e.Cout : e.Cin;
+      e.dw[((size_t)i0 * d1 + i1) * e.taps + st] += e.scale * v;
+    }
+  }
+}
+
 }  // namespace tc
 }  // namespace pg
 
 using namespace pg;
+
+extern "C" int pg_wgrad_unpack_multi(const PgUnpackEntry *table, int n, void *stream) {
+  PG_CHECK_ARG(table && n > 0 && n <= 65535, "pg_wgrad_unpack_multi: bad table");
+  dim3 grid(64, (unsigned)n);
+  tc::wgrad_unpack_multi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(table);
+  PG_CHECK_LAUNCH("pg_wgrad_unpack_multi");
+}
 
 static int pow2_ge32(int v) {
   int p = 32;
@@ -323,10 +352,13 @@ extern "C" int pg_conv_wgrad_tc(const void *x, const void *dy, float *dw, float 
     }
     attr_set = true;
   }
-  cudaError_t e = cudaMemsetAsync(workspace, 0, (size_t)taps * Cin * Cout * sizeof(float), s);
-  if (e != cudaSuccess) {
-    set_error("pg_conv_wgrad_tc: cudaMemsetAsync: %s", cudaGetErrorString(e));
-    return PG_ERR_CUDA;
+  const bool deferred = accumulate == 2;
+  if (!deferred) {
+    cudaError_t e = cudaMemsetAsync(workspace, 0, (size_t)taps * Cin * Cout * sizeof(float), s);
+    if (e != cudaSuccess) {
+      set_error("pg_conv_wgrad_tc: cudaMemsetAsync: %s", cudaGetErrorString(e));
+      return PG_ERR_CUDA;
+    }
   }
   int rc2 = PG_ERR_UNSUPPORTED;
   if (!flat && taps == 9)   // second-generation kernel where the shape allows
@@ -340,6 +372,7 @@ extern "C" int pg_conv_wgrad_tc(const void *x, const void *dy, float *dw, float 
     tc::wgrad_tc_kernel<<<grid, tc::kWgThreads, smem, s>>>(tx, tdy, p);
   }
   const int total = taps * Cin_log * Cout_log;
+  if (!deferred)
   tc::wgrad_unpack_kernel<<<(total + 255) / 256, 256, 0, s>>>(workspace, dw, Cin_log, Cout_log, Cin,
                                                              Cout, taps, scale, swap_io, flip, accumulate);
   PG_CHECK_LAUNCH("pg_conv_wgrad_tc");

@@ -138,6 +138,7 @@ class ConvAct(Function):
     def forward(ctx, x, w, b, op, scale, slope, use_pn):
         ctx.op, ctx.scale = op, scale
         ctx.save_for_backward(x, w, b)
+        ctx.set_materialize_grads(False)     # r never gets a gradient: no zero-fill per backward
         y, r = K().conv_fwd(x, w, b, op, scale, EPI_PN_LRELU if use_pn else EPI_LRELU, slope)
         if r is None:
             r = torch.empty(0, device=x.device, dtype=torch.float32)
@@ -146,6 +147,8 @@ class ConvAct(Function):
 
     @staticmethod
     def backward(ctx, dA, _dr):
+        if dA is None:
+            return (None,) * 7
         x, w, b = ctx.saved_tensors
         dA = dA.contiguous()
         dx = dw = db = None

@@ -9,6 +9,7 @@ Tensor conventions
   image : [N,K,H,W] contiguous float32 (the module boundary, as the train scripts pass it)
   params, param grads, per-pixel statistics: float32
 """
+import ctypes
 import weakref
 from dataclasses import dataclass
 
@@ -92,7 +93,12 @@ class CudaKernels:
         self.conv_impl = "tc"          # "tc": tcgen05 where the shape allows; "simt": always CUDA cores
         self.wgrad_tc = False          # tcgen05 weight-gradient kernel (enabled once validated)
         self.launches = 0              # kernels launched through this shim (bench `gpu_launches`)
-        self._packs = {}               # id(param) -> (weakref, version, {variant: tensor})
+        self._packs = {}               # id(param) -> [weakref, version, {variant: (tensor, pack args)}]
+        self._pack_tables = {}         # ids of a parameter set -> (signature, device table, n)
+        self.defer_wgrad = False       # Trainer: weight gradients accumulate in persistent workspaces
+        self._wgrad_ws = {}            # (grad ptr, variant) -> (workspace, unpack entry)
+        self._pending = {}             # workspaces holding partial sums since the last flush
+        self._unpack_tables = {}
 
     # ------------------------------------------------------------------ utils
     @staticmethod
@@ -130,6 +136,19 @@ class CudaKernels:
     # --------------------------------------------------------------- packing
     def invalidate_packs(self):
         self._packs.clear()
+        self._pack_tables.clear()
+
+    def drop_packs(self, params):
+        """Forget the operand copies of these parameters (they were modified behind autograd's
+        back, e.g. by the EMA kernel, and are not worth refreshing eagerly)."""
+        for p_ in params:
+            self._packs.pop(id(p_), None)
+
+    @staticmethod
+    def _upload(entries, cls, device):
+        arr = (cls * len(entries))(*entries)
+        raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        return raw.to(device)
 
     def packed(self, w, op, layout, dtype, flip=None):
         """Operand-layout copy of weight_orig for (op, layout, dtype); cached per parameter
@@ -142,19 +161,49 @@ class CudaKernels:
             if ent is not None and ent[0]() is w and ent[1] == w._version:
                 hit = ent[2].get(key)
                 if hit is not None:
-                    return hit
+                    return hit[0]
             else:
-                ent = (weakref.ref(w), w._version, {})
+                ent = [weakref.ref(w), w._version, {}]
                 self._packs[id(w)] = ent
         _chk(w, "weight", torch.float32, 4)
         d0, d1, kh, kw = w.shape
         cout, cin = op.cout_phys(w.shape), op.cin_phys(w.shape)
         out = torch.empty(cout * kh * kw * cin, device=w.device, dtype=dtype)
-        self._call("pg_pack_conv_weight", w.data_ptr(), out.data_ptr(), d0, d1, kh, kw,
-                   int(op.swap), int(flip), layout, cin, cout, _DT[dtype], self._stream())
+        args = (d0, d1, kh, kw, int(op.swap), int(flip), layout, cin, cout, _DT[dtype])
+        self._call("pg_pack_conv_weight", w.data_ptr(), out.data_ptr(), *args, self._stream())
         if cacheable:
-            ent[2][key] = out
+            ent[2][key] = (out, args)
         return out
+
+    def refresh_packs(self, params):
+        """Re-pack every cached operand copy of `params` in ONE launch (after an optimizer step
+        that wrote the parameters through the flat bucket).  The copies keep their storage, so a
+        captured CUDA graph stays valid."""
+        ents = []
+        for p_ in params:
+            ent = self._packs.get(id(p_))
+            if ent is not None and ent[0]() is p_:
+                ents.append((p_, ent))
+        sig = tuple((id(p_), k) for p_, ent in ents for k in ent[2])
+        if not sig:
+            return
+        tkey = tuple(id(p_) for p_ in params)
+        tab = self._pack_tables.get(tkey)
+        if tab is None or tab[0] != sig:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("progan_b200: pack table changed during CUDA-graph capture "
+                                   "(run warm-up iterations before capturing)")
+            rows = []
+            for p_, ent in ents:
+                for k, (out, a) in ent[2].items():
+                    d0, d1, kh, kw, swap, flip, layout, cin, cout, dt = a
+                    rows.append(_lib.PackEntry(p_.data_ptr(), out.data_ptr(), cout * kh * kw * cin, d0, d1,
+                                               kh * kw, swap, flip, layout, cin, cout, dt, 0))
+            tab = (sig, self._upload(rows, _lib.PackEntry, params[0].device), len(rows))
+            self._pack_tables[tkey] = tab
+        self._call("pg_pack_conv_weight_multi", tab[1].data_ptr(), tab[2], self._stream())
+        for p_, ent in ents:
+            ent[1] = p_._version
 
     # ------------------------------------------------------------------ conv
     def conv_fwd(self, x, w, bias, op, scale, epi=EPI_LINEAR, slope=0.2):
@@ -216,7 +265,29 @@ class CudaKernels:
             acc = 1
         if mode is not None:
             dw = out if out is not None else torch.empty(tuple(wshape), device=x.device, dtype=torch.float32)
-            ws = torch.empty(k * k * cin * cout, device=x.device, dtype=torch.float32)
+            if out is not None and self.defer_wgrad:
+                # accumulate into the parameter's persistent workspace; flush_wgrads() folds every
+                # pending workspace into its gradient with one launch
+                wkey = (out.data_ptr(), mode, op.swap, op.flip, cin, cout)
+                went = self._wgrad_ws.get(wkey)
+                if went is None:
+                    if torch.cuda.is_current_stream_capturing():
+                        raise RuntimeError("progan_b200: new weight-gradient workspace during CUDA-graph "
+                                           "capture (run warm-up iterations before capturing)")
+                    ws = torch.zeros(k * k * cin * cout, device=x.device, dtype=torch.float32)
+                    if mode == "conv3":
+                        u = (cin_l, cout_l, cin, cout, 9, int(op.swap), int(op.flip))
+                    elif mode == "valid":
+                        u = (cin, cout, cin, cout, k * k, int(op.swap), int(op.flip))
+                    else:
+                        u = (cout, cin, cout, cin, k * k, int(not op.swap), int(not op.flip))
+                    went = (ws, _lib.UnpackEntry(ws.data_ptr(), out.data_ptr(), *u, 0, float(scale), 0.0))
+                    self._wgrad_ws[wkey] = went
+                ws = went[0]
+                self._pending[wkey] = went
+                acc = 2
+            else:
+                ws = torch.empty(k * k * cin * cout, device=x.device, dtype=torch.float32)
             if mode == "conv3":
                 self._call("pg_conv_wgrad_tc", x.data_ptr(), dy.data_ptr(), dw.data_ptr(), ws.data_ptr(),
                            N, H, W, cin, cout, cin_l, cout_l, 9, 0, float(scale), int(op.swap),
@@ -229,7 +300,8 @@ class CudaKernels:
                 self._call("pg_conv_wgrad_tc", dy.data_ptr(), x.data_ptr(), dw.data_ptr(), ws.data_ptr(),
                            N, 1, 1, cout, cin, cout, cin, k * k, 1, float(scale), int(not op.swap),
                            int(not op.flip), acc, st)
-            self.launches += 2          # memset + unpack
+            if acc != 2:
+                self.launches += 2          # memset + unpack
         else:
             if op.xpad or op.ypad:
                 raise RuntimeError("progan_b200: padded channels are only used on the tcgen05 path")
@@ -237,6 +309,22 @@ class CudaKernels:
             self._call("pg_conv_wgrad_simt", x.data_ptr(), dy.data_ptr(), dw.data_ptr(), N, H, W,
                        cin, cout, k, op.pad, float(scale), int(op.swap), int(op.flip), _dt(x), st)
         return dw
+
+    def flush_wgrads(self):
+        """Fold every pending weight-gradient workspace into its gradient (one launch)."""
+        if not self._pending:
+            return
+        sig = tuple(self._pending.keys())
+        tab = self._unpack_tables.get(sig)
+        if tab is None:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("progan_b200: unpack table changed during CUDA-graph capture")
+            rows = [e for _, e in self._pending.values()]
+            dev = next(iter(self._pending.values()))[0].device
+            tab = (self._upload(rows, _lib.UnpackEntry, dev), len(rows))
+            self._unpack_tables[sig] = tab
+        self._call("pg_wgrad_unpack_multi", tab[0].data_ptr(), tab[1], self._stream())
+        self._pending.clear()
 
     def mbstd_channels(self, C, dtype):
         """Physical channel count of the minibatch-stddev output (C real + 1 statistic):

@@ -159,6 +159,7 @@ class Trainer:
         self.iterations = 0
         self._graphs = {}
         self._g_params = list(generator.parameters())
+        self._r_params = list(g_running.parameters()) if g_running is not None else []
 
     # ------------------------------------------------------------------ pieces
     def _allreduce(self, bucket, plan):
@@ -170,15 +171,18 @@ class Trainer:
         bucket.steps.add_(plan["mask"])
         get_kernels().adam_multi(bucket.p, bucket.g, bucket.m, bucket.v, plan["chunks"], bucket.steps,
                                  self.lr, self.betas[0], self.betas[1], self.eps, 1.0 / self.world)
-        get_kernels().invalidate_packs()
+        get_kernels().refresh_packs(plan["params"])     # operand copies of the updated weights
 
     def _iteration(self, real, z, eps, step, alpha, fading):
-        prev = F_.DIRECT_GRADS
+        K = get_kernels()
+        prev, prev_defer = F_.DIRECT_GRADS, getattr(K, "defer_wgrad", False)
         F_.DIRECT_GRADS = True      # gradient kernels accumulate straight into the flat buckets
+        K.defer_wgrad = True        # ... the conv weight gradients through persistent workspaces
         try:
             self._iteration_impl(real, z, eps, step, alpha, fading)
         finally:
             F_.DIRECT_GRADS = prev
+            K.defer_wgrad = prev_defer
 
     def _iteration_impl(self, real, z, eps, step, alpha, fading):
         """alpha: fp32 device scalar tensor when fading else the python number."""
@@ -199,6 +203,7 @@ class Trainer:
         (g,) = torch.autograd.grad(outputs=hat.sum(), inputs=x_hat, create_graph=True)
         gp = F_.gradient_penalty(g, self.gp_lambda)
         gp.backward()
+        K.flush_wgrads()
         self._allreduce(self.bD, planD)
         self._adam(self.bD, planD)
         self.metrics["grad_penalty"].add_(gp.detach())
@@ -207,10 +212,12 @@ class Trainer:
         self.bG.g.zero_()
         loss = -D(fake, step=step, alpha=alpha).mean()
         loss.backward(inputs=planG["params"])
+        K.flush_wgrads()
         self._allreduce(self.bG, planG)
         self._adam(self.bG, planG)
         if self.bR is not None:
             K.ema(self.bR.p, self.bG.p, self.ema_decay)
+            K.drop_packs(self._r_params)
         self.metrics["gen_loss"].add_(loss.detach())
 
     # ------------------------------------------------------------------ public
@@ -243,14 +250,16 @@ class Trainer:
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
                 for _ in range(2):
-                    K.invalidate_packs()
                     self._iteration(sreal, sz, seps, step, a, fading)
             torch.cuda.current_stream().wait_stream(s)
             for dst, src in zip(state, snap):
                 dst.copy_(src)
             if snapR is not None:
                 self.bR.p.copy_(snapR)
-            K.invalidate_packs()
+            # operand copies follow the restored weights (same storage: the capture below and
+            # every replay keep them consistent through the refresh launches after each Adam)
+            K.refresh_packs(list(self.D.parameters()))
+            K.refresh_packs(list(self.G.parameters()))
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 self._iteration(sreal, sz, seps, step, a, fading)
@@ -262,7 +271,6 @@ class Trainer:
         sz.copy_(z, non_blocking=True)
         seps.copy_(eps, non_blocking=True)
         graph.replay()
-        K.invalidate_packs()
 
     def read_metrics(self, reset=True):
         """One host sync for all three running sums (the reference syncs three times per

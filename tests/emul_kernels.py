@@ -34,7 +34,18 @@ class EmulKernels:
         self.launches = 0
         self.conv_impl = "simt"
 
+    defer_wgrad = False
+
     def invalidate_packs(self):
+        pass
+
+    def refresh_packs(self, params):
+        pass
+
+    def drop_packs(self, params):
+        pass
+
+    def flush_wgrads(self):
         pass
 
     def mbstd_channels(self, C, dtype):
