@@ -251,7 +251,8 @@ wgrad_unpack_multi_kernel(const PgUnpackEntry *__restrict__ table) {
       const int st = e.flip ? (e.taps - 1 - tap) : tap;
       const int i0 = e.swap_io ? ci : co, i1 = e.swap_io ? co : ci;
       const int d1 = e.swap_io ? e.Cout : e.Cin;
-      e.dw[((size_t)i0 * d1 + i1) * e.taps + st] += e.scale * v;
+      // two entries (the conv's own and its adjoint form from the GP sweep) may target one dw
+      atomicAdd(e.dw + ((size_t)i0 * d1 + i1) * e.taps + st, e.scale * v);
     }
   }
 }

@@ -378,33 +378,49 @@ class Tanh(Function):
 
 
 # -------------------------------------------------------------------------- mbstd
+def _groups(n, group):
+    """Batch slices that each see their own minibatch statistic.  group=None: the whole batch
+    (the reference, progan_modules.py:289-293).  The Trainer runs D once on cat([real, fake]) with
+    group = per-pass batch, which reproduces the reference's two separate D calls exactly."""
+    if not group or group >= n:
+        return [(0, n)]
+    if n % group:
+        raise RuntimeError("progan_b200: batch %d is not a multiple of mbstd_group %d" % (n, group))
+    return [(i, i + group) for i in range(0, n, group)]
+
+
 class Mbstd(Function):
     @staticmethod
-    def forward(ctx, x, Cp):
-        out, stats = K().mbstd_fwd(x, Cp)
-        ctx.stats = stats
+    def forward(ctx, x, Cp, group=None):
+        gs = _groups(x.shape[0], group)
+        outs, stats = zip(*[K().mbstd_fwd(x[a:b], Cp) for a, b in gs])
+        ctx.stats, ctx.gs = stats, gs
         ctx.save_for_backward(x)
-        return out
+        return outs[0] if len(gs) == 1 else torch.cat(outs)
 
     @staticmethod
     def backward(ctx, dout):
         (x,) = ctx.saved_tensors
-        return MbstdBwd.apply(dout.contiguous(), x, ctx.stats), None
+        return MbstdBwd.apply(dout.contiguous(), x, ctx.stats, ctx.gs), None, None
 
 
 class MbstdBwd(Function):
     @staticmethod
-    def forward(ctx, dout, x, stats):
-        ctx.stats = stats
+    def forward(ctx, dout, x, stats, gs):
+        ctx.stats, ctx.gs = stats, gs
         ctx.save_for_backward(dout, x)
-        return K().mbstd_bwd(dout, x, stats)
+        dx = [K().mbstd_bwd(dout[a:b], x[a:b], st) for (a, b), st in zip(gs, stats)]
+        return dx[0] if len(gs) == 1 else torch.cat(dx)
 
     @staticmethod
     @once_differentiable
     def backward(ctx, t):
         dout, x = ctx.saved_tensors
-        cot_dout, cot_x = K().mbstd_bwd_bwd(t.contiguous(), dout, x, ctx.stats)
-        return cot_dout, cot_x, None
+        t = t.contiguous()
+        res = [K().mbstd_bwd_bwd(t[a:b], dout[a:b], x[a:b], st) for (a, b), st in zip(ctx.gs, ctx.stats)]
+        if len(res) == 1:
+            return res[0][0], res[0][1], None, None
+        return torch.cat([r_[0] for r_ in res]), torch.cat([r_[1] for r_ in res]), None, None
 
 
 # ---------------------------------------------------------------- gradient penalty

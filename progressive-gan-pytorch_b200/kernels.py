@@ -184,7 +184,7 @@ class CudaKernels:
             ent = self._packs.get(id(p_))
             if ent is not None and ent[0]() is p_:
                 ents.append((p_, ent))
-        sig = tuple((id(p_), k) for p_, ent in ents for k in ent[2])
+        sig = tuple((p_.data_ptr(), v[0].data_ptr(), k) for p_, ent in ents for k, v in ent[2].items())
         if not sig:
             return
         tkey = tuple(id(p_) for p_ in params)
@@ -268,7 +268,7 @@ class CudaKernels:
             if out is not None and self.defer_wgrad:
                 # accumulate into the parameter's persistent workspace; flush_wgrads() folds every
                 # pending workspace into its gradient with one launch
-                wkey = (out.data_ptr(), mode, op.swap, op.flip, cin, cout)
+                wkey = (out.data_ptr(), mode, op.swap, op.flip, cin, cout, cin_l, cout_l, k, float(scale))
                 went = self._wgrad_ws.get(wkey)
                 if went is None:
                     if torch.cuda.is_current_stream_capturing():

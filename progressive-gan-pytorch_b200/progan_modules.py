@@ -235,7 +235,10 @@ class Discriminator(nn.Module, _AlphaMixin):
         self.n_layer = len(self.progression)
         self.linear = EqualLinear(f, 1)
 
-    def forward(self, input, step=0, alpha=-1):
+    def forward(self, input, step=0, alpha=-1, mbstd_group=None):
+        """mbstd_group (extension, default = reference behaviour): batch slices of this size get
+        their own minibatch-stddev statistic, so one call on cat([real, fake]) equals the
+        reference's two calls (train.py:126,137)."""
         dt = _act_dtype(self.precision)
         fading = torch.is_tensor(alpha) or (0 <= alpha < 1)
         x = input.contiguous()
@@ -247,7 +250,7 @@ class Discriminator(nn.Module, _AlphaMixin):
             if i == step:
                 out = _from_rgb(x, self.from_rgb[index], dt)
             if i == 0:
-                out = F_.Mbstd.apply(out, F_.K().mbstd_channels(out.shape[-1], out.dtype))
+                out = F_.Mbstd.apply(out, F_.K().mbstd_channels(out.shape[-1], out.dtype), mbstd_group)
             out = self.progression[index](out, pool=(i > 0))
             if i > 0:
                 if i == step and fading:

@@ -190,14 +190,17 @@ class Trainer:
         G, D = self.G, self.D
         planD = self.bD.plan(_d_active(D, step, fading))
         planG = self.bG.plan(_g_active(G, step, fading))
-        # ---- D phase
+        # ---- D phase.  D(real) and D(fake) (train.py:126-139) run as ONE pass over
+        # cat([real, fake]) with per-half minibatch statistics: same gradients (they accumulate
+        # into the same .grad in the reference), half the launches, twice the rows per GEMM.
         self.bD.g.zero_()
-        real_raw = D(real, step=step, alpha=alpha)
-        real_predict = real_raw.mean() - self.drift * (real_raw ** 2).mean()
-        (-real_predict).backward()
+        B = real.shape[0]
         fake = G(z, step=step, alpha=alpha)
-        fake_predict = D(fake.detach(), step=step, alpha=alpha).mean()
-        fake_predict.backward()
+        both = D(torch.cat([real, fake.detach()]), step=step, alpha=alpha, mbstd_group=B)
+        real_raw, fake_raw = both[:B], both[B:]
+        real_predict = real_raw.mean() - self.drift * (real_raw ** 2).mean()
+        fake_predict = fake_raw.mean()
+        (fake_predict - real_predict).backward()
         x_hat = K.interp_xhat(real, fake.detach(), eps.reshape(-1)).requires_grad_(True)
         hat = D(x_hat, step=step, alpha=alpha)
         (g,) = torch.autograd.grad(outputs=hat.sum(), inputs=x_hat, create_graph=True)

@@ -44,8 +44,54 @@ def test_trainer_bf16_tc_runs_and_graph_equals_eager(name):
     me, mg = tr_e.read_metrics(), tr_g.read_metrics()
     for k in me:
         assert me[k] == me[k] and abs(me[k]) < 1e6, (k, me[k])          # finite
-        assert abs(me[k] - mg[k]) <= 5e-2 * abs(me[k]) + 1e-3, (k, me[k], mg[k])
+        assert abs(me[k] - mg[k]) <= 1e-3 * abs(me[k]) + 1e-3, (k, me[k], mg[k])
     # atomics in the weight-gradient reductions make runs differ in the last bits only
-    assert helpers.rel(tr_g.bD.p, tr_e.bD.p) < 1e-2
-    assert helpers.rel(tr_g.bG.p, tr_e.bG.p) < 1e-2
+    rd, rg = helpers.rel(tr_g.bD.p, tr_e.bD.p), helpers.rel(tr_g.bG.p, tr_e.bG.p)
+    worst = {n: round(helpers.rel(tr_g.bD.p[a:b], tr_e.bD.p[a:b]), 5) for n, (a, b) in tr_e.bD.group_range.items()}
+    assert rd < 1e-5, (rd, rg, me, mg, worst)
+    assert rg < 1e-5, (rd, rg, me, mg)
     assert float(tr_g.bD.steps.max()) == 3.0
+
+
+def _trainer_grads(name):
+    """Gradient buckets of one Trainer iteration, captured right before each Adam step."""
+    K = progan_b200.get_kernels()
+    K.conv_impl, K.wgrad_tc = "tc", True
+    inp = common.make_inputs(name)
+    G, D = helpers.build_models(inp, "bf16", device=DEV)
+    tr = progan_b200.Trainer(G, D, None)
+    snaps, orig = [], tr._adam
+
+    def spy(bucket, plan):
+        snaps.append(bucket.g.clone())
+        orig(bucket, plan)
+
+    tr._adam = spy
+    real, z, eps = inp["real"].to(DEV), inp["z"].to(DEV), inp["eps"].to(DEV)
+    tr.step(real, z, eps, inp["step"], inp["alpha"])
+    torch.cuda.synchronize()
+    return inp, tr, D, snaps
+
+
+@pytest.mark.parametrize("name", ["s2_a0.5", "s3_a0.25", "s5_a0.5"])
+def test_trainer_fast_paths_match_plain_autograd(name):
+    """The Trainer's fast paths (one D pass over cat([real, fake]) with per-half minibatch
+    statistics, gradients accumulated straight into the flat bucket, deferred weight-gradient
+    unpack) give the same D gradients as the reference-ordered step through plain autograd
+    (three separate D calls, AccumulateGrad), and are reproducible run to run."""
+    inp, tr, D, snaps = _trainer_grads(name)
+    _, tr2, _, snaps2 = _trainer_grads(name)
+    assert helpers.rel(snaps2[0], snaps[0]) < 1e-5          # only atomics ordering differs
+    assert helpers.rel(snaps2[1], snaps[1]) < 1e-5
+    G0, D0 = helpers.build_models(inp, "bf16", device=DEV)
+    real, z, eps = inp["real"].to(DEV), inp["z"].to(DEV), inp["eps"].to(DEV)
+    res, _ = helpers.product_train_step(G0, D0, real, z, eps, inp["step"], inp["alpha"])
+    names = {id(p): k for k, p in D.named_parameters()}
+    for gname, (a, b) in tr.bD.group_range.items():
+        off = a
+        for p in tr.bD.group_params[gname]:
+            key = names[id(p)]
+            if key in res["d_grads"]:
+                got = snaps[0][off:off + p.numel()].view(p.shape)
+                assert helpers.rel(got, res["d_grads"][key]) < 5e-3, key   # fused bias sums are fp32, autograd sums bf16 dA
+            off += p.numel()
