@@ -115,7 +115,7 @@ int pg_conv_wgrad_tc(const void *x, const void *dy, float *dw, float *workspace,
                      int accumulate, void *stream);
 /* Deferred weight-gradient epilogue for n parameters in ONE launch: for each entry
  * dw[param layout] += scale * ws[tap][co][ci], then ws is reset to zero.  `table` is a DEVICE
- * array. */
+ * array; no two entries of one call may share a dw (the update is not atomic). */
 typedef struct PgUnpackEntry {
   float *ws;
   float *dw;

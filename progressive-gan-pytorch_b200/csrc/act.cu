@@ -23,7 +23,7 @@ __device__ __forceinline__ float subwarp_sum(float v) {
 // fuses avgpool2_bwd into this kernel.  colsum != nullptr (first order only): the per-channel
 // sum of the produced da — the bias gradient of the conv in front — is accumulated too.
 template <typename T, int TPP, int MAXI, bool SECOND, int U>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 pn_lrelu_grad_kernel(const T *__restrict__ t_in, const T *__restrict__ dy,
                      const T *__restrict__ y, const float *__restrict__ rr,
                      T *__restrict__ out0, T *__restrict__ out1, long long P, int C,

@@ -235,13 +235,16 @@ wgrad_unpack_kernel(const float *__restrict__ dwp, float *__restrict__ dw, int C
 }
 
 // deferred epilogue of every pending weight gradient in one launch (blockIdx.y = entry):
-// dw += scale * ws, then ws = 0 for the next accumulation round
+// dw += scale * ws, then ws = 0 for the next accumulation round.  Threads walk the WORKSPACE
+// (coalesced read + reset; walking the gradient instead makes consecutive lanes gather at a
+// 64 KB stride, which camps on one L2 slice: measured 10x slower) and update dw with a plain
+// read-modify-write: the caller never puts two entries with the same dw into one launch.
 __global__ void __launch_bounds__(256)
 wgrad_unpack_multi_kernel(const PgUnpackEntry *__restrict__ table) {
   const PgUnpackEntry e = table[blockIdx.y];
   const int total_p = e.Cin_p * e.Cout_p * e.taps;
+  const int d1 = e.swap_io ? e.Cout : e.Cin;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total_p; i += gridDim.x * blockDim.x) {
-    // i indexes the workspace [tap][co][ci] (physical dims): coalesced read + reset
     const int ci = i % e.Cin_p;
     const int co = (i / e.Cin_p) % e.Cout_p;
     const int tap = i / (e.Cin_p * e.Cout_p);
@@ -250,9 +253,8 @@ wgrad_unpack_multi_kernel(const PgUnpackEntry *__restrict__ table) {
     if (ci < e.Cin && co < e.Cout) {
       const int st = e.flip ? (e.taps - 1 - tap) : tap;
       const int i0 = e.swap_io ? ci : co, i1 = e.swap_io ? co : ci;
-      const int d1 = e.swap_io ? e.Cout : e.Cin;
-      // two entries (the conv's own and its adjoint form from the GP sweep) may target one dw
-      atomicAdd(e.dw + ((size_t)i0 * d1 + i1) * e.taps + st, e.scale * v);
+      float *dst = e.dw + ((size_t)i0 * d1 + i1) * e.taps + st;
+      *dst += e.scale * v;
     }
   }
 }

@@ -311,19 +311,32 @@ class CudaKernels:
         return dw
 
     def flush_wgrads(self):
-        """Fold every pending weight-gradient workspace into its gradient (one launch)."""
+        """Fold every pending weight-gradient workspace into its gradient: one launch per
+        'round', where a round holds at most one workspace per gradient tensor (a conv's own
+        weight gradient and its adjoint form from the GP sweep go to different rounds, so the
+        kernel's read-modify-write of dw needs no atomics)."""
         if not self._pending:
             return
         sig = tuple(self._pending.keys())
-        tab = self._unpack_tables.get(sig)
-        if tab is None:
+        tabs = self._unpack_tables.get(sig)
+        if tabs is None:
             if torch.cuda.is_current_stream_capturing():
                 raise RuntimeError("progan_b200: unpack table changed during CUDA-graph capture")
-            rows = [e for _, e in self._pending.values()]
+            rounds = []
+            for wkey, (ws, ent) in self._pending.items():
+                for r in rounds:
+                    if wkey[0] not in r[0]:
+                        break
+                else:
+                    r = (set(), [])
+                    rounds.append(r)
+                r[0].add(wkey[0])
+                r[1].append(ent)
             dev = next(iter(self._pending.values()))[0].device
-            tab = (self._upload(rows, _lib.UnpackEntry, dev), len(rows))
-            self._unpack_tables[sig] = tab
-        self._call("pg_wgrad_unpack_multi", tab[0].data_ptr(), tab[1], self._stream())
+            tabs = [(self._upload(rows, _lib.UnpackEntry, dev), len(rows)) for _, rows in rounds]
+            self._unpack_tables[sig] = tabs
+        for tab, n in tabs:
+            self._call("pg_wgrad_unpack_multi", tab.data_ptr(), n, self._stream())
         self._pending.clear()
 
     def mbstd_channels(self, C, dtype):
