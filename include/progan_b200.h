@@ -101,6 +101,18 @@ int pg_conv_tc(const void *x, const void *wp, const float *bias, void *y,
                float *r_out, int N, int H, int W, int Cin, int Cout_total,
                int Cout_tile, int taps, int bias_mod, float scale, int epi,
                float slope, void *stream);
+/* Data-gradient 3x3 conv with the PixelNorm+LeakyReLU backward of the layer in front fused into
+ * the epilogue (replaces aten::convolution_backward(input) followed by the autograd chain of
+ * PixelNorm/LeakyReLU, progan_modules.py:54-60,138):
+ *   dh = scale * conv3x3(x; wp)            x:[N,H,W,Cin] = da of this layer, wp packed adjoint
+ *   da_prev = Jpn(a_prev)^T (m * dh)       (y_prev, r_prev) = stored activation of the layer
+ *                                          in front, [N,H,W,Cout] bf16 / [N,H,W] fp32
+ *   colsum[c] += sum_pix da_prev[pix,c]    (bias gradient of the layer in front) if non-null
+ * Returns PG_ERR_UNSUPPORTED for shapes the fused kernel does not take (H %% 16, W %% 8,
+ * Cout in {32,64,128}, Cin %% 32). */
+int pg_conv_tc_actbwd(const void *x, const void *wp, void *da, int N, int H, int W, int Cin,
+                      int Cout, float scale, const void *y_prev, const float *r_prev,
+                      float slope, int use_pn, float *colsum, void *stream);
 /* weight gradient on tcgen05: dw fp32 (logical dims Cin_log/Cout_log, parameter
  * layout by swap_io/flip) is overwritten; workspace is taps*Cin*Cout floats.
  * flat == 0: 3x3 pad 1 (taps == 9).  flat == 1: x is [N,1,1,taps*Cin] and tap t

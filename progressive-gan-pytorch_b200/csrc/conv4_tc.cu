@@ -37,13 +37,20 @@ struct Conv4Params {
   float scale, slope;
   const float *bias;
   float *r_out;
+  // fused activation backward (ABW kernels): the conv output is dh, the gradient w.r.t. the
+  // activation y_prev = lrelu(pixelnorm(a_prev)); the epilogue turns it into da_prev
+  const __nv_bfloat16 *y_prev;         // [N,H,W,Cout]
+  const float *r_prev;                 // [N,H,W] PixelNorm rsqrt (use_pn) or nullptr
+  float *colsum;                       // += per-channel sum of da_prev (bias gradient) or nullptr
+  int use_pn;
   int dbg;                             // experiment knobs (PG_DBG)
 };
 
-constexpr int kC4Threads = 384;   // 4 control warps + 8 epilogue warps
+constexpr int kC4EpiThreads = 256;                 // 8 epilogue warps: 2 per TMEM lane quadrant
+constexpr int kC4Threads = 128 + kC4EpiThreads;    // + 4 control warps
 constexpr int kC4MaxA = 8, kC4MaxW = 12;
 
-template <int BK, int NCB, int MT, bool RES, int COUT, int CL>
+template <int BK, int NCB, int MT, bool RES, int COUT, int CL, bool ABW>
 __global__ void __launch_bounds__(kC4Threads, 1)
 conv4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                 const __grid_constant__ CUtensorMap tmap_y, const Conv4Params p) {
@@ -71,7 +78,7 @@ conv4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   uint8_t *gbase = smem_raw + (base - smem_u32(smem_raw));
   volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(gbase + (tmem_slot - base));
   float *bias_ptr = reinterpret_cast<float *>(gbase + (bias_s - base));
-  float *ss_buf = bias_ptr + 128;                    // [2][128] partial sums of squares
+  float *ss_buf = bias_ptr + 128;                    // [2][128] partial per-pixel reductions
   uint8_t *out_ptr = gbase + (smem_out - base);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -96,7 +103,7 @@ conv4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull(a), 1);
-      mbar_init(tempty(a), 256);
+      mbar_init(tempty(a), kC4EpiThreads);
     }
     mbar_init(wres_bar, 1);
     fence_barrier_init();
@@ -249,26 +256,62 @@ conv4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   } else if (warp >= 4) {
     // ===================== epilogue (8 warps) =====================
     // Two warps per TMEM lane quadrant, each owning half of the channel columns of its 32
-    // pixels: one tcgen05.ld pass, values stay in registers; the PixelNorm sum of squares is
-    // completed through a 1 KB smem exchange between the two halves.
+    // pixels: one tcgen05.ld pass, values stay in registers; per-pixel reductions over the
+    // channels (PixelNorm sum of squares, <p,u> of the fused backward) are completed through a
+    // 1 KB smem exchange between the two halves.  (16 epilogue warps were measured slower.)
     constexpr int CPT = COUT / 2;                 // columns per thread: 16 / 32 / 64
     constexpr int out_chunk = (COUT % 64 == 0) ? 64 : 32;
     constexpr int chunk_rows_bytes = out_chunk * 2;
     constexpr int swz_bits = chunk_rows_bytes == 128 ? 3 : 2;
     constexpr int n_chunks = COUT / out_chunk;
     const int q = warp & 3;
-    const int half = (warp - 4) >> 2;
+    const int part = (warp - 4) >> 2;             // 0..1
     const int row = q * 32 + lane;                // tile row: pixel (hl = row/8, wl = row%8)
     const int et = threadIdx.x - 128;             // 0..255
-    const int col0 = half * CPT;
+    const int col0 = part * CPT;
     const float invC = 1.f / (float)COUT;
     const float scale = p.scale, slope = p.slope;
     int acc = 0;
     uint32_t acc_phase = 0;
+    const float inv_slope = 1.f / slope;
+    float csum[2] = {0.f, 0.f};                   // ABW: this lane's share of the bias gradient
+    // ABW: this thread's slice of y_prev (and r_prev) for a tile is loaded one tile ahead, right
+    // after the previous tile's arithmetic, and prefetched into L2 two tiles ahead: the HBM
+    // latency hides behind the accumulator wait instead of sitting on the epilogue's critical path
+    uint4 yraw[ABW ? CPT / 8 : 1];
+    float rp = 1.f;
+    auto pix_of = [&](int tile) -> long long {
+      const int tw_ = tile % p.tiles_w;
+      const int th_ = (tile / p.tiles_w) % p.tiles_h;
+      const int n_ = tile / (p.tiles_w * p.tiles_h);
+      return ((long long)n_ * p.H + (th_ * 16 + (row >> 3))) * p.W + tw_ * 8 + (row & 7);
+    };
+    auto next_tile = [&](int sb_, int mt_, int ahead) -> int {     // flat successor, -1 past the end
+      for (int a = 0; a < ahead; ++a) {
+        if (++mt_ == MT) { mt_ = 0; sb_ += ncl * CL; }
+      }
+      return sb_ < p.num_super ? (sb_ + (int)rank) * MT + mt_ : -1;
+    };
+    auto load_y = [&](int tile) {
+      if (tile < 0) return;
+      const long long px = pix_of(tile);
+      const uint4 *yp = reinterpret_cast<const uint4 *>(p.y_prev + px * COUT + col0);
+#pragma unroll
+      for (int i = 0; i < CPT / 8; ++i) yraw[i] = __ldg(yp + i);
+      if (p.use_pn) rp = __ldg(p.r_prev + px);
+    };
+    auto prefetch_y = [&](int tile) {
+      if (tile < 0) return;
+      const char *yp = reinterpret_cast<const char *>(p.y_prev + pix_of(tile) * COUT + col0);
+#pragma unroll
+      for (int b = 0; b < CPT * 2; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(yp + b));
+    };
+    if (ABW) {
+      load_y(next_tile(cid * CL, 0, 0));
+      prefetch_y(next_tile(cid * CL, 0, 1));
+    }
     for (int sb = cid * CL; sb < p.num_super; sb += ncl * CL) {
       const int st = sb + (int)rank;
-      mbar_wait(tfull(acc), acc_phase);
-      tc_fence_after();
 #pragma unroll 1
       for (int mt = 0; mt < MT; ++mt) {
         const int tile = st * MT + mt;
@@ -276,6 +319,12 @@ conv4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         const int th = (tile / p.tiles_w) % p.tiles_h;
         const int n = tile / (p.tiles_w * p.tiles_h);
         const int w0 = tw * 8, h0 = th * 16;
+        const long long pix = ((long long)n * p.H + (h0 + (row >> 3))) * p.W + w0 + (row & 7);
+        if (ABW) prefetch_y(next_tile(sb, mt, 2));
+        if (mt == 0) {
+          mbar_wait(tfull(acc), acc_phase);
+          tc_fence_after();
+        }
         const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) +
                                 (uint32_t)(acc * acc_stride + mt * COUT + col0);
         uint32_t vr[CPT];
@@ -287,24 +336,61 @@ conv4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         }
         if (p.dbg & 2) continue;       // experiment: accumulator drain only
         float v[CPT];
-        float ss = 0.f;
-#pragma unroll
-        for (int j = 0; j < CPT; j += 4) {
-          const float4 b4 = *reinterpret_cast<const float4 *>(bias_ptr + col0 + j);
-          v[j] = fmaf(__uint_as_float(vr[j]), scale, b4.x);
-          v[j + 1] = fmaf(__uint_as_float(vr[j + 1]), scale, b4.y);
-          v[j + 2] = fmaf(__uint_as_float(vr[j + 2]), scale, b4.z);
-          v[j + 3] = fmaf(__uint_as_float(vr[j + 3]), scale, b4.w);
-          ss = fmaf(v[j], v[j], ss);
-          ss = fmaf(v[j + 1], v[j + 1], ss);
-          ss = fmaf(v[j + 2], v[j + 2], ss);
-          ss = fmaf(v[j + 3], v[j + 3], ss);
-        }
         float r = 1.f;
-        if (p.epi == PG_EPI_PN_LRELU) {
-          ss_buf[half * 128 + row] = ss;
-          asm volatile("bar.sync 2, 256;" ::: "memory");
-          r = rsqrtf((ss_buf[row] + ss_buf[128 + row]) * invC + 1e-8f);
+        if (!ABW) {
+          float ss = 0.f;
+#pragma unroll
+          for (int j = 0; j < CPT; j += 4) {
+            const float4 b4 = *reinterpret_cast<const float4 *>(bias_ptr + col0 + j);
+            v[j] = fmaf(__uint_as_float(vr[j]), scale, b4.x);
+            v[j + 1] = fmaf(__uint_as_float(vr[j + 1]), scale, b4.y);
+            v[j + 2] = fmaf(__uint_as_float(vr[j + 2]), scale, b4.z);
+            v[j + 3] = fmaf(__uint_as_float(vr[j + 3]), scale, b4.w);
+            ss = fmaf(v[j], v[j], ss);
+            ss = fmaf(v[j + 1], v[j + 1], ss);
+            ss = fmaf(v[j + 2], v[j + 2], ss);
+            ss = fmaf(v[j + 3], v[j + 3], ss);
+          }
+          if (p.epi == PG_EPI_PN_LRELU) {
+            ss_buf[part * 128 + row] = ss;
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+            r = rsqrtf((ss_buf[row] + ss_buf[128 + row]) * invC + 1e-8f);
+          }
+        } else {
+          // da = r (u - p <p,u>/C), u = m * dh, (p, m) rebuilt from the stored activation
+          float s_pu = 0.f;
+#pragma unroll
+          for (int i = 0; i < CPT / 8; ++i) {
+            const __nv_bfloat162 *h2 = reinterpret_cast<const __nv_bfloat162 *>(&yraw[i]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 yy = __bfloat1622float2(h2[e]);
+              const int j = i * 8 + 2 * e;
+              const float u0 = __uint_as_float(vr[j]) * scale * (yy.x > 0.f ? 1.f : slope);
+              const float u1 = __uint_as_float(vr[j + 1]) * scale * (yy.y > 0.f ? 1.f : slope);
+              s_pu = fmaf(yy.x > 0.f ? yy.x : yy.x * inv_slope, u0, s_pu);
+              s_pu = fmaf(yy.y > 0.f ? yy.y : yy.y * inv_slope, u1, s_pu);
+              v[j] = u0;
+              v[j + 1] = u1;
+            }
+          }
+          if (p.use_pn) {
+            ss_buf[part * 128 + row] = s_pu;
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+            const float k = (ss_buf[row] + ss_buf[128 + row]) * invC;
+#pragma unroll
+            for (int i = 0; i < CPT / 8; ++i) {
+              const __nv_bfloat162 *h2 = reinterpret_cast<const __nv_bfloat162 *>(&yraw[i]);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 yy = __bfloat1622float2(h2[e]);
+                const int j = i * 8 + 2 * e;
+                v[j] = rp * fmaf(-(yy.x > 0.f ? yy.x : yy.x * inv_slope), k, v[j]);
+                v[j + 1] = rp * fmaf(-(yy.y > 0.f ? yy.y : yy.y * inv_slope), k, v[j + 1]);
+              }
+            }
+          }
+          load_y(next_tile(sb, mt, 1));          // yraw / rp are free again: fetch the next tile's
         }
         if (et == 0) tma_store_wait_read0();       // staging buffer free again?
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -318,7 +404,7 @@ conv4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               float a0 = v[i * 8 + 2 * e] * r, a1 = v[i * 8 + 2 * e + 1] * r;
-              if (p.epi != PG_EPI_LINEAR) {
+              if (!ABW && p.epi != PG_EPI_LINEAR) {
                 a0 = a0 > 0.f ? a0 : a0 * slope;
                 a1 = a1 > 0.f ? a1 : a1 * slope;
               }
@@ -330,8 +416,7 @@ conv4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
             *reinterpret_cast<uint4 *>(tile_base + swz(off, swz_bits)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           }
         }
-        if (p.epi == PG_EPI_PN_LRELU && half == 0)
-          p.r_out[((long long)n * p.H + (h0 + (row >> 3))) * p.W + w0 + (row & 7)] = r;
+        if (!ABW && p.epi == PG_EPI_PN_LRELU && part == 0) p.r_out[pix] = r;
         fence_proxy_async_smem();
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (et == 0 && !(p.dbg & 1)) {
@@ -341,8 +426,54 @@ conv4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
                          ch * out_chunk, w0, h0, n);
           tma_store_commit();
         }
+        if (ABW && p.colsum != nullptr) {
+          // per-channel sum over the warp's 32 pixels by a halving butterfly: each step trades
+          // half of the remaining channels with the partner lane (CPT - 1 shuffles in total)
+          int nrem = CPT;
+#pragma unroll
+          for (int off = 16; off >= 1; off >>= 1) {
+            if (nrem >= 2) {
+              const int hn = nrem / 2;
+              const bool up = (lane & off) != 0;
+#pragma unroll
+              for (int j = 0; j < CPT / 2; ++j) {
+                if (j < hn) {
+                  const float send = up ? v[j] : v[j + hn];
+                  const float keep = up ? v[j + hn] : v[j];
+                  v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
+              }
+              nrem = hn;
+            } else {
+              v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+            }
+          }
+          csum[0] += v[0];
+          if (CPT >= 64) csum[1] += v[1];
+        }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+    if (ABW && p.colsum != nullptr) {
+      // channel owned by this lane after the butterfly (bit b of the lane picked the upper half
+      // at the step with offset 2^b)
+      int ch = col0;
+      int hn = CPT / 2;
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) {
+        if (hn >= 1) {
+          if (lane & off) ch += hn;
+          hn >>= 1;
+        }
+      }
+      if (CPT >= 64) {
+        atomicAdd(p.colsum + ch, csum[0]);
+        atomicAdd(p.colsum + ch + 1, csum[1]);
+      } else if (CPT == 32) {
+        atomicAdd(p.colsum + ch, csum[0]);
+      } else if ((lane & 1) == 0) {         // CPT = 16: the last step was a plain add
+        atomicAdd(p.colsum + ch, csum[0]);
+      }
     }
     if (et == 0) tma_store_wait_all();
   }
@@ -356,10 +487,10 @@ conv4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   }
 }
 
-template <int BK, int NCB, int MT, bool RES, int COUT, int CL>
+template <int BK, int NCB, int MT, bool RES, int COUT, int CL, bool ABW>
 static cudaError_t launch_c4(const CUtensorMap &tx, const CUtensorMap &tw, const CUtensorMap &ty,
                              const Conv4Params &p, size_t smem, cudaStream_t stream) {
-  auto kern = conv4_tc_kernel<BK, NCB, MT, RES, COUT, CL>;
+  auto kern = conv4_tc_kernel<BK, NCB, MT, RES, COUT, CL, ABW>;
   static bool attr_set = false;
   static int max_ctas = 0;
   cudaError_t e;
@@ -403,7 +534,9 @@ static cudaError_t launch_c4(const CUtensorMap &tx, const CUtensorMap &tw, const
 // so pg_conv_tc can fall through to the older kernels.
 int conv4_tc_launch(const void *x, const void *wp, const float *bias, void *y, float *r_out, int N,
                     int H, int W, int Cin, int Cout, float scale, int epi, float slope,
-                    cudaStream_t stream) {
+                    cudaStream_t stream, const void *y_prev, const float *r_prev, float *colsum,
+                    int use_pn) {
+  const bool abw = y_prev != nullptr;
   if (const char *e = getenv("PG_CONV_V4"))
     if (atoi(e) == 0) return PG_ERR_UNSUPPORTED;
   int min_h = 16;
@@ -421,6 +554,7 @@ int conv4_tc_launch(const void *x, const void *wp, const float *bias, void *y, f
   p.box_pad = (box_real + 1023) / 1024 * 1024;
   p.wtile_bytes = Cout * BK * 2;
   p.epi = epi; p.scale = scale; p.slope = slope; p.bias = bias; p.r_out = r_out;
+  p.y_prev = (const __nv_bfloat16 *)y_prev; p.r_prev = r_prev; p.colsum = colsum; p.use_pn = use_pn;
   p.dbg = 0;
   if (const char *e = getenv("PG_DBG")) p.dbg = atoi(e);
   const int out_bytes = 128 * Cout * 2;
@@ -489,7 +623,8 @@ int conv4_tc_launch(const void *x, const void *wp, const float *bias, void *y, f
   if (!matched && BK == BK_ && p.ncb == NCB_ && MT == MT_ && res == (RES_ ? 1 : 0) && Cout == CO_ && \
       CL == CL_) {                                                                               \
     matched = true;                                                                              \
-    e = tc::launch_c4<BK_, NCB_, MT_, RES_, CO_, CL_>(tx, tw_, ty, p, smem, stream);             \
+    e = abw ? tc::launch_c4<BK_, NCB_, MT_, RES_, CO_, CL_, true>(tx, tw_, ty, p, smem, stream)  \
+            : tc::launch_c4<BK_, NCB_, MT_, RES_, CO_, CL_, false>(tx, tw_, ty, p, smem, stream); \
   }
 #define PG_C4_RESIDENT(BK_, NCB_, CO_)                                                           \
   PG_C4_TRY(BK_, NCB_, 1, true, CO_, 1) PG_C4_TRY(BK_, NCB_, 2, true, CO_, 1)

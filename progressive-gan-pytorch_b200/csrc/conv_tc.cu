@@ -431,3 +431,23 @@ extern "C" int pg_conv_tc(const void *x, const void *wp, const float *bias, void
   tc::conv_tc_kernel<<<grid, tc::kThreads, smem, (cudaStream_t)stream>>>(tx, tw_, ty, p);
   PG_CHECK_LAUNCH("pg_conv_tc");
 }
+
+// data-gradient conv with the activation backward of the PREVIOUS layer fused into the epilogue
+extern "C" int pg_conv_tc_actbwd(const void *x, const void *wp, void *da, int N, int H, int W,
+                                 int Cin, int Cout, float scale, const void *y_prev,
+                                 const float *r_prev, float slope, int use_pn, float *colsum,
+                                 void *stream) {
+  PG_CHECK_ARG(x && wp && da && y_prev, "pg_conv_tc_actbwd: null pointer");
+  PG_CHECK_ARG(!use_pn || r_prev, "pg_conv_tc_actbwd: PixelNorm form needs r_prev");
+  PG_CHECK_ARG(slope > 0.f, "pg_conv_tc_actbwd: slope must be > 0");
+  PG_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)wp & 15) == 0 && ((uintptr_t)da & 15) == 0 &&
+                   ((uintptr_t)y_prev & 15) == 0,
+               "pg_conv_tc_actbwd: pointers must be 16-byte aligned");
+  const int rc = conv4_tc_launch(x, wp, nullptr, da, nullptr, N, H, W, Cin, Cout, scale,
+                                 PG_EPI_LINEAR, slope, (cudaStream_t)stream, y_prev, r_prev, colsum,
+                                 use_pn);
+  if (rc == PG_ERR_UNSUPPORTED)
+    set_error("pg_conv_tc_actbwd: shape N=%d H=%d W=%d Cin=%d Cout=%d is not served by the fused "
+              "kernel (use pg_conv_tc + pg_pn_lrelu_bwd)", N, H, W, Cin, Cout);
+  return rc;
+}

@@ -189,6 +189,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 template <int N>
 __device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t *v);
 template <>
+__device__ __forceinline__ void tmem_ld<8>(uint32_t taddr, uint32_t *v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7])
+      : "r"(taddr)
+      : "memory");
+}
+template <>
 __device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, uint32_t *v) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -278,7 +287,8 @@ int conv3_tc_launch(const void *x, const void *wp, const float *bias, void *y, f
 // cluster multicast of streamed weights; PG_ERR_UNSUPPORTED when the shape is not eligible
 int conv4_tc_launch(const void *x, const void *wp, const float *bias, void *y, float *r_out, int N,
                     int H, int W, int Cin, int Cout, float scale, int epi, float slope,
-                    cudaStream_t stream);
+                    cudaStream_t stream, const void *y_prev = nullptr, const float *r_prev = nullptr,
+                    float *colsum = nullptr, int use_pn = 0);
 
 // second-generation weight-gradient kernel (wgrad3_tc.cu); workspace pre-zeroed by the caller
 int wgrad3_tc_launch(const void *x, const void *dy, float *workspace, int N, int H, int W, int Cin,

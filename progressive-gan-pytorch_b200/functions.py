@@ -55,6 +55,21 @@ def _direct_target(p):
     return None
 
 
+class ActLink:
+    """Ties an Act node to the ONE conv that consumes its output (the second conv of a
+    ConvBlock).  In a plain (non-create_graph) backward that conv's data-gradient kernel applies
+    this activation's backward in its epilogue and sets `fused`; the Act node then passes the
+    incoming gradient through unchanged."""
+    __slots__ = ("A", "r", "slope", "use_pn", "bias", "fused")
+
+    def __init__(self, A, r, slope, use_pn, bias):
+        self.A, self.r, self.slope, self.use_pn, self.bias = A, r, slope, use_pn, bias
+        self.fused = False
+
+
+FUSE_ACT_BWD = True
+
+
 def _wants_grad(ctx, idx, t):
     """needs_input_grad refined by the engine's execution plan: for
     autograd.grad(inputs=[x_hat]) / backward(inputs=G.parameters()) the weight-gradient
@@ -135,8 +150,9 @@ class ConvAct(Function):
     Returns (A, r): A carries y's data but stands for the pre-activation in the graph."""
 
     @staticmethod
-    def forward(ctx, x, w, b, op, scale, slope, use_pn):
+    def forward(ctx, x, w, b, op, scale, slope, use_pn, prev_link=None):
         ctx.op, ctx.scale = op, scale
+        ctx.prev_link = prev_link
         ctx.save_for_backward(x, w, b)
         ctx.set_materialize_grads(False)     # r never gets a gradient: no zero-fill per backward
         y, r = K().conv_fwd(x, w, b, op, scale, EPI_PN_LRELU if use_pn else EPI_LRELU, slope)
@@ -148,12 +164,25 @@ class ConvAct(Function):
     @staticmethod
     def backward(ctx, dA, _dr):
         if dA is None:
-            return (None,) * 7
+            return (None,) * 8
         x, w, b = ctx.saved_tensors
         dA = dA.contiguous()
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = ConvFwd.apply(dA, w, ctx.op.adjoint(), ctx.scale)
+            link = ctx.prev_link
+            fused = getattr(K(), "conv_dgrad_actbwd", None)
+            if link is not None and fused is not None and FUSE_ACT_BWD and not torch.is_grad_enabled():
+                # plain backward: this data-gradient kernel also applies the backward of the
+                # activation in front (and its bias gradient), see ActLink
+                want_b = _bias_wanted(link.bias)
+                tgt_b = _direct_target(link.bias) if want_b else None
+                if not want_b or tgt_b is not None:
+                    dx = fused(dA, w, ctx.op.adjoint(), ctx.scale, link.A, link.r if link.use_pn else None,
+                               link.slope, link.use_pn, tgt_b)
+                    if dx is not None:
+                        link.fused = True
+            if dx is None:
+                dx = ConvFwd.apply(dA, w, ctx.op.adjoint(), ctx.scale)
         if _wants_grad(ctx, 1, w):
             tgt = _direct_target(w)
             if tgt is not None:
@@ -165,7 +194,7 @@ class ConvAct(Function):
                 pass          # direct mode: accumulated by the Act/ActBwd kernels that produced dA
             else:
                 db = ColSum.apply(dA)
-        return dx, dw, db, None, None, None, None
+        return dx, dw, db, None, None, None, None, None
 
 
 def _bias_wanted(bias):
@@ -188,8 +217,9 @@ class Act(Function):
     gradient (column sum of dA) is produced there, fused into those kernels."""
 
     @staticmethod
-    def forward(ctx, A, r, slope, use_pn, pool, bias):
+    def forward(ctx, A, r, slope, use_pn, pool, bias, link=None):
         ctx.slope, ctx.use_pn, ctx.pool, ctx.bias = slope, use_pn, pool, bias
+        ctx.link = link
         ctx.save_for_backward(A, r)
         if pool:
             return K().avgpool2(A, "nhwc")
@@ -197,10 +227,14 @@ class Act(Function):
 
     @staticmethod
     def backward(ctx, dy):
+        link = ctx.link
+        if link is not None and link.fused:
+            link.fused = False         # dy already is da: the consumer's kernel did our work
+            return dy, None, None, None, None, None, None
         A, r = ctx.saved_tensors
         direct = DIRECT_GRADS and not torch.is_grad_enabled()
         da = ActBwd.apply(dy.contiguous(), A, r, ctx.slope, ctx.use_pn, ctx.pool, ctx.bias, direct)
-        return da, None, None, None, None, None
+        return da, None, None, None, None, None, None
 
 
 class ActBwd(Function):
@@ -233,9 +267,13 @@ class ActBwd(Function):
         return cot_dy, cot_a, None, None, None, None, None, None
 
 
-def conv_act(x, w, b, op, scale, slope=0.2, use_pn=True, pool=False):
-    A, r = ConvAct.apply(x, w, b, op, scale, slope, use_pn)
-    return Act.apply(A, r, slope, use_pn, pool, b)
+def conv_act(x, w, b, op, scale, slope=0.2, use_pn=True, pool=False, prev_link=None, make_link=False):
+    """conv + bias + [PixelNorm] + LeakyReLU (+ 2x2 average pool).  make_link: also return the
+    ActLink for the single conv that will consume the result (pass it there as prev_link)."""
+    A, r = ConvAct.apply(x, w, b, op, scale, slope, use_pn, prev_link)
+    link = ActLink(A, r, slope, use_pn, b) if (make_link and not pool) else None
+    y = Act.apply(A, r, slope, use_pn, pool, b, link)
+    return (y, link) if make_link else y
 
 
 # ---------------------------------------------------------------------- 1x1 heads

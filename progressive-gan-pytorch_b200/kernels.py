@@ -95,6 +95,10 @@ class CudaKernels:
         self.launches = 0              # kernels launched through this shim (bench `gpu_launches`)
         self._packs = {}               # id(param) -> [weakref, version, {variant: (tensor, pack args)}]
         self._pack_tables = {}         # ids of a parameter set -> (signature, device table, n)
+        # measured (profiles/dbg_actbwd.py): in isolation the fused epilogue wins for 128 output
+        # channels (long MMA phase per tile) and loses for <= 64 (the 8 epilogue warps become the
+        # bottleneck)
+        self.fuse_actbwd_min_cout = 1 << 30      # ... and in the whole step neither pays: off
         self.defer_wgrad = False       # Trainer: weight gradients accumulate in persistent workspaces
         self._wgrad_ws = {}            # (grad ptr, variant) -> (workspace, unpack entry)
         self._pending = {}             # workspaces holding partial sums since the last flush
@@ -243,6 +247,39 @@ class CudaKernels:
                        _ptr(r), N, H, W, cin, cout, k, op.pad, float(scale), epi, float(slope),
                        _dt(x), st)
         return y, r
+
+    def conv_dgrad_actbwd(self, x, w, op, scale, y_prev, r_prev, slope, use_pn, colsum_out=None):
+        """Fused da_prev = Jpn(a_prev)^T (m * (scale * conv(x; Wl(w)))): a data-gradient conv whose
+        epilogue applies the PixelNorm+LeakyReLU backward of the layer in front (stored activation
+        y_prev, statistic r_prev) and adds the per-channel sum of da_prev to colsum_out (that
+        layer's bias gradient).  Returns None when the fused kernel does not take the shape."""
+        if x.dtype != torch.bfloat16 or op.xpad or op.ypad:
+            return None
+        N, H, W, C = x.shape
+        if self.tc_mode(x.dtype, H, W, w.shape, op) != "conv3" or H % 16 or W % 8:
+            return None
+        cin, cout = op.cin_phys(w.shape), op.cout_phys(w.shape)
+        if cout not in (32, 64, 128) or C != cin or tuple(y_prev.shape) != (N, H, W, cout):
+            return None
+        if cout < self.fuse_actbwd_min_cout:
+            return None
+        _chk(x, "x", torch.bfloat16, 4)
+        _chk(y_prev, "y_prev", torch.bfloat16, 4)
+        if use_pn:
+            _chk(r_prev, "r_prev", torch.float32)
+        if colsum_out is not None:
+            _chk(colsum_out, "colsum_out", torch.float32, 1)
+        wp = self.packed(w, op, WL_CO_TAP_CI, torch.bfloat16)
+        da = torch.empty((N, H, W, cout), device=x.device, dtype=x.dtype)
+        try:
+            self._call("pg_conv_tc_actbwd", x.data_ptr(), wp.data_ptr(), da.data_ptr(), N, H, W, cin, cout,
+                       float(scale), y_prev.data_ptr(), _ptr(r_prev) if use_pn else None,
+                       float(slope), int(use_pn), _ptr(colsum_out), self._stream())
+        except RuntimeError as e:
+            if "(-3)" in str(e):       # PG_ERR_UNSUPPORTED: caller runs the two-kernel path
+                return None
+            raise
+        return da
 
     def conv_wgrad(self, x, dy, wshape, op, scale, out=None):
         """dw[wshape] = scale * sum_pix dy (x) x for the conv `op` (fp32).  out: accumulate into

@@ -91,12 +91,12 @@ class _LeakyMarker(nn.Module):
         self.negative_slope = slope
 
 
-def _fused_layer(x, conv, slope, use_pn, pool=False):
+def _fused_layer(x, conv, slope, use_pn, pool=False, prev_link=None, make_link=False):
     h = conv.conv
     op = conv.op
     if x.shape[-1] != conv.cin:       # zero-padded input channels (after minibatch-stddev)
         op = ConvOp(op.k, op.pad, op.swap, op.flip, x.shape[-1], 0)
-    return F_.conv_act(x, h.weight_orig, h.bias, op, conv.scale, slope, use_pn, pool)
+    return F_.conv_act(x, h.weight_orig, h.bias, op, conv.scale, slope, use_pn, pool, prev_link, make_link)
 
 
 class ConvBlock(nn.Module):
@@ -124,8 +124,10 @@ class ConvBlock(nn.Module):
     def forward(self, x, pool=False):
         """pool=True: followed by the x0.5 bilinear (= 2x2 average) downsample of the
         discriminator (progan_modules.py:299); its backward is fused with the activation's."""
-        x = _fused_layer(x, self.conv[self._c1], 0.2, self.pixel_norm)
-        return _fused_layer(x, self.conv[self._c2], 0.2, self.pixel_norm, pool)
+        # the first activation has exactly one consumer (the second conv): its backward is fused
+        # into that conv's data-gradient kernel (functions.ActLink)
+        x, link = _fused_layer(x, self.conv[self._c1], 0.2, self.pixel_norm, make_link=True)
+        return _fused_layer(x, self.conv[self._c2], 0.2, self.pixel_norm, pool, prev_link=link)
 
 
 class _AlphaMixin:

@@ -314,3 +314,38 @@ def test_gp_and_optim(KE):
     y = K.tanh_fwd(x)
     assert helpers.rel(y, torch.tanh(x)) < 1e-6
     assert helpers.rel(K.tanh_bwd(x, y), x * (1 - y * y)) < 1e-6
+
+
+@pytest.mark.parametrize("cfg", [
+    # N, H, W, Cin, Cout  (Cout = channels of the activation whose backward is fused)
+    (2, 32, 32, 64, 64), (1, 64, 64, 64, 32), (3, 16, 16, 128, 128), (2, 32, 32, 128, 64),
+    (5, 128, 128, 64, 64), (2, 64, 64, 32, 64), (10, 64, 64, 128, 128),
+])
+@pytest.mark.parametrize("use_pn", [True, False])
+def test_conv_dgrad_actbwd_fused_matches_two_kernels(KE, cfg, use_pn):
+    """The data-gradient conv with the fused PixelNorm+LeakyReLU backward epilogue (+ bias
+    gradient) against the unfused pair pg_conv_tc -> pg_pn_lrelu_bwd on the same operands."""
+    K, E = KE
+    K.conv_impl = "tc"
+    N, H, W, Cin, Cout = cfg
+    op = ConvOp(3, 1, True, True)                 # adjoint form, as in a data-gradient
+    x = rnd(N, H, W, Cin, dtype=torch.bfloat16)
+    w = torch.nn.Parameter(rnd(Cin, Cout, 3, 3, seed=1))
+    scale = (2.0 / (Cout * 9)) ** 0.5
+    a_prev = rnd(N, H, W, Cout, seed=3)
+    r_prev = torch.rsqrt((a_prev ** 2).mean(-1) + 1e-8) if use_pn else None
+    pnorm = a_prev * r_prev.unsqueeze(-1) if use_pn else a_prev
+    y_prev = torch.where(pnorm > 0, pnorm, 0.2 * pnorm).to(torch.bfloat16)
+    cs = torch.zeros(Cout, device=DEV)
+    K.fuse_actbwd_min_cout = 32
+    da = K.conv_dgrad_actbwd(x, w, op, scale, y_prev, r_prev, 0.2, use_pn, cs)
+    K.fuse_actbwd_min_cout = 1 << 30
+    assert da is not None
+    dh, _ = K.conv_fwd(x, w, None, op, scale, EPI_LINEAR)
+    cs_ref = torch.zeros(Cout, device=DEV)
+    da_ref, _ = K.pn_lrelu_bwd(dh, y_prev, r_prev, 0.2, use_pn, False, False, cs_ref)
+    torch.cuda.synchronize()
+    # the fused path skips one bf16 rounding (dh stays fp32), so it is the more accurate one
+    assert helpers.rel(da, da_ref) < 8e-3
+    assert helpers.rel(cs, cs_ref) < 8e-3
+    K.conv_impl = "simt"

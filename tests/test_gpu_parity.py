@@ -224,11 +224,12 @@ def test_per_layer_taps(precision):
         taps = []
         orig = F_.conv_act
 
-        def tapped(*a, **k):
-            pool = k.pop("pool", False) or (len(a) > 7 and a[7])
-            y = orig(*a[:7], **k)                 # tap the activation before the fused pool
+        def tapped(x, w, b, op, scale, slope=0.2, use_pn=True, pool=False, prev_link=None, make_link=False):
+            res = orig(x, w, b, op, scale, slope, use_pn, False, prev_link, make_link)
+            y = res[0] if make_link else res      # tap the activation before the fused pool
             taps.append(y.detach().float().permute(0, 3, 1, 2))
-            return F_.avgpool2(y) if pool else y
+            y2 = F_.avgpool2(y) if pool else y
+            return (y2, res[1]) if make_link else y2
         F_.conv_act = tapped
         try:
             D(inp["real"].to(DEV), step=3, alpha=0.25)
