@@ -294,4 +294,9 @@ int conv4_tc_launch(const void *x, const void *wp, const float *bias, void *y, f
 int wgrad3_tc_launch(const void *x, const void *dy, float *workspace, int N, int H, int W, int Cin,
                      int Cout, cudaStream_t stream);
 
+
+// third-generation weight-gradient kernel (wgrad4_tc.cu): single halo box, paired taps
+int wgrad4_tc_launch(const void *x, const void *dy, float *workspace, int N, int H, int W, int Cin,
+                     int Cout, cudaStream_t stream);
+
 }  // namespace pg

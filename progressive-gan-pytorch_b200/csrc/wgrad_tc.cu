@@ -364,8 +364,10 @@ extern "C" int pg_conv_wgrad_tc(const void *x, const void *dy, float *dw, float 
     }
   }
   int rc2 = PG_ERR_UNSUPPORTED;
-  if (!flat && taps == 9)   // second-generation kernel where the shape allows
-    rc2 = wgrad3_tc_launch(x, dy, workspace, N, H, W, Cin, Cout, s);
+  if (!flat && taps == 9) {  // newer kernel generations where the shape allows
+    rc2 = wgrad4_tc_launch(x, dy, workspace, N, H, W, Cin, Cout, s);
+    if (rc2 == PG_ERR_UNSUPPORTED) rc2 = wgrad3_tc_launch(x, dy, workspace, N, H, W, Cin, Cout, s);
+  }
   if (rc2 != PG_OK && rc2 != PG_ERR_UNSUPPORTED) return rc2;
   if (rc2 == PG_ERR_UNSUPPORTED) {
     int gx = sm_count() / passes;
