@@ -140,10 +140,12 @@ int pg_wgrad_unpack_multi(const PgUnpackEntry *table, int n, void *stream);
  * y is the stored post-activation, r the stored per-pixel rsqrt.            */
 /* pool_h/pool_w != 0: dy is the gradient of the 2x2-average-pooled activation
  * ([N,H/2,W/2,C]); the x1/4 expansion (avgpool backward) is fused.  colsum (nullable, fp32
- * [C], zero-initialised) += per-channel sum of da = bias gradient of the conv in front. */
+ * [C], zero-initialised) += per-channel sum of da = bias gradient of the conv in front.
+ * addend (nullable, [P,C]): a second gradient contribution to the same pre-activation (the
+ * PixelNorm Hessian term of the GP sweep); da = backward(dy) + addend, colsum covers both. */
 int pg_pn_lrelu_bwd(const void *dy, const void *y, const float *r, void *da,
                     long long P, int C, float slope, int use_pn, int pool_h, int pool_w,
-                    float *colsum, int dtype, void *stream);
+                    float *colsum, const void *addend, int dtype, void *stream);
 /* second order (WGAN-GP, train.py:146-151): given t = cotangent of da,
  * cot_dy = M Jpn t ;  cot_a = d/da <t, Jpn(a) M dy>                          */
 int pg_pn_lrelu_bwd_bwd(const void *t, const void *dy, const void *y, const float *r,

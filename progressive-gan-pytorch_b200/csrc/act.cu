@@ -22,14 +22,15 @@ __device__ __forceinline__ float subwarp_sum(float v) {
 // reference's bilinear x0.5, progan_modules.py:299) and is expanded on the fly (x 1/4), which
 // fuses avgpool2_bwd into this kernel.  colsum != nullptr (first order only): the per-channel
 // sum of the produced da — the bias gradient of the conv in front — is accumulated too.
-template <typename T, int TPP, int MAXI, bool SECOND, int U>
+template <typename T, int TPP, int MAXI, bool SECOND, int U, bool ADD>
 __global__ void __launch_bounds__(256, 3)
 pn_lrelu_grad_kernel(const T *__restrict__ t_in, const T *__restrict__ dy,
                      const T *__restrict__ y, const float *__restrict__ rr,
                      T *__restrict__ out0, T *__restrict__ out1, long long P, int C,
                      float slope, int use_pn, int pool_h, int pool_w,
                      float *__restrict__ colsum) {
-  // first order : out0 = da                 (t_in unused)
+  // first order : out0 = da (+ t_in when ADD: a second gradient contribution to the same
+  //               pre-activation, summed here instead of by a separate add kernel)
   // second order: out0 = cot_dy, out1 = cot_a
   using Raw = typename RawOf<T>::type;
   const int sub = threadIdx.x % TPP;
@@ -71,7 +72,7 @@ pn_lrelu_grad_kernel(const T *__restrict__ t_in, const T *__restrict__ dy,
           } else {
             rd[u][i] = ldraw8(dy + off);
           }
-          if (SECOND) rt[u][i] = ldraw8(t_in + off);
+          if (SECOND || ADD) rt[u][i] = ldraw8(t_in + off);
         }
       }
       if (use_pn && live) rv[u] = rr[pix];
@@ -91,7 +92,7 @@ pn_lrelu_grad_kernel(const T *__restrict__ t_in, const T *__restrict__ dy,
         if (live && ch < nch) {
           const F8 yv = unpack8(ry[u][i]);
           const F8 dv = unpack8(rd[u][i]);
-          if (SECOND) tv[i] = unpack8(rt[u][i]);
+          if (SECOND || ADD) tv[i] = unpack8(rt[u][i]);
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const bool pos = yv.v[e] > 0.f;
@@ -127,6 +128,7 @@ pn_lrelu_grad_kernel(const T *__restrict__ t_in, const T *__restrict__ dy,
             const float p = pv[i].v[e], uu = uv[i].v[e];
             if (!SECOND) {
               o0.v[e] = use_pn ? r * (uu - p * s_pu * invC) : uu;
+              if (ADD) o0.v[e] += tv[i].v[e];
               csum[i][e] += o0.v[e];
             } else {
               const float t = tv[i].v[e];
@@ -178,8 +180,12 @@ static int launch_pn_grad(const T *t, const T *dy, const T *y, const float *r, T
     constexpr int U_ = (MAXI == 1) ? (SECOND ? 2 : 4) : 1;                                 \
     const int grid = bw_grid(P, (int)ppb * U_);                                           \
     const size_t sm = (!SECOND && colsum) ? (size_t)ppb * C * sizeof(float) : 0;          \
-    pn_lrelu_grad_kernel<T, TPP, MAXI, SECOND, U_><<<grid, 256, sm, s>>>(                 \
-        t, dy, y, r, o0, o1, P, C, slope, use_pn, pool_h, pool_w, colsum);                \
+    if (!SECOND && t != nullptr)                                                          \
+      pn_lrelu_grad_kernel<T, TPP, MAXI, false, U_, true><<<grid, 256, sm, s>>>(          \
+          t, dy, y, r, o0, o1, P, C, slope, use_pn, pool_h, pool_w, colsum);              \
+    else                                                                                  \
+      pn_lrelu_grad_kernel<T, TPP, MAXI, SECOND, U_, false><<<grid, 256, sm, s>>>(        \
+          t, dy, y, r, o0, o1, P, C, slope, use_pn, pool_h, pool_w, colsum);              \
   }
   if (nch <= 4) PG_LAUNCH_PN(4, 1)
   else if (nch <= 8) PG_LAUNCH_PN(8, 1)
@@ -238,7 +244,8 @@ static void pg_encode_pool(int *h, int *w) {
 
 extern "C" int pg_pn_lrelu_bwd(const void *dy, const void *y, const float *r, void *da,
                                long long P, int C, float slope, int use_pn, int pool_h,
-                               int pool_w, float *colsum, int dtype, void *stream) {
+                               int pool_w, float *colsum, const void *addend, int dtype,
+                               void *stream) {
   PG_CHECK_ARG((pool_h == 0) == (pool_w == 0) && pool_h % 2 == 0 && pool_w % 2 == 0,
                "pg_pn_lrelu_bwd: pooled form needs even H and W");
   PG_CHECK_ARG(pool_w == 0 || P % ((long long)pool_h * pool_w) == 0, "pg_pn_lrelu_bwd: P is not N*H*W");
@@ -248,7 +255,7 @@ extern "C" int pg_pn_lrelu_bwd(const void *dy, const void *y, const float *r, vo
   PG_CHECK_ARG(P > 0 && C > 0 && C % 8 == 0, "pg_pn_lrelu_bwd: need C %% 8 == 0 (C=%d)", C);
   PG_CHECK_ARG(slope > 0.f, "pg_pn_lrelu_bwd: slope must be > 0");
   PG_DISPATCH_DTYPE(dtype, T, {
-    int rc = launch_pn_grad<T, false>(nullptr, (const T *)dy, (const T *)y, r, (T *)da, nullptr,
+    int rc = launch_pn_grad<T, false>((const T *)addend, (const T *)dy, (const T *)y, r, (T *)da, nullptr,
                                       P, C, slope, use_pn, pool_h, pool_w, colsum,
                                       (cudaStream_t)stream);
     if (rc) return rc;

@@ -11,10 +11,13 @@ namespace pg {
 
 constexpr int kMaxK = 4;
 
-template <typename T>
+// I = index type of the pixel arithmetic: unsigned (one 32-bit division per element; the 64-bit
+// divisions of the generic form made these kernels ALU-bound at ~25% of HBM bandwidth) or
+// long long for tensors with more than 2^31 elements.
+template <typename T, typename I>
 __global__ void __launch_bounds__(256)
 pw_expand_kernel(const float *__restrict__ img, const float *__restrict__ w,
-                 const float *__restrict__ bias, T *__restrict__ act, int N, long long HW,
+                 const float *__restrict__ bias, T *__restrict__ act, int N, I HW,
                  int K, int C, int w_sc, int w_sk, float scale) {
   extern __shared__ float sw[];  // [K][C] then bias[C]
   float *sb = sw + K * C;
@@ -24,17 +27,17 @@ pw_expand_kernel(const float *__restrict__ img, const float *__restrict__ w,
   }
   for (int c = threadIdx.x; c < C; c += blockDim.x) sb[c] = bias ? bias[c] : 0.f;
   __syncthreads();
-  const int nch = C >> 3;
-  const long long total = (long long)N * HW * nch;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int cj = (int)(i % nch);
-    const long long pix = i / nch;
-    const long long n = pix / HW, hw = pix - n * HW;
+  const I nch = (I)(C >> 3);
+  const I total = (I)N * HW * nch;
+  for (I i = (I)blockIdx.x * (I)blockDim.x + (I)threadIdx.x; i < total;
+       i += (I)gridDim.x * (I)blockDim.x) {
+    const I pix = i / nch;
+    const int cj = (int)(i - pix * nch);
+    const I n = pix / HW, hw = pix - n * HW;
     float xin[kMaxK];
 #pragma unroll
     for (int k = 0; k < kMaxK; ++k)
-      xin[k] = (k < K) ? img[(n * K + k) * HW + hw] : 0.f;
+      xin[k] = (k < K) ? img[((long long)n * K + k) * (long long)HW + (long long)hw] : 0.f;
     F8 o;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -45,14 +48,14 @@ pw_expand_kernel(const float *__restrict__ img, const float *__restrict__ w,
         if (k < K) v = fmaf(xin[k], sw[k * C + c], v);
       o.v[e] = v;
     }
-    st8(act + pix * C + (long long)cj * 8, o);
+    st8(act + (long long)pix * C + (long long)cj * 8, o);
   }
 }
 
-template <typename T, int TPP>
+template <typename T, int TPP, typename I>
 __global__ void __launch_bounds__(256)
 pw_reduce_kernel(const T *__restrict__ act, const float *__restrict__ w,
-                 const float *__restrict__ bias, float *__restrict__ img, int N, long long HW,
+                 const float *__restrict__ bias, float *__restrict__ img, int N, I HW,
                  int K, int C, int w_sc, int w_sk, float scale) {
   extern __shared__ float sw[];  // [K][C]
   for (int i = threadIdx.x; i < K * C; i += blockDim.x) {
@@ -61,16 +64,16 @@ pw_reduce_kernel(const T *__restrict__ act, const float *__restrict__ w,
   }
   __syncthreads();
   const int sub = threadIdx.x % TPP;
-  const long long ppb = blockDim.x / TPP;
+  const I ppb = (I)(blockDim.x / TPP);
   const int nch = C >> 3;
-  const long long P = (long long)N * HW;
-  const long long Pr = ((P + ppb - 1) / ppb) * ppb;
-  for (long long pix = blockIdx.x * ppb + threadIdx.x / TPP; pix < Pr;
-       pix += (long long)gridDim.x * ppb) {
+  const I P = (I)N * HW;
+  const I Pr = ((P + ppb - 1) / ppb) * ppb;
+  for (I pix = (I)blockIdx.x * ppb + (I)(threadIdx.x / TPP); pix < Pr;
+       pix += (I)gridDim.x * ppb) {
     float acc[kMaxK] = {0.f, 0.f, 0.f, 0.f};
     if (pix < P) {
       for (int ch = sub; ch < nch; ch += TPP) {
-        F8 v = ld8(act + pix * C + (long long)ch * 8);
+        F8 v = ld8(act + (long long)pix * C + (long long)ch * 8);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const int c = ch * 8 + e;
@@ -86,39 +89,38 @@ pw_reduce_kernel(const T *__restrict__ act, const float *__restrict__ w,
       for (int o = TPP / 2; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
     }
     if (pix < P && sub == 0) {
-      const long long n = pix / HW, hw = pix - n * HW;
+      const I n = pix / HW, hw = pix - n * HW;
 #pragma unroll
       for (int k = 0; k < kMaxK; ++k)
-        if (k < K) img[(n * K + k) * HW + hw] = acc[k] + (bias ? bias[k] : 0.f);
+        if (k < K) img[((long long)n * K + k) * (long long)HW + (long long)hw] = acc[k] + (bias ? bias[k] : 0.f);
     }
   }
 }
 
 // dw(c,k) += scale * sum_pix act[pix,c] * img[k,pix]
-template <typename T>
+template <typename T, typename I>
 __global__ void __launch_bounds__(256)
 pw_wgrad_kernel(const T *__restrict__ act, const float *__restrict__ img,
-                float *__restrict__ dw, int N, long long HW, int K, int C, int w_sc, int w_sk,
+                float *__restrict__ dw, int N, I HW, int K, int C, int w_sc, int w_sk,
                 float scale) {
   extern __shared__ float sm[];  // [rows][K][C]
   const int nch = C >> 3;
   const int rows = blockDim.x / nch;
   const int cj = threadIdx.x % nch, rj = threadIdx.x / nch;
-  const long long P = (long long)N * HW;
+  const I P = (I)N * HW;
   float acc[kMaxK][8];
 #pragma unroll
   for (int k = 0; k < kMaxK; ++k)
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[k][e] = 0.f;
   if (rj < rows) {
-    for (long long pix = (long long)blockIdx.x * rows + rj; pix < P;
-         pix += (long long)gridDim.x * rows) {
-      const long long n = pix / HW, hw = pix - n * HW;
-      F8 v = ld8(act + pix * C + (long long)cj * 8);
+    for (I pix = (I)blockIdx.x * (I)rows + (I)rj; pix < P; pix += (I)gridDim.x * (I)rows) {
+      const I n = pix / HW, hw = pix - n * HW;
+      F8 v = ld8(act + (long long)pix * C + (long long)cj * 8);
 #pragma unroll
       for (int k = 0; k < kMaxK; ++k) {
         if (k < K) {
-          const float g = img[(n * K + k) * HW + hw];
+          const float g = img[((long long)n * K + k) * (long long)HW + (long long)hw];
 #pragma unroll
           for (int e = 0; e < 8; ++e) acc[k][e] = fmaf(v.v[e], g, acc[k][e]);
         }
@@ -176,8 +178,15 @@ extern "C" int pg_pw_expand(const float *img, const float *w, const float *bias,
   const long long total = (long long)N * HW * (C / 8);
   const int grid = bw_grid(total, 256);
   const size_t smem = (size_t)(K + 1) * C * sizeof(float);
-  PG_DISPATCH_DTYPE(dtype, T, pw_expand_kernel<T><<<grid, 256, smem, (cudaStream_t)stream>>>(
-                                  img, w, bias, (T *)act, N, HW, K, C, w_sc, w_sk, scale));
+  const bool small = total + (long long)grid * 256 < (1ll << 31);
+  PG_DISPATCH_DTYPE(dtype, T, {
+    if (small)
+      pw_expand_kernel<T, unsigned><<<grid, 256, smem, (cudaStream_t)stream>>>(
+          img, w, bias, (T *)act, N, (unsigned)HW, K, C, w_sc, w_sk, scale);
+    else
+      pw_expand_kernel<T, long long><<<grid, 256, smem, (cudaStream_t)stream>>>(
+          img, w, bias, (T *)act, N, HW, K, C, w_sc, w_sk, scale);
+  });
   PG_CHECK_LAUNCH("pg_pw_expand");
 }
 
@@ -193,8 +202,12 @@ extern "C" int pg_pw_reduce(const void *act, const float *w, const float *bias, 
 #define PG_LAUNCH_PWR(TPP)                                                                  \
   {                                                                                         \
     const int grid = bw_grid(P, 256 / TPP);                                                 \
-    pw_reduce_kernel<T, TPP><<<grid, 256, smem, s>>>((const T *)act, w, bias, img, N, HW, K, \
-                                                     C, w_sc, w_sk, scale);                 \
+    if (P + (long long)grid * 256 < (1ll << 31))                                            \
+      pw_reduce_kernel<T, TPP, unsigned><<<grid, 256, smem, s>>>(                           \
+          (const T *)act, w, bias, img, N, (unsigned)HW, K, C, w_sc, w_sk, scale);          \
+    else                                                                                    \
+      pw_reduce_kernel<T, TPP, long long><<<grid, 256, smem, s>>>(                          \
+          (const T *)act, w, bias, img, N, HW, K, C, w_sc, w_sk, scale);                    \
   }
   PG_DISPATCH_DTYPE(dtype, T, {
     if (nch <= 4) PG_LAUNCH_PWR(4)
@@ -217,8 +230,14 @@ extern "C" int pg_pw_wgrad(const void *act, const float *img, float *dw, int N, 
   const long long P = (long long)N * HW;
   const int grid = bw_grid(P, rows * 16, 4);
   const size_t smem = (size_t)rows * K * C * sizeof(float);
-  PG_DISPATCH_DTYPE(dtype, T, pw_wgrad_kernel<T><<<grid, 256, smem, (cudaStream_t)stream>>>(
-                                  (const T *)act, img, dw, N, HW, K, C, w_sc, w_sk, scale));
+  PG_DISPATCH_DTYPE(dtype, T, {
+    if (P + (long long)grid * 256 < (1ll << 31))
+      pw_wgrad_kernel<T, unsigned><<<grid, 256, smem, (cudaStream_t)stream>>>(
+          (const T *)act, img, dw, N, (unsigned)HW, K, C, w_sc, w_sk, scale);
+    else
+      pw_wgrad_kernel<T, long long><<<grid, 256, smem, (cudaStream_t)stream>>>(
+          (const T *)act, img, dw, N, HW, K, C, w_sc, w_sk, scale);
+  });
   PG_CHECK_LAUNCH("pg_pw_wgrad");
 }
 

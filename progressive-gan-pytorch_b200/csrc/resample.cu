@@ -36,19 +36,19 @@ struct Grp {
   }
 };
 
-template <typename T, int G>
+template <typename T, int G, typename I>
 __global__ void __launch_bounds__(256)
 avgpool2_kernel(const T *__restrict__ x, T *__restrict__ y, int N, int H, int W, int C) {
   const int Ho = H / 2, Wo = W / 2, cg = C / G;
-  const long long total = (long long)N * Ho * Wo * cg;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % cg) * G;
-    long long t = i / cg;
-    const int ox = (int)(t % Wo);
-    t /= Wo;
-    const int oy = (int)(t % Ho);
-    const long long n = t / Ho;
+  const I total = (I)N * (I)Ho * (I)Wo * (I)cg;
+  for (I i = (I)blockIdx.x * (I)blockDim.x + (I)threadIdx.x; i < total;
+       i += (I)gridDim.x * (I)blockDim.x) {
+    I t = i / (I)cg;
+    const int c = (int)(i - t * (I)cg) * G;
+    I t2 = t / (I)Wo;
+    const int ox = (int)(t - t2 * (I)Wo);
+    const long long n = (long long)(t2 / (I)Ho);
+    const int oy = (int)(t2 - (I)n * (I)Ho);
     const T *base = x + ((n * H + 2 * oy) * W + 2 * ox) * (long long)C + c;
     Grp<T, G> a, b, cc, d, o;
     a.load(base);
@@ -61,40 +61,40 @@ avgpool2_kernel(const T *__restrict__ x, T *__restrict__ y, int N, int H, int W,
   }
 }
 
-template <typename T, int G>
+template <typename T, int G, typename I>
 __global__ void __launch_bounds__(256)
 avgpool2_bwd_kernel(const T *__restrict__ dy, T *__restrict__ dx, int N, int H, int W, int C) {
   const int Ho = H / 2, Wo = W / 2, cg = C / G;
-  const long long total = (long long)N * H * W * cg;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % cg) * G;
-    long long t = i / cg;
-    const int xx = (int)(t % W);
-    t /= W;
-    const int yy = (int)(t % H);
-    const long long n = t / H;
+  const I total = (I)N * (I)H * (I)W * (I)cg;
+  for (I i = (I)blockIdx.x * (I)blockDim.x + (I)threadIdx.x; i < total;
+       i += (I)gridDim.x * (I)blockDim.x) {
+    I t = i / (I)cg;
+    const int c = (int)(i - t * (I)cg) * G;
+    I t2 = t / (I)W;
+    const int xx = (int)(t - t2 * (I)W);
+    const long long n = (long long)(t2 / (I)H);
+    const int yy = (int)(t2 - (I)n * (I)H);
     Grp<T, G> g;
     g.load(dy + ((n * Ho + yy / 2) * Wo + xx / 2) * (long long)C + c);
 #pragma unroll
     for (int e = 0; e < G; ++e) g.v[e] *= 0.25f;
-    g.store(dx + i * G);
+    g.store(dx + (long long)i * G);
   }
 }
 
-template <typename T, int G>
+template <typename T, int G, typename I>
 __global__ void __launch_bounds__(256)
 upsample2_kernel(const T *__restrict__ x, T *__restrict__ y, int N, int H, int W, int C) {
   const int Ho = 2 * H, Wo = 2 * W, cg = C / G;
-  const long long total = (long long)N * Ho * Wo * cg;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % cg) * G;
-    long long t = i / cg;
-    const int ox = (int)(t % Wo);
-    t /= Wo;
-    const int oy = (int)(t % Ho);
-    const long long n = t / Ho;
+  const I total = (I)N * (I)Ho * (I)Wo * (I)cg;
+  for (I i = (I)blockIdx.x * (I)blockDim.x + (I)threadIdx.x; i < total;
+       i += (I)gridDim.x * (I)blockDim.x) {
+    I t = i / (I)cg;
+    const int c = (int)(i - t * (I)cg) * G;
+    I t2 = t / (I)Wo;
+    const int ox = (int)(t - t2 * (I)Wo);
+    const long long n = (long long)(t2 / (I)Ho);
+    const int oy = (int)(t2 - (I)n * (I)Ho);
     int y0, y1, x0, x1;
     float wy0, wx0;
     if (oy & 1) { y0 = oy >> 1; y1 = min(y0 + 1, H - 1); wy0 = 0.75f; }
@@ -111,13 +111,13 @@ upsample2_kernel(const T *__restrict__ x, T *__restrict__ y, int N, int H, int W
 #pragma unroll
     for (int e = 0; e < G; ++e)
       o.v[e] = wy0 * (wx0 * a00.v[e] + wx1 * a01.v[e]) + wy1 * (wx0 * a10.v[e] + wx1 * a11.v[e]);
-    o.store(y + i * G);
+    o.store(y + (long long)i * G);
   }
 }
 
 // transpose of the stencil: dx[i] = sum over o in {2i-1,2i,2i+1,2i+2} clamped to [0,2n-1]
 // with weights {.25,.75,.75,.25} per axis.
-template <typename T, int G>
+template <typename T, int G, typename I>
 __global__ void __launch_bounds__(256)
 upsample2_bwd_kernel(const T *__restrict__ dy, T *__restrict__ dx, int N, int H, int W, int C) {
   const int Ho = 2 * H, Wo = 2 * W, cg = C / G;
@@ -151,7 +151,7 @@ upsample2_bwd_kernel(const T *__restrict__ dy, T *__restrict__ dx, int N, int H,
     Grp<T, G> o;
 #pragma unroll
     for (int e = 0; e < G; ++e) o.v[e] = acc[e];
-    o.store(dx + i * G);
+    o.store(dx + (long long)i * G);
   }
 }
 
@@ -206,14 +206,25 @@ using namespace pg;
     PG_CHECK_ARG(N > 0 && H > 0 && W > 0 && C > 0, #fn ": bad dims");                          \
     PG_CHECK_ARG(!(even_check) || (H % 2 == 0 && W % 2 == 0), #fn ": H and W must be even");   \
     const long long work = (work_expr);                                                        \
+    /* 32-bit index arithmetic whenever it fits: the 64-bit div/mod chain per element made   \
+       these kernels ALU-bound */                                                              \
+    const bool small = work * 4 < (1ll << 31);                                                 \
     if (C % 8 == 0) {                                                                          \
       const int grid = bw_grid(work / 8, 256);                                                 \
-      PG_DISPATCH_DTYPE(dtype, T, (kernel<T, 8><<<grid, 256, 0, (cudaStream_t)stream>>>(       \
-                                      (const T *)x, (T *)y, N, H, W, C)));                     \
+      PG_DISPATCH_DTYPE(dtype, T, {                                                            \
+        if (small) kernel<T, 8, unsigned><<<grid, 256, 0, (cudaStream_t)stream>>>(             \
+                       (const T *)x, (T *)y, N, H, W, C);                                      \
+        else kernel<T, 8, long long><<<grid, 256, 0, (cudaStream_t)stream>>>(                  \
+                 (const T *)x, (T *)y, N, H, W, C);                                            \
+      });                                                                                      \
     } else {                                                                                   \
       const int grid = bw_grid(work, 256);                                                     \
-      PG_DISPATCH_DTYPE(dtype, T, (kernel<T, 1><<<grid, 256, 0, (cudaStream_t)stream>>>(       \
-                                      (const T *)x, (T *)y, N, H, W, C)));                     \
+      PG_DISPATCH_DTYPE(dtype, T, {                                                            \
+        if (small) kernel<T, 1, unsigned><<<grid, 256, 0, (cudaStream_t)stream>>>(             \
+                       (const T *)x, (T *)y, N, H, W, C);                                      \
+        else kernel<T, 1, long long><<<grid, 256, 0, (cudaStream_t)stream>>>(                  \
+                 (const T *)x, (T *)y, N, H, W, C);                                            \
+      });                                                                                      \
     }                                                                                          \
     PG_CHECK_LAUNCH(#fn);                                                                      \
   }

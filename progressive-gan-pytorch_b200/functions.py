@@ -220,6 +220,7 @@ class Act(Function):
     def forward(ctx, A, r, slope, use_pn, pool, bias, link=None):
         ctx.slope, ctx.use_pn, ctx.pool, ctx.bias = slope, use_pn, pool, bias
         ctx.link = link
+        ctx.stash = {}
         ctx.save_for_backward(A, r)
         if pool:
             return K().avgpool2(A, "nhwc")
@@ -233,7 +234,17 @@ class Act(Function):
             return dy, None, None, None, None, None, None
         A, r = ctx.saved_tensors
         direct = DIRECT_GRADS and not torch.is_grad_enabled()
-        da = ActBwd.apply(dy.contiguous(), A, r, ctx.slope, ctx.use_pn, ctx.pool, ctx.bias, direct)
+        addend = None
+        ent = ctx.stash.pop("cot_a", None)
+        if ent is not None:
+            # the PixelNorm Hessian term left by ActBwd.backward earlier in THIS sweep: summed
+            # into da (and into the bias gradient) by the kernel instead of by autograd
+            if ent[1] != torch._C._current_graph_task_id():
+                raise RuntimeError("progan_b200: stale second-order term (an earlier backward "
+                                   "sweep did not reach this activation)")
+            addend = ent[0]
+        da = ActBwd.apply(dy.contiguous(), A, r, ctx.slope, ctx.use_pn, ctx.pool, ctx.bias, direct, ctx,
+                          addend)
         return da, None, None, None, None, None, None
 
 
@@ -242,14 +253,18 @@ class ActBwd(Function):
     pool's backward fused when pool=True) + the per-channel sum of da (bias gradient)."""
 
     @staticmethod
-    def forward(ctx, dy, A, r, slope, use_pn, pool, bias, direct):
+    def forward(ctx, dy, A, r, slope, use_pn, pool, bias, direct, act_node=None, addend=None):
         ctx.slope, ctx.use_pn, ctx.pool, ctx.bias = slope, use_pn, pool, bias
+        ctx.act_node = act_node
         ctx.save_for_backward(dy, A, r)
         tgt = None
         want = _bias_wanted(bias)
         if direct and want and bias.is_leaf and bias.grad is not None:
             tgt = bias.grad
-        da, _ = K().pn_lrelu_bwd(dy, A, r if use_pn else None, slope, use_pn, pool, False, tgt)
+        if addend is not None:
+            da, _ = K().pn_lrelu_bwd(dy, A, r if use_pn else None, slope, use_pn, pool, False, tgt, addend)
+        else:
+            da, _ = K().pn_lrelu_bwd(dy, A, r if use_pn else None, slope, use_pn, pool, False, tgt)
         return da
 
     @staticmethod
@@ -262,9 +277,23 @@ class ActBwd(Function):
             cot_dy = K().avgpool2(cot_dy, "nhwc")
         if not ctx.needs_input_grad[1] or not ctx.use_pn:
             cot_a = None
-        elif DIRECT_GRADS and _bias_wanted(ctx.bias) and _direct_target(ctx.bias) is not None:
-            K().colsum(cot_a, out=ctx.bias.grad)    # Hessian-term share of the bias gradient
-        return cot_dy, cot_a, None, None, None, None, None, None
+        elif DIRECT_GRADS:
+            node = ctx.act_node
+            fusable = node is not None and node.link is not None and \
+                getattr(K(), "fuse_actbwd_min_cout", 1 << 30) <= 128     # pass-through Act: no stash
+            if (STASH_SECOND_ORDER and node is not None and not fusable
+                    and torch._C._will_engine_execute_node(node)):
+                # the Act node of this layer runs later in this sweep (it receives the chain
+                # term through the layer above): hand it the Hessian term directly — no autograd
+                # add kernel, and its bias-gradient share is summed by that kernel too
+                node.stash["cot_a"] = (cot_a, torch._C._current_graph_task_id())
+                cot_a = None
+            elif _bias_wanted(ctx.bias) and _direct_target(ctx.bias) is not None:
+                K().colsum(cot_a, out=ctx.bias.grad)    # Hessian-term share of the bias gradient
+        return cot_dy, cot_a, None, None, None, None, None, None, None, None
+
+
+STASH_SECOND_ORDER = True
 
 
 def conv_act(x, w, b, op, scale, slope=0.2, use_pn=True, pool=False, prev_link=None, make_link=False):

@@ -384,9 +384,14 @@ class CudaKernels:
         return C + 1
 
     # ------------------------------------------------- PixelNorm + LeakyReLU
-    def pn_lrelu_bwd(self, dy, y, r, slope, use_pn, pool=False, want_colsum=False, colsum_out=None):
-        """da = Jpn(a)^T (m*dy).  pool: dy is the gradient of avgpool2(y).  Returns (da, colsum)
-        where colsum = per-channel sum of da (bias gradient) when requested, else None."""
+    def pn_lrelu_bwd(self, dy, y, r, slope, use_pn, pool=False, want_colsum=False, colsum_out=None,
+                     addend=None):
+        """da = Jpn(a)^T (m*dy) [+ addend].  pool: dy is the gradient of avgpool2(y).  Returns
+        (da, colsum) where colsum = per-channel sum of da (bias gradient) when requested, else None."""
+        if addend is not None:
+            _chk(addend, "addend", y.dtype)
+            if addend.shape != y.shape:
+                raise RuntimeError("progan_b200: addend shape mismatch")
         _chk(dy, "dy", y.dtype)
         _chk(y, "y")
         N, H, W, C = y.shape
@@ -398,7 +403,7 @@ class CudaKernels:
             cs = torch.zeros(C, device=y.device, dtype=torch.float32)
         self._call("pg_pn_lrelu_bwd", dy.data_ptr(), y.data_ptr(), _ptr(r), da.data_ptr(),
                    y.numel() // C, C, float(slope), int(use_pn), H if pool else 0, W if pool else 0,
-                   _ptr(cs), _dt(y), self._stream())
+                   _ptr(cs), _ptr(addend), _dt(y), self._stream())
         return da, cs
 
     def pn_lrelu_bwd_bwd(self, t, dy, y, r, slope, use_pn, pool=False):

@@ -137,13 +137,15 @@ class FlatBucket:
 class Trainer:
     def __init__(self, generator, discriminator, g_running=None, lr=1e-3, betas=(0.0, 0.99),
                  eps=1e-8, ema_decay=0.999, gp_lambda=10.0, drift=0.001, process_group=None,
-                 use_graph=False):
+                 use_graph=False, segment_graphs=None):
         self.G, self.D, self.G_run = generator, discriminator, g_running
         self.lr, self.betas, self.eps = lr, betas, eps
         self.ema_decay, self.gp_lambda, self.drift = ema_decay, gp_lambda, drift
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
         self.use_graph = use_graph
+        # multi-GPU: three graphs per iteration with the NCCL all-reduces between the replays
+        self.segment_graphs = (self.world > 1) if segment_graphs is None else bool(segment_graphs)
         self.bD = FlatBucket(_d_groups(discriminator), betas[0])
         self.bG = FlatBucket(_g_groups(generator), betas[0])
         self.bR = None
@@ -173,55 +175,79 @@ class Trainer:
                                  self.lr, self.betas[0], self.betas[1], self.eps, 1.0 / self.world)
         get_kernels().refresh_packs(plan["params"])     # operand copies of the updated weights
 
-    def _iteration(self, real, z, eps, step, alpha, fading):
-        K = get_kernels()
-        prev, prev_defer = F_.DIRECT_GRADS, getattr(K, "defer_wgrad", False)
-        F_.DIRECT_GRADS = True      # gradient kernels accumulate straight into the flat buckets
-        K.defer_wgrad = True        # ... the conv weight gradients through persistent workspaces
-        try:
-            self._iteration_impl(real, z, eps, step, alpha, fading)
-        finally:
-            F_.DIRECT_GRADS = prev
-            K.defer_wgrad = prev_defer
+    class _fast_paths:
+        """Gradient kernels accumulate straight into the flat buckets; the conv weight gradients
+        go through persistent workspaces (kernels.flush_wgrads)."""
 
-    def _iteration_impl(self, real, z, eps, step, alpha, fading):
-        """alpha: fp32 device scalar tensor when fading else the python number."""
-        K = get_kernels()
-        G, D = self.G, self.D
-        planD = self.bD.plan(_d_active(D, step, fading))
-        planG = self.bG.plan(_g_active(G, step, fading))
+        def __enter__(self):
+            K = get_kernels()
+            self.prev = (F_.DIRECT_GRADS, getattr(K, "defer_wgrad", False))
+            F_.DIRECT_GRADS, K.defer_wgrad = True, True
+
+        def __exit__(self, *exc):
+            F_.DIRECT_GRADS, get_kernels().defer_wgrad = self.prev
+
+    def _iteration(self, real, z, eps, step, alpha, fading):
+        """alpha: fp32 device scalar tensor when fading else the python number.  The iteration
+        is three segments separated by the two gradient all-reduces (the segments are what a
+        multi-GPU run captures as CUDA graphs; the collectives stay outside the graphs)."""
+        st = self._state(real, z, eps, step, alpha, fading)
+        with self._fast_paths():
+            self._seg_d(st)
+            self._allreduce(self.bD, st["planD"])
+            self._seg_g(st)
+            self._allreduce(self.bG, st["planG"])
+            self._seg_end(st)
+
+    def _state(self, real, z, eps, step, alpha, fading):
+        return dict(real=real, z=z, eps=eps, step=step, alpha=alpha,
+                    planD=self.bD.plan(_d_active(self.D, step, fading)),
+                    planG=self.bG.plan(_g_active(self.G, step, fading)))
+
+    def _seg_d(self, st):
         # ---- D phase.  D(real) and D(fake) (train.py:126-139) run as ONE pass over
         # cat([real, fake]) with per-half minibatch statistics: same gradients (they accumulate
         # into the same .grad in the reference), half the launches, twice the rows per GEMM.
+        K = get_kernels()
+        G, D = self.G, self.D
+        real, step, alpha = st["real"], st["step"], st["alpha"]
         self.bD.g.zero_()
         B = real.shape[0]
-        fake = G(z, step=step, alpha=alpha)
+        fake = G(st["z"], step=step, alpha=alpha)
         both = D(torch.cat([real, fake.detach()]), step=step, alpha=alpha, mbstd_group=B)
         real_raw, fake_raw = both[:B], both[B:]
         real_predict = real_raw.mean() - self.drift * (real_raw ** 2).mean()
         fake_predict = fake_raw.mean()
         (fake_predict - real_predict).backward()
-        x_hat = K.interp_xhat(real, fake.detach(), eps.reshape(-1)).requires_grad_(True)
+        x_hat = K.interp_xhat(real, fake.detach(), st["eps"].reshape(-1)).requires_grad_(True)
         hat = D(x_hat, step=step, alpha=alpha)
         (g,) = torch.autograd.grad(outputs=hat.sum(), inputs=x_hat, create_graph=True)
         gp = F_.gradient_penalty(g, self.gp_lambda)
         gp.backward()
         K.flush_wgrads()
-        self._allreduce(self.bD, planD)
-        self._adam(self.bD, planD)
-        self.metrics["grad_penalty"].add_(gp.detach())
-        self.metrics["disc_loss"].add_((real_predict - fake_predict).detach())
+        st["fake"] = fake
+        st["gp"] = gp.detach()
+        st["d_loss"] = (real_predict - fake_predict).detach()
+
+    def _seg_g(self, st):
+        K = get_kernels()
+        self._adam(self.bD, st["planD"])
+        self.metrics["grad_penalty"].add_(st["gp"])
+        self.metrics["disc_loss"].add_(st["d_loss"])
         # ---- G phase (D already updated, train.py:158-169)
         self.bG.g.zero_()
-        loss = -D(fake, step=step, alpha=alpha).mean()
-        loss.backward(inputs=planG["params"])
+        loss = -self.D(st["fake"], step=st["step"], alpha=st["alpha"]).mean()
+        loss.backward(inputs=st["planG"]["params"])
         K.flush_wgrads()
-        self._allreduce(self.bG, planG)
-        self._adam(self.bG, planG)
+        st["g_loss"] = loss.detach()
+
+    def _seg_end(self, st):
+        K = get_kernels()
+        self._adam(self.bG, st["planG"])
         if self.bR is not None:
             K.ema(self.bR.p, self.bG.p, self.ema_decay)
             K.drop_packs(self._r_params)
-        self.metrics["gen_loss"].add_(loss.detach())
+        self.metrics["gen_loss"].add_(st["g_loss"])
 
     # ------------------------------------------------------------------ public
     def step(self, real, z, eps, step, alpha):
@@ -263,17 +289,40 @@ class Trainer:
             # every replay keep them consistent through the refresh launches after each Adam)
             K.refresh_packs(list(self.D.parameters()))
             K.refresh_packs(list(self.G.parameters()))
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                self._iteration(sreal, sz, seps, step, a, fading)
-            ent = (graph, sreal, sz, seps)
+            torch.cuda.synchronize()
+            if not self.segment_graphs:
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    self._iteration(sreal, sz, seps, step, a, fading)
+                graphs = [graph]
+            else:
+                # one graph per segment; the NCCL all-reduces run between the replays
+                st = self._state(sreal, sz, seps, step, a, fading)
+                graphs, pool = [], None
+                for seg in (self._seg_d, self._seg_g, self._seg_end):
+                    gph = torch.cuda.CUDAGraph()
+                    with self._fast_paths(), torch.cuda.graph(gph, pool=pool,
+                                                              capture_error_mode="thread_local"):
+                        seg(st)
+                    pool = gph.pool()
+                    graphs.append(gph)
+                del st
+            ent = (graphs, sreal, sz, seps, self.bD.plan(_d_active(self.D, step, fading)),
+                   self.bG.plan(_g_active(self.G, step, fading)))
             self._graphs[key] = ent
             # the capture itself did not execute anything
-        graph, sreal, sz, seps = ent
+        graphs, sreal, sz, seps, planD, planG = ent
         sreal.copy_(real, non_blocking=True)
         sz.copy_(z, non_blocking=True)
         seps.copy_(eps, non_blocking=True)
-        graph.replay()
+        if len(graphs) == 1:
+            graphs[0].replay()
+        else:
+            graphs[0].replay()
+            self._allreduce(self.bD, planD)
+            graphs[1].replay()
+            self._allreduce(self.bG, planG)
+            graphs[2].replay()
 
     def read_metrics(self, reset=True):
         """One host sync for all three running sums (the reference syncs three times per

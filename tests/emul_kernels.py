@@ -102,7 +102,8 @@ class EmulKernels:
     def _unpool(dy):
         return 0.25 * dy.repeat_interleave(2, 1).repeat_interleave(2, 2)
 
-    def pn_lrelu_bwd(self, dy, y, r, slope, use_pn, pool=False, want_colsum=False, colsum_out=None):
+    def pn_lrelu_bwd(self, dy, y, r, slope, use_pn, pool=False, want_colsum=False, colsum_out=None,
+                     addend=None):
         self.launches += 1
         cd = torch.float64 if y.dtype == torch.float64 else torch.float32
         p, m = self._pm(y.to(cd), slope)
@@ -112,6 +113,8 @@ class EmulKernels:
             C = y.shape[-1]
             s = (p * u).sum(-1, keepdim=True)
             u = r.to(cd).unsqueeze(-1) * (u - p * s / C)
+        if addend is not None:
+            u = u + addend.to(cd)
         cs = None
         if want_colsum or colsum_out is not None:
             cs = u.reshape(-1, y.shape[-1]).sum(0).to(cd if cd == torch.float64 else torch.float32)
