@@ -152,6 +152,16 @@ def run_product(args):
         e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
     sampler.stop_flag = True
+    eager_launches = None
+    if tr.use_graph:
+        # launches inside one captured iteration = launches of one eager iteration (every rank
+        # runs it: the iteration contains the gradient all-reduces)
+        K2 = K.launches
+        tr.use_graph = False
+        tr.step(real, z, eps, step, alpha)
+        torch.cuda.synchronize()
+        tr.use_graph = True
+        eager_launches = K.launches - K2
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -180,13 +190,8 @@ def run_product(args):
                              "over step time; peak = %s" % (step_flops(res) / 1e9, which)},
         "clocks": sampler.summary(),
     }
-    if tr.use_graph:
-        # launches inside one captured iteration = launches of one eager iteration
-        K2 = K.launches
-        tr.use_graph = False
-        tr.step(real, z, eps, step, alpha)
-        torch.cuda.synchronize()
-        line["gpu_launches"] = (K.launches - K2) * args.steps
+    if eager_launches is not None:
+        line["gpu_launches"] = eager_launches * args.steps
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(res, B, alpha, sample_batch=args.cpu_batch)
     print(json.dumps(line))
