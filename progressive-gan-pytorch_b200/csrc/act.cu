@@ -169,11 +169,121 @@ pn_lrelu_grad_kernel(const T *__restrict__ t_in, const T *__restrict__ dy,
   }
 }
 
+// First-order backward through PixelNorm + LeakyReLU + 2x2 average pool, one sub-warp per POOLED
+// pixel: the four full-resolution pixels of the quad share one dy vector, which is loaded once
+// (the generic kernel re-reads it from four different CTAs and pays the index arithmetic four
+// times).  C <= 8*TPP.
+template <typename T, int TPP, bool ADD>
+__global__ void __launch_bounds__(256, 3)
+pn_lrelu_bwd_pooled_kernel(const T *__restrict__ addend, const T *__restrict__ dy,
+                           const T *__restrict__ y, const float *__restrict__ rr,
+                           T *__restrict__ da, unsigned NQ, unsigned H2, unsigned W2, int C,
+                           float slope, int use_pn, float *__restrict__ colsum) {
+  using Raw = typename RawOf<T>::type;
+  const int sub = threadIdx.x % TPP;
+  const unsigned qpb = blockDim.x / TPP;
+  const int nch = C >> 3;
+  const bool lane_live = sub < nch;
+  const float invC = 1.f / (float)C;
+  const float inv_slope = 1.f / slope;
+  const unsigned W = 2u * W2;
+  float csum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const unsigned NQr = ((NQ + qpb - 1) / qpb) * qpb;
+  for (unsigned q = blockIdx.x * qpb + threadIdx.x / TPP; q < NQr; q += gridDim.x * qpb) {
+    const bool live = q < NQ && lane_live;
+    const unsigned t = q / W2, w2 = q - t * W2;
+    const unsigned n = t / H2, h2 = t - n * H2;
+    const long long p00 = ((long long)n * (2u * H2) + 2u * h2) * W + 2u * w2;
+    const long long pix[4] = {p00, p00 + 1, p00 + W, p00 + W + 1};
+    Raw ry[4], ra[4], rd;
+    float rv[4] = {1.f, 1.f, 1.f, 1.f};
+    if (live) {
+      rd = ldraw8(dy + (long long)q * C + (long long)sub * 8);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        ry[u] = ldraw8(y + pix[u] * C + (long long)sub * 8);
+        if (ADD) ra[u] = ldraw8(addend + pix[u] * C + (long long)sub * 8);
+      }
+    }
+    if (use_pn && q < NQ) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) rv[u] = rr[pix[u]];
+    }
+    F8 dv;
+    if (live) dv = unpack8(rd);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      F8 pv, uv;
+      float s_pu = 0.f;
+      if (live) {
+        const F8 yv = unpack8(ry[u]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const bool pos = yv.v[e] > 0.f;
+          pv.v[e] = pos ? yv.v[e] : yv.v[e] * inv_slope;
+          uv.v[e] = (pos ? 0.25f : 0.25f * slope) * dv.v[e];
+          s_pu += pv.v[e] * uv.v[e];
+        }
+      }
+      if (use_pn) s_pu = subwarp_sum<TPP>(s_pu);
+      if (live) {
+        F8 o;
+        F8 av;
+        if (ADD) av = unpack8(ra[u]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          o.v[e] = use_pn ? rv[u] * (uv.v[e] - pv.v[e] * s_pu * invC) : uv.v[e];
+          if (ADD) o.v[e] += av.v[e];
+          csum[e] += o.v[e];
+        }
+        st8(da + pix[u] * C + (long long)sub * 8, o);
+      }
+    }
+  }
+  if (colsum != nullptr) {
+    extern __shared__ float cs_sm[];              // [qpb][C]
+    const int slot = threadIdx.x / TPP;
+    if (lane_live) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) cs_sm[slot * C + sub * 8 + e] = csum[e];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float a = 0.f;
+      for (int sl = 0; sl < (int)qpb; ++sl) a += cs_sm[sl * C + c];
+      atomicAdd(colsum + c, a);
+    }
+  }
+}
+
 template <typename T, bool SECOND>
 static int launch_pn_grad(const T *t, const T *dy, const T *y, const float *r, T *o0, T *o1,
                           long long P, int C, float slope, int use_pn, int pool_h, int pool_w,
                           float *colsum, cudaStream_t s) {
   const int nch = C / 8;
+  if (!SECOND && pool_w > 0 && nch <= 32 && P < (1ll << 31)) {
+    // quad kernel (pool_h/pool_w still carry the log2 encoding in their high halves)
+    const unsigned H_ = (unsigned)pool_h & 0xFFFFu, W_ = (unsigned)pool_w & 0xFFFFu;
+    const unsigned NQ = (unsigned)(P / 4);
+#define PG_LAUNCH_PQ(TPP)                                                                  \
+  {                                                                                        \
+    const int qpb = 256 / TPP;                                                             \
+    const int grid = bw_grid(NQ, qpb, 3);                                                  \
+    const size_t sm = colsum ? (size_t)qpb * C * sizeof(float) : 0;                        \
+    if (t != nullptr)                                                                      \
+      pn_lrelu_bwd_pooled_kernel<T, TPP, true><<<grid, 256, sm, s>>>(                      \
+          t, dy, y, r, o0, NQ, H_ / 2, W_ / 2, C, slope, use_pn, colsum);                  \
+    else                                                                                   \
+      pn_lrelu_bwd_pooled_kernel<T, TPP, false><<<grid, 256, sm, s>>>(                     \
+          t, dy, y, r, o0, NQ, H_ / 2, W_ / 2, C, slope, use_pn, colsum);                  \
+  }
+    if (nch <= 4) PG_LAUNCH_PQ(4)
+    else if (nch <= 8) PG_LAUNCH_PQ(8)
+    else if (nch <= 16) PG_LAUNCH_PQ(16)
+    else PG_LAUNCH_PQ(32)
+#undef PG_LAUNCH_PQ
+    return PG_OK;
+  }
 #define PG_LAUNCH_PN(TPP, MAXI)                                                           \
   {                                                                                       \
     const long long ppb = 256 / TPP;                                                      \

@@ -29,26 +29,38 @@ pw_expand_kernel(const float *__restrict__ img, const float *__restrict__ w,
   __syncthreads();
   const I nch = (I)(C >> 3);
   const I total = (I)N * HW * nch;
-  for (I i = (I)blockIdx.x * (I)blockDim.x + (I)threadIdx.x; i < total;
-       i += (I)gridDim.x * (I)blockDim.x) {
-    const I pix = i / nch;
-    const int cj = (int)(i - pix * nch);
-    const I n = pix / HW, hw = pix - n * HW;
-    float xin[kMaxK];
+  constexpr int UN = 4;                       // independent elements per thread: bytes in flight
+  const I stride = (I)gridDim.x * (I)blockDim.x;
+  for (I i0 = (I)blockIdx.x * (I)blockDim.x + (I)threadIdx.x; i0 < total; i0 += stride * UN) {
+    float xin[UN][kMaxK];
+    I pixs[UN];
+    int cjs[UN];
 #pragma unroll
-    for (int k = 0; k < kMaxK; ++k)
-      xin[k] = (k < K) ? img[((long long)n * K + k) * (long long)HW + (long long)hw] : 0.f;
-    F8 o;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int c = cj * 8 + e;
-      float v = sb[c];
+    for (int u = 0; u < UN; ++u) {
+      const I i = i0 + (I)u * stride;
+      const I pix = i / nch;
+      pixs[u] = pix;
+      cjs[u] = (int)(i - pix * nch);
+      const I n = pix / HW, hw = pix - n * HW;
 #pragma unroll
       for (int k = 0; k < kMaxK; ++k)
-        if (k < K) v = fmaf(xin[k], sw[k * C + c], v);
-      o.v[e] = v;
+        xin[u][k] = (k < K && i < total) ? img[((long long)n * K + k) * (long long)HW + (long long)hw] : 0.f;
     }
-    st8(act + (long long)pix * C + (long long)cj * 8, o);
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      if (i0 + (I)u * stride >= total) break;
+      F8 o;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int c = cjs[u] * 8 + e;
+        float v = sb[c];
+#pragma unroll
+        for (int k = 0; k < kMaxK; ++k)
+          if (k < K) v = fmaf(xin[u][k], sw[k * C + c], v);
+        o.v[e] = v;
+      }
+      st8(act + (long long)pixs[u] * C + (long long)cjs[u] * 8, o);
+    }
   }
 }
 
@@ -68,31 +80,49 @@ pw_reduce_kernel(const T *__restrict__ act, const float *__restrict__ w,
   const int nch = C >> 3;
   const I P = (I)N * HW;
   const I Pr = ((P + ppb - 1) / ppb) * ppb;
-  for (I pix = (I)blockIdx.x * ppb + (I)(threadIdx.x / TPP); pix < Pr;
-       pix += (I)gridDim.x * ppb) {
-    float acc[kMaxK] = {0.f, 0.f, 0.f, 0.f};
-    if (pix < P) {
-      for (int ch = sub; ch < nch; ch += TPP) {
-        F8 v = ld8(act + (long long)pix * C + (long long)ch * 8);
+  constexpr int UN = 4;                       // pixels per sub-warp in flight
+  const I pstride = (I)gridDim.x * ppb;
+  for (I pix0 = (I)blockIdx.x * ppb + (I)(threadIdx.x / TPP); pix0 < Pr; pix0 += pstride * UN) {
+    float acc[UN][kMaxK];
+    typename RawOf<T>::type raw[UN];
+    const bool one = nch <= TPP;              // the usual case: one 16-byte chunk per lane
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int c = ch * 8 + e;
+    for (int u = 0; u < UN; ++u) {
+      const I pix = pix0 + (I)u * pstride;
+      if (one && pix < P && sub < nch) raw[u] = ldraw8(act + (long long)pix * C + (long long)sub * 8);
+    }
 #pragma unroll
-          for (int k = 0; k < kMaxK; ++k)
-            if (k < K) acc[k] = fmaf(v.v[e], sw[k * C + c], acc[k]);
+    for (int u = 0; u < UN; ++u) {
+      const I pix = pix0 + (I)u * pstride;
+#pragma unroll
+      for (int k = 0; k < kMaxK; ++k) acc[u][k] = 0.f;
+      if (pix < P) {
+        for (int ch = sub; ch < nch; ch += TPP) {
+          F8 v = one ? unpack8(raw[u]) : ld8(act + (long long)pix * C + (long long)ch * 8);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int c = ch * 8 + e;
+#pragma unroll
+            for (int k = 0; k < kMaxK; ++k)
+              if (k < K) acc[u][k] = fmaf(v.v[e], sw[k * C + c], acc[u][k]);
+          }
         }
       }
     }
 #pragma unroll
-    for (int k = 0; k < kMaxK; ++k) {
+    for (int u = 0; u < UN; ++u) {
+      const I pix = pix0 + (I)u * pstride;
 #pragma unroll
-      for (int o = TPP / 2; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
-    }
-    if (pix < P && sub == 0) {
-      const I n = pix / HW, hw = pix - n * HW;
+      for (int k = 0; k < kMaxK; ++k) {
 #pragma unroll
-      for (int k = 0; k < kMaxK; ++k)
-        if (k < K) img[((long long)n * K + k) * (long long)HW + (long long)hw] = acc[k] + (bias ? bias[k] : 0.f);
+        for (int o = TPP / 2; o > 0; o >>= 1) acc[u][k] += __shfl_xor_sync(0xffffffffu, acc[u][k], o);
+      }
+      if (pix < P && sub == 0) {
+        const I n = pix / HW, hw = pix - n * HW;
+#pragma unroll
+        for (int k = 0; k < kMaxK; ++k)
+          if (k < K) img[((long long)n * K + k) * (long long)HW + (long long)hw] = acc[u][k] + (bias ? bias[k] : 0.f);
+      }
     }
   }
 }
@@ -114,15 +144,34 @@ pw_wgrad_kernel(const T *__restrict__ act, const float *__restrict__ img,
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[k][e] = 0.f;
   if (rj < rows) {
-    for (I pix = (I)blockIdx.x * (I)rows + (I)rj; pix < P; pix += (I)gridDim.x * (I)rows) {
-      const I n = pix / HW, hw = pix - n * HW;
-      F8 v = ld8(act + (long long)pix * C + (long long)cj * 8);
+    constexpr int UN = 4;                     // pixels in flight per thread
+    const I pstride = (I)gridDim.x * (I)rows;
+    for (I pix0 = (I)blockIdx.x * (I)rows + (I)rj; pix0 < P; pix0 += pstride * UN) {
+      typename RawOf<T>::type raw[UN];
+      float g[UN][kMaxK];
 #pragma unroll
-      for (int k = 0; k < kMaxK; ++k) {
-        if (k < K) {
-          const float g = img[((long long)n * K + k) * (long long)HW + (long long)hw];
+      for (int u = 0; u < UN; ++u) {
+        const I pix = pix0 + (I)u * pstride;
+        if (pix < P) {
+          const I n = pix / HW, hw = pix - n * HW;
+          raw[u] = ldraw8(act + (long long)pix * C + (long long)cj * 8);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) acc[k][e] = fmaf(v.v[e], g, acc[k][e]);
+          for (int k = 0; k < kMaxK; ++k)
+            g[u][k] = (k < K) ? img[((long long)n * K + k) * (long long)HW + (long long)hw] : 0.f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const I pix = pix0 + (I)u * pstride;
+        if (pix < P) {
+          const F8 v = unpack8(raw[u]);
+#pragma unroll
+          for (int k = 0; k < kMaxK; ++k) {
+            if (k < K) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) acc[k][e] = fmaf(v.v[e], g[u][k], acc[k][e]);
+            }
+          }
         }
       }
     }
