@@ -230,7 +230,9 @@ static int launch_w4(const void *x, const void *dy, float *workspace, int N, int
   while (p.tmem_cols < cols) p.tmem_cols <<= 1;
   p.dwp = workspace;
   const int misc = 1024 + 8 * (2 * kW4MaxUnits + 5) + 64;
-  int units = (227 * 1024 - 2 * dy_bytes - box_pad - misc) / unit_bytes;
+  // leave ~32 KB of the SM's shared memory free: the kernel runs on a side stream next to the
+  // bandwidth-bound activation-backward kernels, whose bias-gradient reduction needs a few KB
+  int units = (195 * 1024 - 2 * dy_bytes - box_pad - misc) / unit_bytes;
   if (units > kW4MaxUnits) units = kW4MaxUnits;
   if (units < 2) return PG_ERR_UNSUPPORTED;
   p.units = units;

@@ -56,6 +56,14 @@ class ConvOp:
         return self.ypad or self.cout(wshape)
 
 
+class _nullctx:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
 def _dt(t):
     try:
         return _DT[t.dtype]
@@ -99,6 +107,8 @@ class CudaKernels:
         # channels (long MMA phase per tile) and loses for <= 64 (the 8 epilogue warps become the
         # bottleneck)
         self.fuse_actbwd_min_cout = 1 << 30      # ... and in the whole step neither pays: off
+        self.wgrad_side_stream = None  # Trainer: deferred weight gradients run on this stream, next
+        self._side_dirty = False       # to the bandwidth-bound kernels of the data-gradient chain
         self.defer_wgrad = False       # Trainer: weight gradients accumulate in persistent workspaces
         self._wgrad_ws = {}            # (grad ptr, variant) -> (workspace, unpack entry)
         self._pending = {}             # workspaces holding partial sums since the last flush
@@ -325,18 +335,30 @@ class CudaKernels:
                 acc = 2
             else:
                 ws = torch.empty(k * k * cin * cout, device=x.device, dtype=torch.float32)
-            if mode == "conv3":
-                self._call("pg_conv_wgrad_tc", x.data_ptr(), dy.data_ptr(), dw.data_ptr(), ws.data_ptr(),
-                           N, H, W, cin, cout, cin_l, cout_l, 9, 0, float(scale), int(op.swap),
-                           int(op.flip), acc, st)
-            elif mode == "valid":
-                self._call("pg_conv_wgrad_tc", x.data_ptr(), dy.data_ptr(), dw.data_ptr(), ws.data_ptr(),
-                           N, 1, 1, cin, cout, cin, cout, k * k, 1, float(scale), int(op.swap),
-                           int(op.flip), acc, st)
-            else:   # "full": the same quantity as the valid-form weight gradient of the adjoint op
-                self._call("pg_conv_wgrad_tc", dy.data_ptr(), x.data_ptr(), dw.data_ptr(), ws.data_ptr(),
-                           N, 1, 1, cout, cin, cout, cin, k * k, 1, float(scale), int(not op.swap),
-                           int(not op.flip), acc, st)
+            side = self.wgrad_side_stream if acc == 2 else None
+            if side is not None:
+                # fork: the weight gradient only needs x and dy, nothing on the main stream needs
+                # its result before flush_wgrads() — let it overlap the activation-backward /
+                # resampling kernels that follow (tensor-bound next to HBM-bound)
+                main = torch.cuda.current_stream()
+                side.wait_stream(main)
+                x.record_stream(side)
+                dy.record_stream(side)
+                self._side_dirty = True
+            with (torch.cuda.stream(side) if side is not None else _nullctx()):
+                st = self._stream()
+                if mode == "conv3":
+                    self._call("pg_conv_wgrad_tc", x.data_ptr(), dy.data_ptr(), dw.data_ptr(), ws.data_ptr(),
+                               N, H, W, cin, cout, cin_l, cout_l, 9, 0, float(scale), int(op.swap),
+                               int(op.flip), acc, st)
+                elif mode == "valid":
+                    self._call("pg_conv_wgrad_tc", x.data_ptr(), dy.data_ptr(), dw.data_ptr(), ws.data_ptr(),
+                               N, 1, 1, cin, cout, cin, cout, k * k, 1, float(scale), int(op.swap),
+                               int(op.flip), acc, st)
+                else:   # "full": the same quantity as the valid-form weight gradient of the adjoint op
+                    self._call("pg_conv_wgrad_tc", dy.data_ptr(), x.data_ptr(), dw.data_ptr(), ws.data_ptr(),
+                               N, 1, 1, cout, cin, cout, cin, k * k, 1, float(scale), int(not op.swap),
+                               int(not op.flip), acc, st)
             if acc != 2:
                 self.launches += 2          # memset + unpack
         else:
@@ -354,6 +376,9 @@ class CudaKernels:
         kernel's read-modify-write of dw needs no atomics)."""
         if not self._pending:
             return
+        if self._side_dirty:             # join the weight-gradient stream
+            torch.cuda.current_stream().wait_stream(self.wgrad_side_stream)
+            self._side_dirty = False
         sig = tuple(self._pending.keys())
         tabs = self._unpack_tables.get(sig)
         if tabs is None:

@@ -137,7 +137,7 @@ class FlatBucket:
 class Trainer:
     def __init__(self, generator, discriminator, g_running=None, lr=1e-3, betas=(0.0, 0.99),
                  eps=1e-8, ema_decay=0.999, gp_lambda=10.0, drift=0.001, process_group=None,
-                 use_graph=False, segment_graphs=None):
+                 use_graph=False, segment_graphs=None, overlap_wgrad=True):
         self.G, self.D, self.G_run = generator, discriminator, g_running
         self.lr, self.betas, self.eps = lr, betas, eps
         self.ema_decay, self.gp_lambda, self.drift = ema_decay, gp_lambda, drift
@@ -160,6 +160,9 @@ class Trainer:
                         for k in ("disc_loss", "grad_penalty", "gen_loss")}
         self.iterations = 0
         self._graphs = {}
+        # weight-gradient kernels (tensor-bound) run on a side stream next to the HBM-bound kernels
+        # of the data-gradient chain
+        self._side = torch.cuda.Stream() if (overlap_wgrad and dev.type == "cuda") else None
         self._g_params = list(generator.parameters())
         self._r_params = list(g_running.parameters()) if g_running is not None else []
 
@@ -179,20 +182,25 @@ class Trainer:
         """Gradient kernels accumulate straight into the flat buckets; the conv weight gradients
         go through persistent workspaces (kernels.flush_wgrads)."""
 
+        def __init__(self, side_stream=None):
+            self.side = side_stream
+
         def __enter__(self):
             K = get_kernels()
-            self.prev = (F_.DIRECT_GRADS, getattr(K, "defer_wgrad", False))
-            F_.DIRECT_GRADS, K.defer_wgrad = True, True
+            self.prev = (F_.DIRECT_GRADS, getattr(K, "defer_wgrad", False),
+                         getattr(K, "wgrad_side_stream", None))
+            F_.DIRECT_GRADS, K.defer_wgrad, K.wgrad_side_stream = True, True, self.side
 
         def __exit__(self, *exc):
-            F_.DIRECT_GRADS, get_kernels().defer_wgrad = self.prev
+            K = get_kernels()
+            F_.DIRECT_GRADS, K.defer_wgrad, K.wgrad_side_stream = self.prev
 
     def _iteration(self, real, z, eps, step, alpha, fading):
         """alpha: fp32 device scalar tensor when fading else the python number.  The iteration
         is three segments separated by the two gradient all-reduces (the segments are what a
         multi-GPU run captures as CUDA graphs; the collectives stay outside the graphs)."""
         st = self._state(real, z, eps, step, alpha, fading)
-        with self._fast_paths():
+        with self._fast_paths(self._side):
             self._seg_d(st)
             self._allreduce(self.bD, st["planD"])
             self._seg_g(st)
@@ -301,7 +309,7 @@ class Trainer:
                 graphs, pool = [], None
                 for seg in (self._seg_d, self._seg_g, self._seg_end):
                     gph = torch.cuda.CUDAGraph()
-                    with self._fast_paths(), torch.cuda.graph(gph, pool=pool,
+                    with self._fast_paths(self._side), torch.cuda.graph(gph, pool=pool,
                                                               capture_error_mode="thread_local"):
                         seg(st)
                     pool = gph.pool()

@@ -35,6 +35,7 @@ class EmulKernels:
         self.conv_impl = "simt"
 
     defer_wgrad = False
+    wgrad_side_stream = None
 
     def invalidate_packs(self):
         pass
