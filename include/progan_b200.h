@@ -100,7 +100,10 @@ int pg_conv_wgrad_simt(const void *x, const void *dy, float *dw, int N, int H,
 int pg_conv_tc(const void *x, const void *wp, const float *bias, void *y,
                float *r_out, int N, int H, int W, int Cin, int Cout_total,
                int Cout_tile, int taps, int bias_mod, float scale, int epi,
-               float slope, void *stream);
+               float slope, void *y_pool, void *stream);
+/* y_pool (nullable, [N,H/2,W/2,Cout]): the 2x2 average pool of y (the x0.5 bilinear downsample
+ * after every discriminator block, progan_modules.py:299) written by the same epilogue; 3x3
+ * form with H %% 16 == 0, W %% 8 == 0, Cout in {32,64,128} only. */
 /* Data-gradient 3x3 conv with the PixelNorm+LeakyReLU backward of the layer in front fused into
  * the epilogue (replaces aten::convolution_backward(input) followed by the autograd chain of
  * PixelNorm/LeakyReLU, progan_modules.py:54-60,138):

@@ -27,7 +27,7 @@ SIGNATURES = {
     "pg_conv_wgrad_simt": [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
                            c_int, c_int, c_int, P],
     "pg_conv_tc": [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
-                   c_int, c_float, P],
+                   c_int, c_float, P, P],
     "pg_conv_tc_actbwd": [P, P, P, c_int, c_int, c_int, c_int, c_int, c_float, P, P, c_float, c_int, P, P],
     "pg_conv_wgrad_tc": [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                          c_float, c_int, c_int, c_int, P],

@@ -43,6 +43,7 @@ struct Conv4Params {
   const float *r_prev;                 // [N,H,W] PixelNorm rsqrt (use_pn) or nullptr
   float *colsum;                       // += per-channel sum of da_prev (bias gradient) or nullptr
   int use_pn;
+  int pool;                            // also write the 2x2-average-pooled activation (tmap_yp)
   int dbg;                             // experiment knobs (PG_DBG)
 };
 
@@ -53,7 +54,8 @@ constexpr int kC4MaxA = 8, kC4MaxW = 12;
 template <int BK, int NCB, int MT, bool RES, int COUT, int CL, bool ABW>
 __global__ void __launch_bounds__(kC4Threads, 1)
 conv4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                const __grid_constant__ CUtensorMap tmap_y, const Conv4Params p) {
+                const __grid_constant__ CUtensorMap tmap_y, const __grid_constant__ CUtensorMap tmap_yp,
+                const Conv4Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr uint32_t row_bytes = BK * 2u;                          // 128 or 64
   constexpr uint32_t box_real = 18u * 10u * row_bytes;
@@ -65,7 +67,9 @@ conv4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   const uint32_t smem_a = base + w_bytes;
   const uint32_t smem_out = smem_a + (uint32_t)(p.a_stages * MT) * kBoxPad;
   const uint32_t out_bytes = 128u * (uint32_t)COUT * 2u;
-  const uint32_t bar_base = smem_out + out_bytes;
+  // pooled staging tile (32 pooled pixels x COUT) only when the launch asks for it
+  const uint32_t smem_pool = smem_out + out_bytes;
+  const uint32_t bar_base = smem_pool + (p.pool ? out_bytes / 4u : 0u);
   auto afull = [&](int s) { return bar_base + 8u * (uint32_t)s; };
   auto aempty = [&](int s) { return bar_base + 8u * (uint32_t)(kC4MaxA + s); };
   auto wfull = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kC4MaxA + s); };
@@ -80,6 +84,7 @@ conv4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   float *bias_ptr = reinterpret_cast<float *>(gbase + (bias_s - base));
   float *ss_buf = bias_ptr + 128;                    // [2][128] partial per-pixel reductions
   uint8_t *out_ptr = gbase + (smem_out - base);
+  uint8_t *pool_ptr = gbase + (smem_pool - base);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CL > 1 ? cluster_ctarank() : 0u;
@@ -91,6 +96,7 @@ conv4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     prefetch_tmap(&tmap_x);
     prefetch_tmap(&tmap_w);
     prefetch_tmap(&tmap_y);
+    if (p.pool) prefetch_tmap(&tmap_yp);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.a_stages; ++s) {
@@ -426,6 +432,50 @@ conv4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
                          ch * out_chunk, w0, h0, n);
           tma_store_commit();
         }
+        if (!ABW && p.pool) {
+          // 2x2 average pool of the staged tile (the reference's bilinear x0.5,
+          // progan_modules.py:299): 32 pooled pixels x COUT/8 16-byte chunks over 256 threads
+          constexpr int CH8 = COUT / 8;
+          for (int item = et; item < 32 * CH8; item += kC4EpiThreads) {
+            const int pp = item / CH8, c8 = item - pp * CH8;
+            const int ph = pp >> 2, pw = pp & 3;
+            const int chunk_i = (c8 * 8) / out_chunk;
+            const uint32_t cb = (uint32_t)((c8 * 8) % out_chunk) * 2u;
+            const uint8_t *tb = out_ptr + (size_t)chunk_i * 128 * chunk_rows_bytes;
+            float acc8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const int srow = (2 * ph + (q4 >> 1)) * 8 + 2 * pw + (q4 & 1);
+              const uint4 raw = *reinterpret_cast<const uint4 *>(
+                  tb + swz((uint32_t)srow * (uint32_t)chunk_rows_bytes + cb, swz_bits));
+              const __nv_bfloat162 *h2 = reinterpret_cast<const __nv_bfloat162 *>(&raw);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __bfloat1622float2(h2[e]);
+                acc8[2 * e] += f.x;
+                acc8[2 * e + 1] += f.y;
+              }
+            }
+            uint32_t pk[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(0.25f * acc8[2 * e], 0.25f * acc8[2 * e + 1]);
+              pk[e] = *reinterpret_cast<uint32_t *>(&h);
+            }
+            uint8_t *pb = pool_ptr + (size_t)chunk_i * 32 * chunk_rows_bytes;
+            *reinterpret_cast<uint4 *>(pb + swz((uint32_t)pp * (uint32_t)chunk_rows_bytes + cb, swz_bits)) =
+                make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+          fence_proxy_async_smem();
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (et == 0 && !(p.dbg & 1)) {
+#pragma unroll
+            for (int ch = 0; ch < n_chunks; ++ch)
+              tma_store_4d(&tmap_yp, smem_pool + (uint32_t)ch * 32u * (uint32_t)chunk_rows_bytes,
+                           ch * out_chunk, w0 >> 1, h0 >> 1, n);
+            tma_store_commit();
+          }
+        }
         if (ABW && p.colsum != nullptr) {
           // per-channel sum over the warp's 32 pixels by a halving butterfly: each step trades
           // half of the remaining channels with the partner lane (CPT - 1 shuffles in total)
@@ -489,7 +539,8 @@ conv4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
 
 template <int BK, int NCB, int MT, bool RES, int COUT, int CL, bool ABW>
 static cudaError_t launch_c4(const CUtensorMap &tx, const CUtensorMap &tw, const CUtensorMap &ty,
-                             const Conv4Params &p, size_t smem, cudaStream_t stream) {
+                             const CUtensorMap &typ, const Conv4Params &p, size_t smem,
+                             cudaStream_t stream) {
   auto kern = conv4_tc_kernel<BK, NCB, MT, RES, COUT, CL, ABW>;
   static bool attr_set = false;
   static int max_ctas = 0;
@@ -525,7 +576,7 @@ static cudaError_t launch_c4(const CUtensorMap &tx, const CUtensorMap &tw, const
   int grid = p.num_super < max_ctas ? p.num_super : max_ctas;
   grid = grid / CL * CL;
   cfg.gridDim = dim3((unsigned)grid);
-  return cudaLaunchKernelEx(&cfg, kern, tx, tw, ty, p);
+  return cudaLaunchKernelEx(&cfg, kern, tx, tw, ty, typ, p);
 }
 
 }  // namespace tc
@@ -535,8 +586,9 @@ static cudaError_t launch_c4(const CUtensorMap &tx, const CUtensorMap &tw, const
 int conv4_tc_launch(const void *x, const void *wp, const float *bias, void *y, float *r_out, int N,
                     int H, int W, int Cin, int Cout, float scale, int epi, float slope,
                     cudaStream_t stream, const void *y_prev, const float *r_prev, float *colsum,
-                    int use_pn) {
+                    int use_pn, void *y_pool) {
   const bool abw = y_prev != nullptr;
+  if (abw && y_pool) return PG_ERR_UNSUPPORTED;
   if (const char *e = getenv("PG_CONV_V4"))
     if (atoi(e) == 0) return PG_ERR_UNSUPPORTED;
   int min_h = 16;
@@ -555,9 +607,10 @@ int conv4_tc_launch(const void *x, const void *wp, const float *bias, void *y, f
   p.wtile_bytes = Cout * BK * 2;
   p.epi = epi; p.scale = scale; p.slope = slope; p.bias = bias; p.r_out = r_out;
   p.y_prev = (const __nv_bfloat16 *)y_prev; p.r_prev = r_prev; p.colsum = colsum; p.use_pn = use_pn;
+  p.pool = y_pool != nullptr;
   p.dbg = 0;
   if (const char *e = getenv("PG_DBG")) p.dbg = atoi(e);
-  const int out_bytes = 128 * Cout * 2;
+  const int out_bytes = 128 * Cout * 2 + (y_pool ? 32 * Cout * 2 : 0);   // staging (+ pooled tile)
   const int misc = 1024 + 8 * (2 * tc::kC4MaxA + 2 * tc::kC4MaxW + 5) + 16 + 16 + 128 * 4 + 2 * 128 * 4 + 64;
   const int budget = 227 * 1024 - out_bytes - misc;
   const int wres = 9 * p.ncb * p.wtile_bytes;
@@ -617,14 +670,21 @@ int conv4_tc_launch(const void *x, const void *wp, const float *bias, void *y, f
     uint32_t box[4] = {(uint32_t)out_chunk, 8u, 16u, 1u};
     if (int rc = make_tmap_bf16(&ty, y, 4, dims, str, box, out_chunk * 2, "pg_conv_tc/v4(y)")) return rc;
   }
+  CUtensorMap typ = ty;
+  if (y_pool) {
+    uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)(W / 2), (uint64_t)(H / 2), (uint64_t)N};
+    uint64_t str[3] = {(uint64_t)Cout * 2, (uint64_t)(W / 2) * Cout * 2, (uint64_t)(H / 2) * (W / 2) * Cout * 2};
+    uint32_t box[4] = {(uint32_t)out_chunk, 4u, 8u, 1u};
+    if (int rc = make_tmap_bf16(&typ, y_pool, 4, dims, str, box, out_chunk * 2, "pg_conv_tc/v4(y_pool)")) return rc;
+  }
   cudaError_t e = cudaErrorInvalidValue;
   bool matched = false;
 #define PG_C4_TRY(BK_, NCB_, MT_, RES_, CO_, CL_)                                                \
   if (!matched && BK == BK_ && p.ncb == NCB_ && MT == MT_ && res == (RES_ ? 1 : 0) && Cout == CO_ && \
       CL == CL_) {                                                                               \
     matched = true;                                                                              \
-    e = abw ? tc::launch_c4<BK_, NCB_, MT_, RES_, CO_, CL_, true>(tx, tw_, ty, p, smem, stream)  \
-            : tc::launch_c4<BK_, NCB_, MT_, RES_, CO_, CL_, false>(tx, tw_, ty, p, smem, stream); \
+    e = abw ? tc::launch_c4<BK_, NCB_, MT_, RES_, CO_, CL_, true>(tx, tw_, ty, typ, p, smem, stream)  \
+            : tc::launch_c4<BK_, NCB_, MT_, RES_, CO_, CL_, false>(tx, tw_, ty, typ, p, smem, stream); \
   }
 #define PG_C4_RESIDENT(BK_, NCB_, CO_)                                                           \
   PG_C4_TRY(BK_, NCB_, 1, true, CO_, 1) PG_C4_TRY(BK_, NCB_, 2, true, CO_, 1)

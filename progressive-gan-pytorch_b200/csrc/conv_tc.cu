@@ -336,7 +336,8 @@ static int pow2_ge(int v) {
 
 extern "C" int pg_conv_tc(const void *x, const void *wp, const float *bias, void *y, float *r_out,
                           int N, int H, int W, int Cin, int Cout_total, int Cout_tile, int taps,
-                          int bias_mod, float scale, int epi, float slope, void *stream) {
+                          int bias_mod, float scale, int epi, float slope, void *y_pool,
+                          void *stream) {
   PG_CHECK_ARG(x && wp && y, "pg_conv_tc: null pointer");
   PG_CHECK_ARG(taps == 9 || taps == 1, "pg_conv_tc: taps must be 9 (3x3 pad 1) or 1");
   PG_CHECK_ARG(N > 0 && H > 0 && W > 0, "pg_conv_tc: bad dims");
@@ -354,12 +355,14 @@ extern "C" int pg_conv_tc(const void *x, const void *wp, const float *bias, void
                "pg_conv_tc: pointers must be 16-byte aligned");
   if (taps == 9 && n_tiles == 1) {   // newer kernel generations where the shape allows
     const int rc4 = conv4_tc_launch(x, wp, bias, y, r_out, N, H, W, Cin, Cout, scale, epi, slope,
-                                    (cudaStream_t)stream);
+                                    (cudaStream_t)stream, nullptr, nullptr, nullptr, 0, y_pool);
     if (rc4 != PG_ERR_UNSUPPORTED) return rc4;
     const int rc = conv3_tc_launch(x, wp, bias, y, r_out, N, H, W, Cin, Cout, scale, epi, slope,
                                    (cudaStream_t)stream);
     if (rc != PG_ERR_UNSUPPORTED) return rc;
   }
+  PG_CHECK_ARG(!y_pool, "pg_conv_tc: the fused 2x2 pool needs a 3x3 conv with H %% 16 == 0, W %% 8 == 0, "
+                        "Cout in {32,64,128} (H=%d W=%d Cout=%d taps=%d)", H, W, Cout, taps);
   tc::ConvTcParams p;
   p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.taps = taps; p.n_tiles = n_tiles;
   p.bw = W < 16 ? W : 16;

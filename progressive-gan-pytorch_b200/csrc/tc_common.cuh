@@ -288,7 +288,7 @@ int conv3_tc_launch(const void *x, const void *wp, const float *bias, void *y, f
 int conv4_tc_launch(const void *x, const void *wp, const float *bias, void *y, float *r_out, int N,
                     int H, int W, int Cin, int Cout, float scale, int epi, float slope,
                     cudaStream_t stream, const void *y_prev = nullptr, const float *r_prev = nullptr,
-                    float *colsum = nullptr, int use_pn = 0);
+                    float *colsum = nullptr, int use_pn = 0, void *y_pool = nullptr);
 
 // second-generation weight-gradient kernel (wgrad3_tc.cu); workspace pre-zeroed by the caller
 int wgrad3_tc_launch(const void *x, const void *dy, float *workspace, int N, int H, int W, int Cin,

@@ -150,21 +150,28 @@ class ConvAct(Function):
     Returns (A, r): A carries y's data but stands for the pre-activation in the graph."""
 
     @staticmethod
-    def forward(ctx, x, w, b, op, scale, slope, use_pn, prev_link=None):
+    def forward(ctx, x, w, b, op, scale, slope, use_pn, prev_link=None, pool=False):
         ctx.op, ctx.scale = op, scale
         ctx.prev_link = prev_link
         ctx.save_for_backward(x, w, b)
         ctx.set_materialize_grads(False)     # r never gets a gradient: no zero-fill per backward
-        y, r = K().conv_fwd(x, w, b, op, scale, EPI_PN_LRELU if use_pn else EPI_LRELU, slope)
+        epi = EPI_PN_LRELU if use_pn else EPI_LRELU
+        yp = None
+        if pool:          # the kernel also writes avgpool2(y) where its epilogue can (else None)
+            y, r, yp = K().conv_fwd(x, w, b, op, scale, epi, slope, pool_out=True)
+        else:
+            y, r = K().conv_fwd(x, w, b, op, scale, epi, slope)
         if r is None:
             r = torch.empty(0, device=x.device, dtype=torch.float32)
-        ctx.mark_non_differentiable(r)
-        return y, r
+        if yp is None:
+            yp = torch.empty(0, device=x.device, dtype=y.dtype)
+        ctx.mark_non_differentiable(r, yp)
+        return y, r, yp
 
     @staticmethod
-    def backward(ctx, dA, _dr):
+    def backward(ctx, dA, _dr, _dp):
         if dA is None:
-            return (None,) * 8
+            return (None,) * 9
         x, w, b = ctx.saved_tensors
         dA = dA.contiguous()
         dx = dw = db = None
@@ -194,7 +201,7 @@ class ConvAct(Function):
                 pass          # direct mode: accumulated by the Act/ActBwd kernels that produced dA
             else:
                 db = ColSum.apply(dA)
-        return dx, dw, db, None, None, None, None, None
+        return dx, dw, db, None, None, None, None, None, None
 
 
 def _bias_wanted(bias):
@@ -217,12 +224,14 @@ class Act(Function):
     gradient (column sum of dA) is produced there, fused into those kernels."""
 
     @staticmethod
-    def forward(ctx, A, r, slope, use_pn, pool, bias, link=None):
+    def forward(ctx, A, r, slope, use_pn, pool, bias, link=None, pooled=None):
         ctx.slope, ctx.use_pn, ctx.pool, ctx.bias = slope, use_pn, pool, bias
         ctx.link = link
         ctx.stash = {}
         ctx.save_for_backward(A, r)
         if pool:
+            if pooled is not None and pooled.numel() > 0:
+                return pooled.view_as(pooled)        # written by the conv's own epilogue
             return K().avgpool2(A, "nhwc")
         return A.view_as(A)
 
@@ -231,7 +240,7 @@ class Act(Function):
         link = ctx.link
         if link is not None and link.fused:
             link.fused = False         # dy already is da: the consumer's kernel did our work
-            return dy, None, None, None, None, None, None
+            return dy, None, None, None, None, None, None, None
         A, r = ctx.saved_tensors
         direct = DIRECT_GRADS and not torch.is_grad_enabled()
         addend = None
@@ -245,7 +254,7 @@ class Act(Function):
             addend = ent[0]
         da = ActBwd.apply(dy.contiguous(), A, r, ctx.slope, ctx.use_pn, ctx.pool, ctx.bias, direct, ctx,
                           addend)
-        return da, None, None, None, None, None, None
+        return da, None, None, None, None, None, None, None
 
 
 class ActBwd(Function):
@@ -299,9 +308,9 @@ STASH_SECOND_ORDER = True
 def conv_act(x, w, b, op, scale, slope=0.2, use_pn=True, pool=False, prev_link=None, make_link=False):
     """conv + bias + [PixelNorm] + LeakyReLU (+ 2x2 average pool).  make_link: also return the
     ActLink for the single conv that will consume the result (pass it there as prev_link)."""
-    A, r = ConvAct.apply(x, w, b, op, scale, slope, use_pn, prev_link)
+    A, r, pooled = ConvAct.apply(x, w, b, op, scale, slope, use_pn, prev_link, pool)
     link = ActLink(A, r, slope, use_pn, b) if (make_link and not pool) else None
-    y = Act.apply(A, r, slope, use_pn, pool, b, link)
+    y = Act.apply(A, r, slope, use_pn, pool, b, link, pooled)
     return (y, link) if make_link else y
 
 

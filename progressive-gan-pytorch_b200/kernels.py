@@ -220,9 +220,11 @@ class CudaKernels:
             ent[1] = p_._version
 
     # ------------------------------------------------------------------ conv
-    def conv_fwd(self, x, w, bias, op, scale, epi=EPI_LINEAR, slope=0.2):
+    def conv_fwd(self, x, w, bias, op, scale, epi=EPI_LINEAR, slope=0.2, pool_out=False):
         """y = epi(scale * conv(x; Wl(w)) + bias).  Returns (y, r) with r the per-pixel
-        PixelNorm rsqrt (fp32 [N,Ho,Wo]) for EPI_PN_LRELU, else None."""
+        PixelNorm rsqrt (fp32 [N,Ho,Wo]) for EPI_PN_LRELU, else None.  pool_out: returns
+        (y, r, y_pool) where y_pool = avgpool2(y) written by the same kernel, or None when the
+        shape is not served by the fused epilogue (the caller then pools separately)."""
         _chk(x, "x", ndim=4)
         _chk(w, "w", torch.float32, 4)
         if bias is not None:
@@ -239,24 +241,27 @@ class CudaKernels:
         mode = self.tc_mode(x.dtype, H, W, w.shape, op)
         nb = bias.numel() if bias is not None else 0
         st = self._stream()
+        yp = None
         if mode == "conv3":
             wp = self.packed(w, op, WL_CO_TAP_CI, torch.bfloat16)
+            if pool_out and H % 16 == 0 and W % 8 == 0 and cout in (32, 64, 128) and not (op.xpad or op.ypad):
+                yp = torch.empty((N, H // 2, W // 2, cout), device=x.device, dtype=x.dtype)
             self._call("pg_conv_tc", x.data_ptr(), wp.data_ptr(), _ptr(bias), y.data_ptr(), _ptr(r),
-                       N, H, W, cin, cout, cout, 9, nb, float(scale), epi, float(slope), st)
+                       N, H, W, cin, cout, cout, 9, nb, float(scale), epi, float(slope), _ptr(yp), st)
         elif mode == "valid":      # [N, k*k*cin] x [cout, k*k*cin]^T
             wp = self.packed(w, op, WL_CO_TAP_CI, torch.bfloat16)
             self._call("pg_conv_tc", x.data_ptr(), wp.data_ptr(), _ptr(bias), y.data_ptr(), _ptr(r),
-                       N, 1, 1, k * k * cin, cout, cout, 1, nb, float(scale), epi, float(slope), st)
+                       N, 1, 1, k * k * cin, cout, cout, 1, nb, float(scale), epi, float(slope), None, st)
         elif mode == "full":       # [N, cin] x [(pos, cout), cin]^T ; output position = flipped tap
             wp = self.packed(w, op, WL_TAP_CO_CI, torch.bfloat16, flip=not op.flip)
             self._call("pg_conv_tc", x.data_ptr(), wp.data_ptr(), _ptr(bias), y.data_ptr(), _ptr(r),
-                       N, 1, 1, cin, k * k * cout, cout, 1, nb, float(scale), epi, float(slope), st)
+                       N, 1, 1, cin, k * k * cout, cout, 1, nb, float(scale), epi, float(slope), None, st)
         else:
             wp = self.packed(w, op, WL_TAP_CI_CO, x.dtype)
             self._call("pg_conv_fwd_simt", x.data_ptr(), wp.data_ptr(), _ptr(bias), y.data_ptr(),
                        _ptr(r), N, H, W, cin, cout, k, op.pad, float(scale), epi, float(slope),
                        _dt(x), st)
-        return y, r
+        return (y, r, yp) if pool_out else (y, r)
 
     def conv_dgrad_actbwd(self, x, w, op, scale, y_prev, r_prev, slope, use_pn, colsum_out=None):
         """Fused da_prev = Jpn(a_prev)^T (m * (scale * conv(x; Wl(w)))): a data-gradient conv whose

@@ -53,7 +53,7 @@ class EmulKernels:
         return C + 1
 
     # ---- conv
-    def conv_fwd(self, x, w, bias, op, scale, epi=EPI_LINEAR, slope=0.2):
+    def conv_fwd(self, x, w, bias, op, scale, epi=EPI_LINEAR, slope=0.2, pool_out=False):
         self.launches += 1
         cd = torch.float64 if x.dtype == torch.float64 else torch.float32
         wl = logical_weight(w, op).to(x.dtype).to(cd)   # packed operands carry the activation dtype
@@ -72,6 +72,8 @@ class EmulKernels:
             y = F.pad(y, (0, op.ypad - y.shape[-1]))
         if r is not None:
             r = r.contiguous().to(torch.float64 if cd == torch.float64 else torch.float32)
+        if pool_out:
+            return y, r, None          # the emulation pools with the separate kernel
         return y, r
 
     def conv_wgrad(self, x, dy, wshape, op, scale, out=None):

@@ -349,3 +349,25 @@ def test_conv_dgrad_actbwd_fused_matches_two_kernels(KE, cfg, use_pn):
     assert helpers.rel(da, da_ref) < 8e-3
     assert helpers.rel(cs, cs_ref) < 8e-3
     K.conv_impl = "simt"
+
+
+@pytest.mark.parametrize("cfg", [(2, 32, 32, 64, 64), (3, 16, 16, 128, 128), (1, 64, 64, 32, 64),
+                                 (10, 64, 64, 128, 128), (2, 32, 64, 64, 32)])
+@pytest.mark.parametrize("epi", [EPI_PN_LRELU, EPI_LRELU])
+def test_conv_fused_avgpool_matches_separate_kernel(KE, cfg, epi):
+    """The conv epilogue's fused 2x2 average pool (bilinear x0.5, progan_modules.py:299) equals
+    pg_avgpool2 of the conv output bit for bit (same bf16 inputs, fp32 sum, one rounding)."""
+    K, E = KE
+    K.conv_impl = "tc"
+    N, H, W, Cin, Cout = cfg
+    op = ConvOp(3, 1)
+    x = rnd(N, H, W, Cin, dtype=torch.bfloat16)
+    w = torch.nn.Parameter(rnd(Cout, Cin, 3, 3, seed=1))
+    b = rnd(Cout, seed=2, scale=0.1)
+    y, r, yp = K.conv_fwd(x, w, b, op, 0.05, epi, 0.2, pool_out=True)
+    assert yp is not None
+    y2, r2 = K.conv_fwd(x, w, b, op, 0.05, epi, 0.2)
+    torch.cuda.synchronize()
+    assert torch.equal(y, y2)
+    assert torch.equal(yp, K.avgpool2(y2))
+    K.conv_impl = "simt"
