@@ -108,7 +108,8 @@ class CudaKernels:
         # bottleneck)
         self.fuse_actbwd_min_cout = 1 << 30      # ... and in the whole step neither pays: off
         self.wgrad_side_stream = None  # Trainer: deferred weight gradients run on this stream, next
-        self._side_dirty = False       # to the bandwidth-bound kernels of the data-gradient chain
+        self._side_dirty = set()       # to the bandwidth-bound kernels of the data-gradient chain
+        self._side_streams = {}        # one side stream per forking stream
         self.defer_wgrad = False       # Trainer: weight gradients accumulate in persistent workspaces
         self._wgrad_ws = {}            # (grad ptr, variant) -> (workspace, unpack entry)
         self._pending = {}             # workspaces holding partial sums since the last flush
@@ -340,7 +341,7 @@ class CudaKernels:
                 acc = 2
             else:
                 ws = torch.empty(k * k * cin * cout, device=x.device, dtype=torch.float32)
-            side = self.wgrad_side_stream if acc == 2 else None
+            side = self._side_stream_for_current() if acc == 2 else None
             if side is not None:
                 # fork: the weight gradient only needs x and dy, nothing on the main stream needs
                 # its result before flush_wgrads() — let it overlap the activation-backward /
@@ -349,7 +350,7 @@ class CudaKernels:
                 side.wait_stream(main)
                 x.record_stream(side)
                 dy.record_stream(side)
-                self._side_dirty = True
+                self._side_dirty.add(side)
             with (torch.cuda.stream(side) if side is not None else _nullctx()):
                 st = self._stream()
                 if mode == "conv3":
@@ -374,6 +375,18 @@ class CudaKernels:
                        cin, cout, k, op.pad, float(scale), int(op.swap), int(op.flip), _dt(x), st)
         return dw
 
+    def _side_stream_for_current(self):
+        """The weight-gradient stream paired with the current stream (None when the feature is
+        off): concurrent passes on different streams each get their own."""
+        if self.wgrad_side_stream is None:
+            return None
+        cur = torch.cuda.current_stream()
+        side = self._side_streams.get(cur.cuda_stream)
+        if side is None:
+            side = self.wgrad_side_stream if not self._side_streams else torch.cuda.Stream()
+            self._side_streams[cur.cuda_stream] = side
+        return side
+
     def flush_wgrads(self):
         """Fold every pending weight-gradient workspace into its gradient: one launch per
         'round', where a round holds at most one workspace per gradient tensor (a conv's own
@@ -381,9 +394,9 @@ class CudaKernels:
         kernel's read-modify-write of dw needs no atomics)."""
         if not self._pending:
             return
-        if self._side_dirty:             # join the weight-gradient stream
-            torch.cuda.current_stream().wait_stream(self.wgrad_side_stream)
-            self._side_dirty = False
+        for side in self._side_dirty:    # join the weight-gradient streams
+            torch.cuda.current_stream().wait_stream(side)
+        self._side_dirty = set()
         sig = tuple(self._pending.keys())
         tabs = self._unpack_tables.get(sig)
         if tabs is None:

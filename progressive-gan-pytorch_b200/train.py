@@ -75,6 +75,14 @@ def _g_active(G, step, fading):
     return names
 
 
+class _NullCtx:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
 class FlatBucket:
     """Flat fp32 storage for the parameters, gradients and Adam state of one network."""
 
@@ -137,7 +145,7 @@ class FlatBucket:
 class Trainer:
     def __init__(self, generator, discriminator, g_running=None, lr=1e-3, betas=(0.0, 0.99),
                  eps=1e-8, ema_decay=0.999, gp_lambda=10.0, drift=0.001, process_group=None,
-                 use_graph=False, segment_graphs=None, overlap_wgrad=True):
+                 use_graph=False, segment_graphs=None, overlap_wgrad=True, overlap_passes=True):
         self.G, self.D, self.G_run = generator, discriminator, g_running
         self.lr, self.betas, self.eps = lr, betas, eps
         self.ema_decay, self.gp_lambda, self.drift = ema_decay, gp_lambda, drift
@@ -163,6 +171,7 @@ class Trainer:
         # weight-gradient kernels (tensor-bound) run on a side stream next to the HBM-bound kernels
         # of the data-gradient chain
         self._side = torch.cuda.Stream() if (overlap_wgrad and dev.type == "cuda") else None
+        self._gp_stream = torch.cuda.Stream() if (overlap_passes and dev.type == "cuda") else None
         self._g_params = list(generator.parameters())
         self._r_params = list(g_running.parameters()) if g_running is not None else []
 
@@ -222,16 +231,28 @@ class Trainer:
         self.bD.g.zero_()
         B = real.shape[0]
         fake = G(st["z"], step=step, alpha=alpha)
+        # The gradient-penalty pass (train.py:142-151) and the real/fake pass are independent
+        # given `fake`: they run as two concurrent chains (streams; parallel branches of the
+        # captured graph).  Every gradient kernel accumulates atomically (workspaces, bias sums),
+        # so the two chains may add into the same buckets at the same time; the latency-bound
+        # low-resolution layers of one chain hide behind the large kernels of the other.
+        s2 = self._gp_stream if (self._gp_stream is not None and K.name == "cuda" and K.conv_impl == "tc") else None
+        cur = torch.cuda.current_stream() if s2 is not None else None
+        if s2 is not None:
+            s2.wait_stream(cur)
+        with (torch.cuda.stream(s2) if s2 is not None else _NullCtx()):
+            x_hat = K.interp_xhat(real, fake.detach(), st["eps"].reshape(-1)).requires_grad_(True)
+            hat = D(x_hat, step=step, alpha=alpha)
+            (g,) = torch.autograd.grad(outputs=hat.sum(), inputs=x_hat, create_graph=True)
+            gp = F_.gradient_penalty(g, self.gp_lambda)
+            gp.backward()
         both = D(torch.cat([real, fake.detach()]), step=step, alpha=alpha, mbstd_group=B)
         real_raw, fake_raw = both[:B], both[B:]
         real_predict = real_raw.mean() - self.drift * (real_raw ** 2).mean()
         fake_predict = fake_raw.mean()
         (fake_predict - real_predict).backward()
-        x_hat = K.interp_xhat(real, fake.detach(), st["eps"].reshape(-1)).requires_grad_(True)
-        hat = D(x_hat, step=step, alpha=alpha)
-        (g,) = torch.autograd.grad(outputs=hat.sum(), inputs=x_hat, create_graph=True)
-        gp = F_.gradient_penalty(g, self.gp_lambda)
-        gp.backward()
+        if s2 is not None:
+            cur.wait_stream(s2)
         K.flush_wgrads()
         st["fake"] = fake
         st["gp"] = gp.detach()
