@@ -354,6 +354,9 @@ extern "C" int pg_conv_tc(const void *x, const void *wp, const float *bias, void
   PG_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)wp & 15) == 0 && ((uintptr_t)y & 15) == 0,
                "pg_conv_tc: pointers must be 16-byte aligned");
   if (taps == 9 && n_tiles == 1) {   // newer kernel generations where the shape allows
+    const int rc5 = conv5_tc_launch(x, wp, bias, y, r_out, N, H, W, Cin, Cout, scale, epi, slope,
+                                    (cudaStream_t)stream, y_pool);
+    if (rc5 != PG_ERR_UNSUPPORTED) return rc5;
     const int rc4 = conv4_tc_launch(x, wp, bias, y, r_out, N, H, W, Cin, Cout, scale, epi, slope,
                                     (cudaStream_t)stream, nullptr, nullptr, nullptr, 0, y_pool);
     if (rc4 != PG_ERR_UNSUPPORTED) return rc4;

@@ -231,6 +231,69 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// ------------------------------------------------------- CTA pairs (cta_group::2)
+// A CTA pair (cluster of 2 on one TPC) executes one M = 256 MMA: each CTA supplies its own 128
+// rows of A and HALF of the N rows of B from the same smem offsets, the leader (rank 0) issues.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;      // clears the CTA-rank bit of a shared address
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_remote(uint32_t cluster_addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;"
+               ::"r"(cluster_addr), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the mbarrier at this offset in BOTH CTAs of the pair once the MMAs issued so far are done
+__device__ __forceinline__ void umma_commit2(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"((uint16_t)3)
+      : "memory");
+}
+// TMA loads of a CTA pair: data lands in the executing CTA's smem, the complete_tx goes to the
+// LEADER's mbarrier at the same offset (peer bit cleared)
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap *m, uint32_t bar,
+                                                 int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(m), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *m, uint32_t bar,
+                                                 int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(m), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+
 // --------------------------------------------------------------- descriptors
 // UMMA shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp layout):
 //   [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1,
@@ -294,6 +357,11 @@ int conv4_tc_launch(const void *x, const void *wp, const float *bias, void *y, f
 int wgrad3_tc_launch(const void *x, const void *dy, float *workspace, int N, int H, int W, int Cin,
                      int Cout, cudaStream_t stream);
 
+
+// CTA-pair (cta_group::2) variant of the 3x3 kernel for resident half-weights (conv5_tc.cu)
+int conv5_tc_launch(const void *x, const void *wp, const float *bias, void *y, float *r_out, int N,
+                    int H, int W, int Cin, int Cout, float scale, int epi, float slope,
+                    cudaStream_t stream, void *y_pool);
 
 // third-generation weight-gradient kernel (wgrad4_tc.cu): single halo box, paired taps
 int wgrad4_tc_launch(const void *x, const void *dy, float *workspace, int N, int H, int W, int Cin,

@@ -99,7 +99,7 @@ class CudaKernels:
     def __init__(self):
         self.lib = _lib.load()
         self.conv_impl = "tc"          # "tc": tcgen05 where the shape allows; "simt": always CUDA cores
-        self.wgrad_tc = False          # tcgen05 weight-gradient kernel (enabled once validated)
+        self.wgrad_tc = True           # tcgen05 weight-gradient kernels (False: CUDA-core wgrad)
         self.launches = 0              # kernels launched through this shim (bench `gpu_launches`)
         self._packs = {}               # id(param) -> [weakref, version, {variant: (tensor, pack args)}]
         self._pack_tables = {}         # ids of a parameter set -> (signature, device table, n)
