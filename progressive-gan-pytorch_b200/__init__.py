@@ -7,8 +7,8 @@ from .kernels import ConvOp, get_kernels, set_kernels
 from .progan_modules import (ConvBlock, Discriminator, EqualConv2d, EqualConvTranspose2d,
                              EqualLinear, Generator, PixelNorm, set_default_precision)
 from .functions import gradient_penalty
-from .train import Trainer
+from .train import ProgressiveSchedule, Trainer
 
 __all__ = ["Generator", "Discriminator", "ConvBlock", "EqualConv2d", "EqualConvTranspose2d",
            "EqualLinear", "PixelNorm", "ConvOp", "get_kernels", "set_kernels",
-           "set_default_precision", "gradient_penalty", "Trainer"]
+           "set_default_precision", "gradient_penalty", "Trainer", "ProgressiveSchedule"]

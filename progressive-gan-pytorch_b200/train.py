@@ -142,6 +142,40 @@ class FlatBucket:
         return pl
 
 
+class ProgressiveSchedule:
+    """The (step, alpha) schedule of the reference loop (train.py:100-111), as an object the
+    host loop calls once per iteration:
+
+        alpha = min(1, 2 / (total_iter // n_phases) * iteration)
+        when iteration > total_iter // n_phases: next resolution step (alpha, iteration = 0),
+        clamped at max_step with alpha = 1.
+
+    `next()` returns (step, alpha, new_resolution): new_resolution is True when the caller must
+    rebuild its data loader at 4 * 2**step pixels (train.py:110-111).  The reference hard-codes
+    3 phases and max_step = 3 (:102-109); both are parameters here."""
+
+    def __init__(self, total_iter, init_step=1, max_step=3, n_phases=3):
+        self.total_iter, self.max_step = total_iter, max_step
+        self.phase_len = total_iter // n_phases
+        self.step, self.iteration = init_step, 0
+
+    def next(self):
+        alpha = min(1, (2 / self.phase_len) * self.iteration)
+        new_res = False
+        if self.iteration > self.phase_len:
+            alpha, self.iteration = 0, 0
+            self.step += 1
+            if self.step > self.max_step:
+                alpha, self.step = 1, self.max_step
+            new_res = True
+        self.iteration += 1
+        return self.step, alpha, new_res
+
+    @property
+    def resolution(self):
+        return 4 * 2 ** self.step
+
+
 class Trainer:
     def __init__(self, generator, discriminator, g_running=None, lr=1e-3, betas=(0.0, 0.99),
                  eps=1e-8, ema_decay=0.999, gp_lambda=10.0, drift=0.001, process_group=None,
@@ -177,8 +211,17 @@ class Trainer:
 
     # ------------------------------------------------------------------ pieces
     def _allreduce(self, bucket, plan):
+        """Sum the live gradient ranges over the ranks.  When the gap between the (at most two)
+        ranges is small the whole span goes out as ONE collective — the gap holds zeros (the
+        bucket is cleared every phase and inactive layers receive no gradient) and a second NCCL
+        launch costs more than a few KB of payload."""
         if self.world > 1:
-            for a, b in plan["ranges"]:
+            rs = plan["ranges"]
+            span = rs[-1][1] - rs[0][0]
+            live = sum(b - a for a, b in rs)
+            if len(rs) > 1 and span <= 1.25 * live:
+                rs = [(rs[0][0], rs[-1][1])]
+            for a, b in rs:
                 dist.all_reduce(bucket.g[a:b], group=self.pg)
 
     def _adam(self, bucket, plan):

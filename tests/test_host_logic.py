@@ -88,3 +88,25 @@ def test_generator_step0_returns_none_and_state_dict_keys():
     assert "linear.linear.weight_orig" in D.state_dict()
     assert D.state_dict()["progression.6.conv.0.conv.weight_orig"].shape == (32, 33, 3, 3)
     assert D.state_dict()["progression.6.conv.3.conv.weight_orig"].shape == (32, 32, 4, 4)
+
+
+def test_progressive_schedule_matches_reference_loop():
+    """ProgressiveSchedule.next() against a literal transcription of train.py:97-111."""
+    import progan_b200
+    total_iter, init_step = 90, 1
+    sched = progan_b200.ProgressiveSchedule(total_iter, init_step=init_step, max_step=3)
+    step, iteration = init_step, 0
+    for i in range(3 * total_iter):
+        alpha = min(1, (2 / (total_iter // 3)) * iteration)          # train.py:100
+        reload_data = False
+        if iteration > total_iter // 3:                               # train.py:102-111
+            alpha = 0
+            iteration = 0
+            step += 1
+            if step > 3:
+                alpha = 1
+                step = 3
+            reload_data = True
+        iteration += 1
+        assert sched.next() == (step, alpha, reload_data), i
+        assert sched.resolution == 4 * 2 ** step
