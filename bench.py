@@ -133,11 +133,9 @@ def run_product(args):
     loss_h = torch.zeros(3).pin_memory()
 
     def e2e_step():
-        # public API with HOST buffers: H2D of this step's inputs + D2H of the step's losses
-        r = real_h.to(dev, non_blocking=True)
-        zz = z_h.to(dev, non_blocking=True)
-        ee = eps_h.to(dev, non_blocking=True)
-        tr.step(r, zz, ee, step, alpha)
+        # public API with HOST buffers: H2D of this step's inputs (pinned memory; Trainer.step
+        # issues the copies on its copy stream) + D2H of the step's losses, every step
+        tr.step(real_h, z_h, eps_h, step, alpha)
         loss_h.copy_(torch.stack(list(tr.metrics.values())), non_blocking=True)
 
     for _ in range(max(args.warmup, 3)):

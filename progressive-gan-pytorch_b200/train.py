@@ -206,6 +206,7 @@ class Trainer:
         # of the data-gradient chain
         self._side = torch.cuda.Stream() if (overlap_wgrad and dev.type == "cuda") else None
         self._gp_stream = torch.cuda.Stream() if (overlap_passes and dev.type == "cuda") else None
+        self._copy_stream = None
         self._g_params = list(generator.parameters())
         self._r_params = list(g_running.parameters()) if g_running is not None else []
 
@@ -322,9 +323,48 @@ class Trainer:
         self.metrics["gen_loss"].add_(st["g_loss"])
 
     # ------------------------------------------------------------------ public
+    def _stage_host_inputs(self, real, z, eps):
+        """Host (pinned) inputs -> device, on a copy stream and into one of two staging sets, so
+        the H2D transfer of iteration i+1 overlaps the kernels of iteration i (the host runs
+        ahead of the GPU); the compute stream only waits for the copy's event."""
+        dev = self.bD.p.device
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream()
+            self._staging, self._stg_free, self._stg_idx = {}, {}, 0
+        self._stg_idx ^= 1
+        key = (self._stg_idx, tuple(real.shape), tuple(z.shape))
+        stg = self._staging.get(key)
+        if stg is None:
+            stg = tuple(torch.empty(t.shape, device=dev, dtype=t.dtype) for t in (real, z, eps))
+            self._staging[key] = stg
+        cs = self._copy_stream
+        free = self._stg_free.get(key)
+        if free is not None:
+            cs.wait_event(free)              # the compute stream has consumed this set
+        with torch.cuda.stream(cs):
+            for d, h in zip(stg, (real, z, eps)):
+                d.copy_(h, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(cs)
+        cur = torch.cuda.current_stream()
+        cur.wait_event(done)
+        self._stg_key = key
+        return stg
+
     def step(self, real, z, eps, step, alpha):
-        """One full iteration on device-resident inputs: real [B,3,R,R] fp32, z [B,zdim],
-        eps [B,1,1,1] (drawn by the caller on the CPU generator, train.py:133,142)."""
+        """One full iteration: real [B,3,R,R] fp32, z [B,zdim], eps [B,1,1,1] (drawn by the caller
+        on the CPU generator, train.py:133,142) — device tensors, or host tensors (pinned for an
+        asynchronous copy), which are then transferred on a copy stream."""
+        host = (not real.is_cuda) and self.bD.p.is_cuda
+        if host:
+            real, z, eps = self._stage_host_inputs(real, z, eps)
+        self._step_device(real, z, eps, step, alpha)
+        if host:                             # staging set free again once this iteration has read it
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            self._stg_free[self._stg_key] = ev
+
+    def _step_device(self, real, z, eps, step, alpha):
         fading = 0 <= alpha < 1
         if fading:
             self.alpha_dev.fill_(float(alpha))
