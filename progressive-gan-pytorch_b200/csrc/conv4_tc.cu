@@ -334,35 +334,50 @@ conv4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) +
                                 (uint32_t)(acc * acc_stride + mt * COUT + col0);
         uint32_t vr[CPT];
-        tmem_ld<CPT>(t_addr, vr);
-        tmem_ld_wait();
-        if (mt == MT - 1) {            // accumulator stage fully read: hand it back to the MMA warp
-          tc_fence_before();
-          mbar_arrive(tempty(acc));
-        }
-        if (p.dbg & 2) continue;       // experiment: accumulator drain only
         float v[CPT];
         float r = 1.f;
         if (!ABW) {
+          // accumulator drain in 16-column pieces: the tcgen05.ld of piece c+1 is in flight while
+          // piece c is scaled and squared (TMEM reads are 64 B/clk per SM: the drain of a
+          // 128x128 fp32 tile alone is ~1000 cycles)
+          constexpr int CH = 16, NCHK = CPT / CH;
           float ss = 0.f;
+          tmem_ld<CH>(t_addr, vr);
 #pragma unroll
-          for (int j = 0; j < CPT; j += 4) {
-            const float4 b4 = *reinterpret_cast<const float4 *>(bias_ptr + col0 + j);
-            v[j] = fmaf(__uint_as_float(vr[j]), scale, b4.x);
-            v[j + 1] = fmaf(__uint_as_float(vr[j + 1]), scale, b4.y);
-            v[j + 2] = fmaf(__uint_as_float(vr[j + 2]), scale, b4.z);
-            v[j + 3] = fmaf(__uint_as_float(vr[j + 3]), scale, b4.w);
-            ss = fmaf(v[j], v[j], ss);
-            ss = fmaf(v[j + 1], v[j + 1], ss);
-            ss = fmaf(v[j + 2], v[j + 2], ss);
-            ss = fmaf(v[j + 3], v[j + 3], ss);
+          for (int c = 0; c < NCHK; ++c) {
+            tmem_ld_wait();
+            if (c + 1 < NCHK) {
+              tmem_ld<CH>(t_addr + (uint32_t)((c + 1) * CH), vr + (c + 1) * CH);
+            } else if (mt == MT - 1) {   // accumulator stage fully read: hand it back to the MMA warp
+              tc_fence_before();
+              mbar_arrive(tempty(acc));
+            }
+#pragma unroll
+            for (int j = c * CH; j < (c + 1) * CH; j += 4) {
+              const float4 b4 = *reinterpret_cast<const float4 *>(bias_ptr + col0 + j);
+              v[j] = fmaf(__uint_as_float(vr[j]), scale, b4.x);
+              v[j + 1] = fmaf(__uint_as_float(vr[j + 1]), scale, b4.y);
+              v[j + 2] = fmaf(__uint_as_float(vr[j + 2]), scale, b4.z);
+              v[j + 3] = fmaf(__uint_as_float(vr[j + 3]), scale, b4.w);
+              ss = fmaf(v[j], v[j], ss);
+              ss = fmaf(v[j + 1], v[j + 1], ss);
+              ss = fmaf(v[j + 2], v[j + 2], ss);
+              ss = fmaf(v[j + 3], v[j + 3], ss);
+            }
           }
+          if (p.dbg & 2) continue;       // experiment: accumulator drain only
           if (p.epi == PG_EPI_PN_LRELU) {
             ss_buf[part * 128 + row] = ss;
             asm volatile("bar.sync 2, 256;" ::: "memory");
             r = rsqrtf((ss_buf[row] + ss_buf[128 + row]) * invC + 1e-8f);
           }
         } else {
+          tmem_ld<CPT>(t_addr, vr);
+          tmem_ld_wait();
+          if (mt == MT - 1) {            // accumulator stage fully read: hand it back to the MMA warp
+            tc_fence_before();
+            mbar_arrive(tempty(acc));
+          }
           // da = r (u - p <p,u>/C), u = m * dh, (p, m) rebuilt from the stored activation
           float s_pu = 0.f;
 #pragma unroll
