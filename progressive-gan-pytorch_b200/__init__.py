@@ -4,11 +4,12 @@ Drop-in for the hot path of gwilczynski95/Progressive-GAN-pytorch:
     from progan_b200 import Generator, Discriminator      # instead of progan_modules
 """
 from .kernels import ConvOp, get_kernels, set_kernels
-from .progan_modules import (ConvBlock, Discriminator, EqualConv2d, EqualConvTranspose2d,
-                             EqualLinear, Generator, PixelNorm, set_default_precision)
+from .progan_modules import (ConvBlock, CorrectDiscriminator, CorrectGenerator, Discriminator,
+                             EqualConv2d, EqualConvTranspose2d, EqualLinear, Generator, PixelNorm,
+                             set_default_precision)
 from .functions import gradient_penalty
 from .train import ProgressiveSchedule, Trainer
 
-__all__ = ["Generator", "Discriminator", "ConvBlock", "EqualConv2d", "EqualConvTranspose2d",
+__all__ = ["Generator", "Discriminator", "CorrectGenerator", "CorrectDiscriminator", "ConvBlock", "EqualConv2d", "EqualConvTranspose2d",
            "EqualLinear", "PixelNorm", "ConvOp", "get_kernels", "set_kernels",
            "set_default_precision", "gradient_penalty", "Trainer", "ProgressiveSchedule"]

@@ -422,7 +422,7 @@ class CudaKernels:
     def mbstd_channels(self, C, dtype):
         """Physical channel count of the minibatch-stddev output (C real + 1 statistic):
         padded to a multiple of 32 on the tensor-core path."""
-        if self.conv_impl == "tc" and dtype == torch.bfloat16:
+        if self.conv_impl == "tc" and dtype == torch.bfloat16 and C % 32 == 0 and C <= 256:
             return ((C + 1 + 31) // 32) * 32
         return C + 1
 

@@ -262,3 +262,106 @@ class Discriminator(nn.Module, _AlphaMixin):
         C = out.shape[-1]
         d = F_.PwFwd.apply(out, lin.weight_orig, lin.bias, "reduce", C, 1, 1, C, self.linear.scale, dt)
         return d.view(-1, 1)
+
+
+class CorrectGenerator(nn.Module, _AlphaMixin):
+    """The reference's CorrectGenerator (progan_modules.py:479-552; cifar_train.py /
+    proper_cifar_train.py): 4x4 stem = ConvTranspose + conv in one Sequential, three ConvBlocks
+    up to 32 px, a to_rgb head per resolution (4 px included), `step` counted from 1 = 4 px.
+    Same kernels as Generator; same state-dict keys/shapes/order as the reference class."""
+
+    def __init__(self, input_code_dim=512, in_channel=512, pixel_norm=True, tanh=False, max_step=4,
+                 precision=None):
+        super().__init__()
+        self.input_dim = input_code_dim
+        self.in_channel = in_channel
+        self.tanh = tanh
+        self.pixel_norm = pixel_norm
+        self.precision = precision or _DEFAULT_PRECISION
+        c = in_channel
+        self.progression_4 = nn.Sequential(EqualConvTranspose2d(input_code_dim, c, 4, 1, 0), PixelNorm(),
+                                           _LeakyMarker(0.2), EqualConv2d(c, c, 3, padding=1),
+                                           PixelNorm(), _LeakyMarker(0.2))
+        self.progression_8 = ConvBlock(c, c, 3, 1, pixel_norm=pixel_norm)
+        self.progression_16 = ConvBlock(c, c, 3, 1, pixel_norm=pixel_norm)
+        self.progression_32 = ConvBlock(c, c, 3, 1, pixel_norm=pixel_norm)
+        self.to_rgb_4 = EqualConv2d(c, 3, 1)
+        self.to_rgb_8 = EqualConv2d(c, 3, 1)
+        self.to_rgb_16 = EqualConv2d(c, 3, 1)
+        self.to_rgb_32 = EqualConv2d(c, 3, 1)
+        self.max_step = max_step
+
+    def _output(self, feat1, feat2, head1, head2, alpha, fading, dt):
+        """(:512-521): blend with the upsampled previous head iff 0 <= alpha < 1, then tanh."""
+        out = _to_rgb(feat2, head2, dt)
+        if fading:
+            skip = F_.upsample2(_to_rgb(feat1, head1, dt), "nchw")
+            out = F_.Blend.apply(skip, out, self._alpha(alpha, out.device))
+        return F_.Tanh.apply(out) if self.tanh else out
+
+    def forward(self, input, step=0, alpha=-1):
+        if step > self.max_step:
+            step = self.max_step
+        dt = _act_dtype(self.precision)
+        fading = torch.is_tensor(alpha) or (0 <= alpha < 1)
+        z = input.reshape(-1, 1, 1, self.input_dim).to(dt).contiguous()
+        # the stem applies PixelNorm after both convs whatever `pixel_norm` says (:487-494)
+        out_4 = _fused_layer(z, self.progression_4[0], 0.2, True)
+        out_4 = _fused_layer(out_4, self.progression_4[3], 0.2, True)
+        if step == 1:
+            out = _to_rgb(out_4, self.to_rgb_4, dt)
+            return F_.Tanh.apply(out) if self.tanh else out
+        out_8 = self.progression_8(F_.upsample2(out_4))
+        if step == 2:
+            if self.tanh:                     # reference quirk (:534-537): no blend on this path
+                return F_.Tanh.apply(_to_rgb(out_8, self.to_rgb_8, dt))
+            return self._output(out_4, out_8, self.to_rgb_4, self.to_rgb_8, alpha, fading, dt)
+        out_16 = self.progression_16(F_.upsample2(out_8))
+        if step == 3:
+            return self._output(out_8, out_16, self.to_rgb_8, self.to_rgb_16, alpha, fading, dt)
+        out_32 = self.progression_32(F_.upsample2(out_16))
+        if step == 4:
+            return self._output(out_16, out_32, self.to_rgb_16, self.to_rgb_32, alpha, fading, dt)
+        return None                           # step <= 0: the reference falls through every `if`
+
+
+class CorrectDiscriminator(nn.Module, _AlphaMixin):
+    """The reference's CorrectDiscriminator (progan_modules.py:555-598): four blocks of constant
+    width, `step` counted from 1 = 4 px, fade-in at every step > 1, minibatch-stddev before the
+    last block."""
+
+    def __init__(self, feat_dim=512, precision=None):
+        super().__init__()
+        self.feat_dim = feat_dim
+        self.precision = precision or _DEFAULT_PRECISION
+        f = feat_dim
+        self.progression = nn.ModuleList([ConvBlock(f, f, 3, 1), ConvBlock(f, f, 3, 1),
+                                          ConvBlock(f, f, 3, 1), ConvBlock(f + 1, f, 3, 1, 4, 0)])
+        self.from_rgb = nn.ModuleList([EqualConv2d(3, f, 1) for _ in range(4)])
+        self.n_layer = len(self.progression)
+        self.linear = EqualLinear(f, 1)
+
+    def forward(self, input, step=0, alpha=-1, mbstd_group=None):
+        if step < 1:
+            raise RuntimeError("CorrectDiscriminator: step must be >= 1 (the reference fails with an "
+                               "unbound `out` for step 0, progan_modules.py:578-596)")
+        dt = _act_dtype(self.precision)
+        fading = torch.is_tensor(alpha) or (0 <= alpha < 1)
+        x = input.contiguous()
+        if x.dtype != _img_dtype(self.precision):
+            x = x.to(_img_dtype(self.precision))
+        out = None
+        for i in range(step, 0, -1):
+            index = self.n_layer - i
+            if i == step:
+                out = _from_rgb(x, self.from_rgb[index], dt)
+            if i == 1:
+                out = F_.Mbstd.apply(out, F_.K().mbstd_channels(out.shape[-1], out.dtype), mbstd_group)
+            out = self.progression[index](out, pool=(i > 1))
+            if i > 1 and i == step and fading:
+                skip = _from_rgb(F_.avgpool2(x, "nchw"), self.from_rgb[index + 1], dt)
+                out = F_.Blend.apply(skip, out, self._alpha(alpha, out.device))
+        lin = self.linear.linear
+        C = out.shape[-1]
+        d = F_.PwFwd.apply(out, lin.weight_orig, lin.bias, "reduce", C, 1, 1, C, self.linear.scale, dt)
+        return d.view(-1, 1)

@@ -23,10 +23,37 @@ CASES = {
 }
 
 
-def model_shapes(channel, z_dim, pixel_norm):
+# the Correct* rewiring of the same blocks (progan_modules.py:479-598; step 1 = 4 px ... 4 = 32 px)
+CORRECT_CASES = {
+    "c1_a1.0": (32, 32, 1, 1.0, 4, False, True),
+    "c2_a0.5": (32, 32, 2, 0.5, 4, False, True),
+    "c2_a0.5_tanh": (32, 32, 2, 0.5, 4, True, True),      # quirk: tanh path skips the blend at step 2
+    "c3_a0.25": (32, 16, 3, 0.25, 4, False, True),
+    "c4_a1.0_nopn": (32, 32, 4, 1.0, 2, False, False),
+    "c4_a0.5": (32, 32, 4, 0.5, 2, False, True),
+}
+
+
+def family(name):
+    return "correct" if name in CORRECT_CASES else "base"
+
+
+def classes(mod, name):
+    """(Generator class, Discriminator class) of `mod` (the reference module or the mirror)."""
+    if family(name) == "correct":
+        return mod.CorrectGenerator, mod.CorrectDiscriminator
+    return mod.Generator, mod.Discriminator
+
+
+def model_shapes(channel, z_dim, pixel_norm, fam="base"):
     """state-dict key -> shape, taken from the host mirror (identical to the reference's;
     make_golden.py asserts that)."""
     import progan_b200
+    if fam == "correct":
+        G = progan_b200.CorrectGenerator(input_code_dim=z_dim, in_channel=channel, pixel_norm=pixel_norm)
+        D = progan_b200.CorrectDiscriminator(feat_dim=channel)
+        return ({k: tuple(v.shape) for k, v in G.state_dict().items()},
+                {k: tuple(v.shape) for k, v in D.state_dict().items()})
     G = progan_b200.Generator(input_code_dim=z_dim, in_channel=channel, pixel_norm=pixel_norm)
     D = progan_b200.Discriminator(feat_dim=channel)
     return ({k: tuple(v.shape) for k, v in G.state_dict().items()},
@@ -44,11 +71,11 @@ def make_state(shapes, seed):
 
 
 def make_inputs(name):
-    ch, zd, step, alpha, B, tanh, pn = CASES[name]
-    gs, ds = model_shapes(ch, zd, pn)
+    ch, zd, step, alpha, B, tanh, pn = CASES[name] if name in CASES else CORRECT_CASES[name]
+    gs, ds = model_shapes(ch, zd, pn, family(name))
     G_state, D_state = make_state(gs, 100), make_state(ds, 200)
     g = torch.Generator().manual_seed(1234)
-    R = 4 * 2 ** step
+    R = 4 * 2 ** step if family(name) == "base" else 2 * 2 ** step
     real = torch.rand(B, 3, R, R, generator=g) * 2 - 1
     z = torch.randn(B, zd, generator=g)
     eps = torch.rand(B, 1, 1, 1, generator=g)

@@ -25,11 +25,12 @@ def run_case(name):
 
     inp = common.make_inputs(name)
     step, alpha = inp["step"], inp["alpha"]
-    G = R.Generator(input_code_dim=inp["z_dim"], in_channel=inp["channel"],
-                    pixel_norm=inp["pixel_norm"], tanh=inp["tanh"])
-    D = R.Discriminator(feat_dim=inp["channel"])
-    Grun = R.Generator(input_code_dim=inp["z_dim"], in_channel=inp["channel"],
-                       pixel_norm=inp["pixel_norm"], tanh=inp["tanh"])
+    GC, DC = common.classes(R, name)
+    G = GC(input_code_dim=inp["z_dim"], in_channel=inp["channel"],
+           pixel_norm=inp["pixel_norm"], tanh=inp["tanh"])
+    D = DC(feat_dim=inp["channel"])
+    Grun = GC(input_code_dim=inp["z_dim"], in_channel=inp["channel"],
+              pixel_norm=inp["pixel_norm"], tanh=inp["tanh"])
     assert {k: tuple(v.shape) for k, v in G.state_dict().items()} == \
         {k: tuple(v.shape) for k, v in inp["G"].items()}
     assert {k: tuple(v.shape) for k, v in D.state_dict().items()} == \
@@ -91,7 +92,10 @@ def run_case(name):
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    for name in common.CASES:
+    only = sys.argv[1:]
+    for name in list(common.CASES) + list(common.CORRECT_CASES):
+        if only and name not in only and not (only == ["correct"] and name in common.CORRECT_CASES):
+            continue
         res = run_case(name)
         path = os.path.join(common.HERE, name + ".pt")
         torch.save(res, path)

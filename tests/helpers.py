@@ -11,10 +11,12 @@ def rel(a, b):
     return float((a - b).norm() / (b.norm() + 1e-30))
 
 
-def build_models(inp, precision, device="cpu", dtype=torch.float32):
-    G = progan_b200.Generator(input_code_dim=inp["z_dim"], in_channel=inp["channel"],
-                              pixel_norm=inp["pixel_norm"], tanh=inp["tanh"], precision=precision)
-    D = progan_b200.Discriminator(feat_dim=inp["channel"], precision=precision)
+def build_models(inp, precision, device="cpu", dtype=torch.float32, name=None):
+    import common
+    GC, DC = common.classes(progan_b200, name) if name else (progan_b200.Generator, progan_b200.Discriminator)
+    G = GC(input_code_dim=inp["z_dim"], in_channel=inp["channel"],
+           pixel_norm=inp["pixel_norm"], tanh=inp["tanh"], precision=precision)
+    D = DC(feat_dim=inp["channel"], precision=precision)
     G.load_state_dict(inp["G"])
     D.load_state_dict(inp["D"])
     return G.to(device=device, dtype=dtype), D.to(device=device, dtype=dtype)

@@ -1,0 +1,95 @@
+"""The Correct* rewiring (progan_modules.py:479-598: cifar_train.py / proper_cifar_train.py
+models) through the product modules, pinned to golden vectors recorded from the REAL
+reference classes: forward outputs, gradient penalty, every parameter gradient and the
+parameters after torch.optim.Adam(betas=(0, .99)) steps, EMA included.
+
+CPU: kernels emulated in torch (host/autograd logic).  GPU: the CUDA kernels in fp32 check
+mode against the same fixtures, and the bf16 tcgen05 path against the fp32 one."""
+import os
+
+import pytest
+import torch
+from torch import optim
+
+import common
+import helpers
+import progan_b200
+from emul_kernels import EmulKernels
+
+
+def _run_case(name, precision, device):
+    inp = common.make_inputs(name)
+    G, D = helpers.build_models(inp, precision, device=device, name=name)
+    Grun, _ = helpers.build_models(inp, precision, device=device, name=name)
+    g_opt = optim.Adam(G.parameters(), lr=0.001, betas=(0.0, 0.99))
+    d_opt = optim.Adam(D.parameters(), lr=0.001, betas=(0.0, 0.99))
+    real, z, eps = inp["real"].to(device), inp["z"].to(device), inp["eps"].to(device)
+    res, fake = helpers.product_train_step(G, D, real, z, eps, inp["step"], inp["alpha"], fused_gp=False)
+    d_opt.step()
+    loss, g_grads = helpers.product_g_phase(G, D, fake, inp["step"], inp["alpha"])
+    g_opt.step()
+    with torch.no_grad():
+        for (k, pr), (_, pg) in zip(Grun.named_parameters(), G.named_parameters()):
+            pr.mul_(0.999).add_(pg, alpha=1 - 0.999)
+    return inp, res, loss, g_grads, G, D, Grun
+
+
+def _check(name, res, loss, g_grads, G, D, Grun, tol):
+    gold = torch.load(os.path.join(common.HERE, name + ".pt"), weights_only=True)
+    for k in ("real_predict", "fake", "hat_predict", "grad_x_hat"):
+        assert helpers.rel(res[k], gold[k]) < tol, k
+    assert helpers.rel(res["grad_penalty"], gold["grad_penalty"]) < tol
+    assert abs(float(loss) - float(gold["gen_loss"])) <= tol * abs(float(gold["gen_loss"])) + 1e-6
+    assert sorted(res["d_grads"]) == sorted(gold["d_grads"])
+    for k, g in res["d_grads"].items():
+        s = gold["d_grads"][k]
+        assert float((common.summarize(g, k) - s).norm()) <= 20 * tol * float(s.norm()) + 1e-7, k
+    for k, g in g_grads.items():
+        if k in gold["g_grads"]:
+            s = gold["g_grads"][k]
+            assert float((common.summarize(g, k) - s).norm()) <= 20 * tol * float(s.norm()) + 1e-7, k
+    for tag, mod in (("d_params_after", D), ("g_params_after", G), ("g_running_after", Grun)):
+        for k, p in mod.named_parameters():
+            s = gold[tag][k]
+            assert float((common.summarize(p, k) - s).norm()) <= tol * float(s.norm()) + 1e-7, (tag, k)
+
+
+@pytest.mark.parametrize("name", list(common.CORRECT_CASES))
+def test_correct_variants_match_reference_golden_cpu(name):
+    prev = progan_b200.set_kernels(EmulKernels())
+    try:
+        inp, res, loss, g_grads, G, D, Grun = _run_case(name, "fp32", "cpu")
+        _check(name, res, loss, g_grads, G, D, Grun, 2e-4)
+    finally:
+        progan_b200.set_kernels(prev)
+
+
+def test_correct_state_dict_layout():
+    """Key names/order of the mirrors = what the golden generator asserted against the reference."""
+    G = progan_b200.CorrectGenerator(input_code_dim=16, in_channel=32)
+    keys = list(G.state_dict().keys())
+    assert keys[:4] == ["progression_4.0.conv.bias", "progression_4.0.conv.weight_orig",
+                        "progression_4.3.conv.bias", "progression_4.3.conv.weight_orig"]
+    assert G.state_dict()["progression_4.0.conv.weight_orig"].shape == (16, 32, 4, 4)     # IOHW
+    D = progan_b200.CorrectDiscriminator(feat_dim=32)
+    assert D.state_dict()["progression.3.conv.0.conv.weight_orig"].shape == (32, 33, 3, 3)
+    assert D.state_dict()["progression.3.conv.3.conv.weight_orig"].shape == (32, 32, 4, 4)
+    with pytest.raises(RuntimeError):
+        D(torch.zeros(1, 3, 4, 4), step=0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(common.CORRECT_CASES))
+def test_correct_variants_cuda_check_mode_and_bf16(name):
+    K = progan_b200.get_kernels()
+    K.conv_impl, K.wgrad_tc = "simt", False
+    K.invalidate_packs()
+    inp, res, loss, g_grads, G, D, Grun = _run_case(name, "fp32", "cuda")
+    _check(name, res, loss, g_grads, G, D, Grun, 1e-3)
+    # product mode (bf16, tcgen05 where the shapes allow): forward within the north_star gate
+    K.conv_impl, K.wgrad_tc = "tc", True
+    K.invalidate_packs()
+    inp, res16, loss16, _, _, _, _ = _run_case(name, "bf16", "cuda")
+    assert helpers.rel(res16["fake"], res["fake"]) < 1e-2
+    assert helpers.rel(res16["real_predict"], res["real_predict"]) < 2e-2
+    assert helpers.rel(res16["grad_penalty"], res["grad_penalty"]) < 5e-2
