@@ -5,11 +5,13 @@ Drop-in for the hot path of gwilczynski95/Progressive-GAN-pytorch:
 """
 from .kernels import ConvOp, get_kernels, set_kernels
 from .progan_modules import (ConvBlock, CorrectDiscriminator, CorrectGenerator, Discriminator,
-                             EqualConv2d, EqualConvTranspose2d, EqualLinear, Generator, PixelNorm,
+                             EqualConv2d, EqualConvTranspose2d, EqualLinear, Generator, MnistConvBlock,
+                             PixelNorm,
                              set_default_precision)
 from .functions import gradient_penalty
 from .train import ProgressiveSchedule, Trainer
+from . import mnist_pggan
 
-__all__ = ["Generator", "Discriminator", "CorrectGenerator", "CorrectDiscriminator", "ConvBlock", "EqualConv2d", "EqualConvTranspose2d",
+__all__ = ["Generator", "Discriminator", "CorrectGenerator", "CorrectDiscriminator", "mnist_pggan", "ConvBlock", "EqualConv2d", "EqualConvTranspose2d",
            "EqualLinear", "PixelNorm", "ConvOp", "get_kernels", "set_kernels",
            "set_default_precision", "gradient_penalty", "Trainer", "ProgressiveSchedule"]

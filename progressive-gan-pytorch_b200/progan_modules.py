@@ -130,6 +130,23 @@ class ConvBlock(nn.Module):
         return _fused_layer(x, self.conv[self._c2], 0.2, self.pixel_norm, pool, prev_link=link)
 
 
+class MnistConvBlock(nn.Module):
+    """conv -> [PixelNorm] -> LeakyReLU(0.2): the single-conv block of the mnist models
+    (progan_modules.py:151-164); state-dict index conv.0."""
+
+    def __init__(self, in_channel, out_channel, kernel_size, padding, pixel_norm=True):
+        super().__init__()
+        mods = [EqualConv2d(in_channel, out_channel, kernel_size, padding=padding)]
+        if pixel_norm:
+            mods.append(PixelNorm())
+        mods.append(_LeakyMarker(0.2))
+        self.conv = nn.Sequential(*mods)
+        self.pixel_norm = pixel_norm
+
+    def forward(self, x, pool=False):
+        return _fused_layer(x, self.conv[0], 0.2, self.pixel_norm, pool)
+
+
 class _AlphaMixin:
     @staticmethod
     def _alpha(alpha, device):
@@ -143,7 +160,7 @@ class _AlphaMixin:
 def _to_rgb(feat, m, act_dtype):
     h = m.conv
     C = feat.shape[-1]
-    return F_.PwFwd.apply(feat, h.weight_orig, h.bias, "reduce", C, 3, 1, C, m.scale, act_dtype)
+    return F_.PwFwd.apply(feat, h.weight_orig, h.bias, "reduce", C, m.cout, 1, C, m.scale, act_dtype)
 
 
 def _from_rgb(img, m, act_dtype):

@@ -34,14 +34,30 @@ CORRECT_CASES = {
 }
 
 
+# mnist_pggan.py (BASELINE config 0): 1-channel images, single-conv blocks, step 1 = 8 px ... 3 = 32 px
+MNIST_CASES = {
+    "m1_a1.0": (32, 32, 1, 1.0, 4, True, True),
+    "m2_a0.5": (32, 32, 2, 0.5, 4, True, True),
+    "m3_a0.25": (32, 16, 3, 0.25, 4, False, True),
+    "m3_a1.0_nopn": (32, 32, 3, 1.0, 2, True, False),
+}
+
+
 def family(name):
-    return "correct" if name in CORRECT_CASES else "base"
+    return "correct" if name in CORRECT_CASES else ("mnist" if name in MNIST_CASES else "base")
 
 
 def classes(mod, name):
-    """(Generator class, Discriminator class) of `mod` (the reference module or the mirror)."""
-    if family(name) == "correct":
+    """(Generator class, Discriminator class) of `mod` — the reference's progan_modules (the
+    mnist family lives in its sibling module mnist_pggan) or the mirror package."""
+    fam = family(name)
+    if fam == "correct":
         return mod.CorrectGenerator, mod.CorrectDiscriminator
+    if fam == "mnist":
+        if hasattr(mod, "mnist_pggan"):
+            return mod.mnist_pggan.Generator, mod.mnist_pggan.Discriminator
+        import mnist_pggan
+        return mnist_pggan.Generator, mnist_pggan.Discriminator
     return mod.Generator, mod.Discriminator
 
 
@@ -49,9 +65,13 @@ def model_shapes(channel, z_dim, pixel_norm, fam="base"):
     """state-dict key -> shape, taken from the host mirror (identical to the reference's;
     make_golden.py asserts that)."""
     import progan_b200
-    if fam == "correct":
-        G = progan_b200.CorrectGenerator(input_code_dim=z_dim, in_channel=channel, pixel_norm=pixel_norm)
-        D = progan_b200.CorrectDiscriminator(feat_dim=channel)
+    if fam in ("correct", "mnist"):
+        if fam == "correct":
+            G = progan_b200.CorrectGenerator(input_code_dim=z_dim, in_channel=channel, pixel_norm=pixel_norm)
+            D = progan_b200.CorrectDiscriminator(feat_dim=channel)
+        else:
+            G = progan_b200.mnist_pggan.Generator(input_code_dim=z_dim, in_channel=channel, pixel_norm=pixel_norm)
+            D = progan_b200.mnist_pggan.Discriminator(feat_dim=channel)
         return ({k: tuple(v.shape) for k, v in G.state_dict().items()},
                 {k: tuple(v.shape) for k, v in D.state_dict().items()})
     G = progan_b200.Generator(input_code_dim=z_dim, in_channel=channel, pixel_norm=pixel_norm)
@@ -71,12 +91,12 @@ def make_state(shapes, seed):
 
 
 def make_inputs(name):
-    ch, zd, step, alpha, B, tanh, pn = CASES[name] if name in CASES else CORRECT_CASES[name]
+    ch, zd, step, alpha, B, tanh, pn = (CASES.get(name) or CORRECT_CASES.get(name) or MNIST_CASES[name])
     gs, ds = model_shapes(ch, zd, pn, family(name))
     G_state, D_state = make_state(gs, 100), make_state(ds, 200)
     g = torch.Generator().manual_seed(1234)
-    R = 4 * 2 ** step if family(name) == "base" else 2 * 2 ** step
-    real = torch.rand(B, 3, R, R, generator=g) * 2 - 1
+    R = 2 * 2 ** step if family(name) == "correct" else 4 * 2 ** step
+    real = torch.rand(B, 1 if family(name) == "mnist" else 3, R, R, generator=g) * 2 - 1
     z = torch.randn(B, zd, generator=g)
     eps = torch.rand(B, 1, 1, 1, generator=g)
     return dict(G=G_state, D=D_state, real=real, z=z, eps=eps, step=step, alpha=alpha,

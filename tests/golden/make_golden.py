@@ -93,8 +93,8 @@ def run_case(name):
 if __name__ == "__main__":
     torch.set_num_threads(8)
     only = sys.argv[1:]
-    for name in list(common.CASES) + list(common.CORRECT_CASES):
-        if only and name not in only and not (only == ["correct"] and name in common.CORRECT_CASES):
+    for name in list(common.CASES) + list(common.CORRECT_CASES) + list(common.MNIST_CASES):
+        if only and name not in only and common.family(name) not in only:
             continue
         res = run_case(name)
         path = os.path.join(common.HERE, name + ".pt")

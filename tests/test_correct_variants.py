@@ -1,5 +1,5 @@
 """The Correct* rewiring (progan_modules.py:479-598: cifar_train.py / proper_cifar_train.py
-models) through the product modules, pinned to golden vectors recorded from the REAL
+models) and the mnist_pggan.py models (BASELINE config 0) through the product modules, pinned to golden vectors recorded from the REAL
 reference classes: forward outputs, gradient penalty, every parameter gradient and the
 parameters after torch.optim.Adam(betas=(0, .99)) steps, EMA included.
 
@@ -54,7 +54,7 @@ def _check(name, res, loss, g_grads, G, D, Grun, tol):
             assert float((common.summarize(p, k) - s).norm()) <= tol * float(s.norm()) + 1e-7, (tag, k)
 
 
-@pytest.mark.parametrize("name", list(common.CORRECT_CASES))
+@pytest.mark.parametrize("name", list(common.CORRECT_CASES) + list(common.MNIST_CASES))
 def test_correct_variants_match_reference_golden_cpu(name):
     prev = progan_b200.set_kernels(EmulKernels())
     try:
@@ -79,7 +79,7 @@ def test_correct_state_dict_layout():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", list(common.CORRECT_CASES))
+@pytest.mark.parametrize("name", list(common.CORRECT_CASES) + list(common.MNIST_CASES))
 def test_correct_variants_cuda_check_mode_and_bf16(name):
     K = progan_b200.get_kernels()
     K.conv_impl, K.wgrad_tc = "simt", False
