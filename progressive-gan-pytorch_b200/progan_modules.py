@@ -382,3 +382,139 @@ class CorrectDiscriminator(nn.Module, _AlphaMixin):
         C = out.shape[-1]
         d = F_.PwFwd.apply(out, lin.weight_orig, lin.bias, "reduce", C, 1, 1, C, self.linear.scale, dt)
         return d.view(-1, 1)
+
+
+class _EmbedHolder(nn.Module):
+    def __init__(self, n, d):
+        super().__init__()
+        self.weight_orig = nn.Parameter(torch.randn(n, d))       # embed.weight.data.normal_() (:113)
+
+
+class EqualEmbed(nn.Module):
+    """nn.Embedding with equalized LR (progan_modules.py:109-117): fan_in = embedding_dim (:24).
+    The row gather is host-side glue (B x dim floats), not a kernel of the hot path."""
+
+    def __init__(self, num_embeddings, embedding_dim):
+        super().__init__()
+        self.embed = _EmbedHolder(num_embeddings, embedding_dim)
+        self.scale = sqrt(2 / embedding_dim)
+
+    def forward(self, label):
+        return torch.nn.functional.embedding(label, self.embed.weight_orig) * self.scale
+
+
+class ConditionalCorrectGenerator(CorrectGenerator):
+    """Class-conditional generator of conditional_proper_cifar_train.py / conditional_proper_wikiart.py
+    (progan_modules.py:601-694): the label embedding (dimension = input_code_dim) is concatenated
+    to z in front of the 4x4 ConvTranspose stem; six resolution steps (4 ... 128 px)."""
+
+    def __init__(self, input_code_dim=512, num_of_classes=10, in_channel=512, pixel_norm=True, tanh=False,
+                 max_step=4, do_equal_embed=False, precision=None):
+        nn.Module.__init__(self)
+        self.input_dim = input_code_dim
+        self.in_channel = in_channel
+        self.tanh = tanh
+        self.pixel_norm = pixel_norm
+        self.num_of_classes = num_of_classes
+        self.embedding_dim = input_code_dim
+        self.do_equal_embed = do_equal_embed
+        self.precision = precision or _DEFAULT_PRECISION
+        c = in_channel
+        if do_equal_embed:
+            self.embedding = EqualEmbed(num_of_classes, self.embedding_dim)
+        else:
+            self.embedding = nn.Embedding(num_of_classes, embedding_dim=self.embedding_dim)
+        self.progression_4 = nn.Sequential(
+            EqualConvTranspose2d(input_code_dim + self.embedding_dim, c, 4, 1, 0), PixelNorm(),
+            _LeakyMarker(0.2), EqualConv2d(c, c, 3, padding=1), PixelNorm(), _LeakyMarker(0.2))
+        self.progression_8 = ConvBlock(c, c, 3, 1, pixel_norm=pixel_norm)
+        self.progression_16 = ConvBlock(c, c, 3, 1, pixel_norm=pixel_norm)
+        self.progression_32 = ConvBlock(c, c, 3, 1, pixel_norm=pixel_norm)
+        self.progression_64 = ConvBlock(c, c // 2, 3, 1, pixel_norm=pixel_norm)
+        self.progression_128 = ConvBlock(c // 2, c // 4, 3, 1, pixel_norm=pixel_norm)
+        self.to_rgb_4 = EqualConv2d(c, 3, 1)
+        self.to_rgb_8 = EqualConv2d(c, 3, 1)
+        self.to_rgb_16 = EqualConv2d(c, 3, 1)
+        self.to_rgb_32 = EqualConv2d(c, 3, 1)
+        self.to_rgb_64 = EqualConv2d(c // 2, 3, 1)
+        self.to_rgb_128 = EqualConv2d(c // 4, 3, 1)
+        self.max_step = max_step
+
+    def forward(self, input, label, step=0, alpha=-1):
+        if step > self.max_step:
+            step = self.max_step
+        dt = _act_dtype(self.precision)
+        fading = torch.is_tensor(alpha) or (0 <= alpha < 1)
+        data_in = torch.cat([input, self.embedding(label).to(input.dtype)], 1)        # (:664-668)
+        z = data_in.reshape(-1, 1, 1, self.input_dim + self.embedding_dim).to(dt).contiguous()
+        out_4 = _fused_layer(z, self.progression_4[0], 0.2, True)
+        out_4 = _fused_layer(out_4, self.progression_4[3], 0.2, True)
+        if step == 1:
+            out = _to_rgb(out_4, self.to_rgb_4, dt)
+            return F_.Tanh.apply(out) if self.tanh else out
+        feats = [out_4]
+        blocks = [self.progression_8, self.progression_16, self.progression_32, self.progression_64,
+                  self.progression_128]
+        heads = [self.to_rgb_4, self.to_rgb_8, self.to_rgb_16, self.to_rgb_32, self.to_rgb_64,
+                 self.to_rgb_128]
+        for s_ in range(2, 7):
+            feats.append(blocks[s_ - 2](F_.upsample2(feats[-1])))
+            if step == s_:
+                if s_ == 2 and self.tanh:        # same quirk as CorrectGenerator (:674-676)
+                    return F_.Tanh.apply(_to_rgb(feats[-1], self.to_rgb_8, dt))
+                return self._output(feats[-2], feats[-1], heads[s_ - 2], heads[s_ - 1], alpha, fading, dt)
+        return None
+
+
+class ConditionalCorrectDiscriminatorWgangp(nn.Module, _AlphaMixin):
+    """Class-conditional critic (progan_modules.py:697-775): a per-resolution label embedding of
+    R*R values is appended to the image as a 4th channel in front of from_rgb (and of the fade-in
+    skip from_rgb); six blocks, step 1 = 4 px ... 6 = 128 px."""
+
+    def __init__(self, feat_dim=128, num_of_classes=10, do_equal_embed=False, precision=None):
+        super().__init__()
+        self.feat_dim = feat_dim
+        self.num_of_classes = num_of_classes
+        self.do_equal_embed = do_equal_embed
+        self.precision = precision or _DEFAULT_PRECISION
+        f = feat_dim
+        self.progression = nn.ModuleList([ConvBlock(f // 4, f // 2, 3, 1), ConvBlock(f // 2, f, 3, 1),
+                                          ConvBlock(f, f, 3, 1), ConvBlock(f, f, 3, 1), ConvBlock(f, f, 3, 1),
+                                          ConvBlock(f + 1, f, 3, 1, 4, 0)])
+        sizes = [128 ** 2, 64 ** 2, 32 ** 2, 16 ** 2, 8 ** 2, 4 ** 2]
+        if do_equal_embed:
+            self.embeddings = nn.ModuleList([EqualEmbed(num_of_classes, d) for d in sizes])
+        else:
+            self.embeddings = nn.ModuleList([nn.Embedding(num_of_classes, d) for d in sizes])
+        self.from_rgb = nn.ModuleList([EqualConv2d(3 + 1, c_, 1) for c_ in (f // 4, f // 2, f, f, f, f)])
+        self.n_layer = len(self.progression)
+        self.linear = EqualLinear(f, 1)
+
+    def _with_label_plane(self, img, label, index):
+        plane = self.embeddings[index](label).to(img.dtype).view(-1, 1, img.shape[-2], img.shape[-1])
+        return torch.cat([img, plane], 1).contiguous()                                # (:747-749)
+
+    def forward(self, input, label, step=0, alpha=-1, mbstd_group=None):
+        if step < 1:
+            raise RuntimeError("ConditionalCorrectDiscriminatorWgangp: step must be >= 1")
+        dt = _act_dtype(self.precision)
+        fading = torch.is_tensor(alpha) or (0 <= alpha < 1)
+        x = input.contiguous()
+        if x.dtype != _img_dtype(self.precision):
+            x = x.to(_img_dtype(self.precision))
+        out = None
+        for i in range(step, 0, -1):
+            index = self.n_layer - i
+            if i == step:
+                out = _from_rgb(self._with_label_plane(x, label, index), self.from_rgb[index], dt)
+            if i == 1:
+                out = F_.Mbstd.apply(out, F_.K().mbstd_channels(out.shape[-1], out.dtype), mbstd_group)
+            out = self.progression[index](out, pool=(i > 1))
+            if i > 1 and i == step and fading:
+                skip_img = self._with_label_plane(F_.avgpool2(x, "nchw"), label, index + 1)   # (:766-768)
+                skip = _from_rgb(skip_img, self.from_rgb[index + 1], dt)
+                out = F_.Blend.apply(skip, out, self._alpha(alpha, out.device))
+        lin = self.linear.linear
+        C = out.shape[-1]
+        d = F_.PwFwd.apply(out, lin.weight_orig, lin.bias, "reduce", C, 1, 1, C, self.linear.scale, dt)
+        return d.view(-1, 1)

@@ -43,8 +43,38 @@ MNIST_CASES = {
 }
 
 
+# class-conditional Correct* models (progan_modules.py:601-775; BASELINE configs 3 and 5):
+# name: (channel, z_dim, step, alpha, batch, tanh, pixel_norm, num_classes, do_equal_embed)
+COND_CASES = {
+    "k1_a1.0": (32, 16, 1, 1.0, 4, False, True, 10, False),
+    "k2_a0.5_eq": (32, 16, 2, 0.5, 4, False, True, 10, True),
+    "k3_a0.25": (32, 16, 3, 0.25, 4, True, True, 14, False),
+    "k4_a1.0_eq": (32, 32, 4, 1.0, 2, False, True, 10, True),
+    "k5_a0.5": (32, 16, 5, 0.5, 2, False, True, 10, False),
+}
+
+
 def family(name):
-    return "correct" if name in CORRECT_CASES else ("mnist" if name in MNIST_CASES else "base")
+    if name in CORRECT_CASES:
+        return "correct"
+    if name in MNIST_CASES:
+        return "mnist"
+    return "cond" if name in COND_CASES else "base"
+
+
+def build(mod, name, inp, **extra):
+    """(G, D) instances of the case's model family from `mod` (reference module or mirror)."""
+    GC, DC = classes(mod, name)
+    if family(name) == "cond":
+        G = GC(input_code_dim=inp["z_dim"], num_of_classes=inp["num_classes"], in_channel=inp["channel"],
+               pixel_norm=inp["pixel_norm"], tanh=inp["tanh"], max_step=6,
+               do_equal_embed=inp["equal_embed"], **extra)
+        D = DC(feat_dim=inp["channel"], num_of_classes=inp["num_classes"],
+               do_equal_embed=inp["equal_embed"], **extra)
+        return G, D
+    G = GC(input_code_dim=inp["z_dim"], in_channel=inp["channel"], pixel_norm=inp["pixel_norm"],
+           tanh=inp["tanh"], **extra)
+    return G, DC(feat_dim=inp["channel"], **extra)
 
 
 def classes(mod, name):
@@ -53,6 +83,8 @@ def classes(mod, name):
     fam = family(name)
     if fam == "correct":
         return mod.CorrectGenerator, mod.CorrectDiscriminator
+    if fam == "cond":
+        return mod.ConditionalCorrectGenerator, mod.ConditionalCorrectDiscriminatorWgangp
     if fam == "mnist":
         if hasattr(mod, "mnist_pggan"):
             return mod.mnist_pggan.Generator, mod.mnist_pggan.Discriminator
@@ -61,12 +93,16 @@ def classes(mod, name):
     return mod.Generator, mod.Discriminator
 
 
-def model_shapes(channel, z_dim, pixel_norm, fam="base"):
+def model_shapes(channel, z_dim, pixel_norm, fam="base", ncls=10, eq=False):
     """state-dict key -> shape, taken from the host mirror (identical to the reference's;
     make_golden.py asserts that)."""
     import progan_b200
-    if fam in ("correct", "mnist"):
-        if fam == "correct":
+    if fam in ("correct", "mnist", "cond"):
+        if fam == "cond":
+            G = progan_b200.ConditionalCorrectGenerator(z_dim, ncls, channel, pixel_norm=pixel_norm,
+                                                        max_step=6, do_equal_embed=eq)
+            D = progan_b200.ConditionalCorrectDiscriminatorWgangp(channel, ncls, do_equal_embed=eq)
+        elif fam == "correct":
             G = progan_b200.CorrectGenerator(input_code_dim=z_dim, in_channel=channel, pixel_norm=pixel_norm)
             D = progan_b200.CorrectDiscriminator(feat_dim=channel)
         else:
@@ -91,16 +127,20 @@ def make_state(shapes, seed):
 
 
 def make_inputs(name):
-    ch, zd, step, alpha, B, tanh, pn = (CASES.get(name) or CORRECT_CASES.get(name) or MNIST_CASES[name])
-    gs, ds = model_shapes(ch, zd, pn, family(name))
+    spec = CASES.get(name) or CORRECT_CASES.get(name) or MNIST_CASES.get(name) or COND_CASES[name]
+    ch, zd, step, alpha, B, tanh, pn = spec[:7]
+    ncls, eq = (spec[7], spec[8]) if len(spec) > 7 else (0, False)
+    gs, ds = model_shapes(ch, zd, pn, family(name), ncls, eq)
     G_state, D_state = make_state(gs, 100), make_state(ds, 200)
     g = torch.Generator().manual_seed(1234)
-    R = 2 * 2 ** step if family(name) == "correct" else 4 * 2 ** step
+    R = 2 * 2 ** step if family(name) in ("correct", "cond") else 4 * 2 ** step
     real = torch.rand(B, 1 if family(name) == "mnist" else 3, R, R, generator=g) * 2 - 1
     z = torch.randn(B, zd, generator=g)
     eps = torch.rand(B, 1, 1, 1, generator=g)
+    label = torch.randint(0, ncls, (B,), generator=g) if ncls else None     # drawn last: older fixtures unchanged
     return dict(G=G_state, D=D_state, real=real, z=z, eps=eps, step=step, alpha=alpha,
-                tanh=tanh, pixel_norm=pn, channel=ch, z_dim=zd)
+                tanh=tanh, pixel_norm=pn, channel=ch, z_dim=zd, label=label, num_classes=ncls,
+                equal_embed=eq)
 
 
 def summarize(t, key):

@@ -25,12 +25,10 @@ def run_case(name):
 
     inp = common.make_inputs(name)
     step, alpha = inp["step"], inp["alpha"]
-    GC, DC = common.classes(R, name)
-    G = GC(input_code_dim=inp["z_dim"], in_channel=inp["channel"],
-           pixel_norm=inp["pixel_norm"], tanh=inp["tanh"])
-    D = DC(feat_dim=inp["channel"])
-    Grun = GC(input_code_dim=inp["z_dim"], in_channel=inp["channel"],
-              pixel_norm=inp["pixel_norm"], tanh=inp["tanh"])
+    G, D = common.build(R, name, inp)
+    Grun, _ = common.build(R, name, inp)
+    lab = inp["label"]
+    la = (lab,) if lab is not None else ()          # conditional models take the label second
     assert {k: tuple(v.shape) for k, v in G.state_dict().items()} == \
         {k: tuple(v.shape) for k, v in inp["G"].items()}
     assert {k: tuple(v.shape) for k, v in D.state_dict().items()} == \
@@ -46,16 +44,16 @@ def run_case(name):
     # --- train.py:98, 122-155
     D.zero_grad()
     b_size = real.size(0)
-    real_predict_raw = D(real, step=step, alpha=alpha)
+    real_predict_raw = D(real, *la, step=step, alpha=alpha)
     real_predict = real_predict_raw.mean() - 0.001 * (real_predict_raw ** 2).mean()
     real_predict.backward(mone)
-    fake_image = G(z, step=step, alpha=alpha)
-    fake_predict = D(fake_image.detach(), step=step, alpha=alpha)
+    fake_image = G(z, *la, step=step, alpha=alpha)
+    fake_predict = D(fake_image.detach(), *la, step=step, alpha=alpha)
     fake_predict = fake_predict.mean()
     fake_predict.backward(one)
     x_hat = eps * real.data + (1 - eps) * fake_image.detach().data
     x_hat.requires_grad = True
-    hat_predict = D(x_hat, step=step, alpha=alpha)
+    hat_predict = D(x_hat, *la, step=step, alpha=alpha)
     grad_x_hat = grad(outputs=hat_predict.sum(), inputs=x_hat, create_graph=True)[0]
     grad_penalty = ((grad_x_hat.view(grad_x_hat.size(0), -1).norm(2, dim=1) - 1) ** 2).mean()
     grad_penalty = 10 * grad_penalty
@@ -73,7 +71,7 @@ def run_case(name):
     out["d_params_after"] = common.summarize_dict(dict(D.named_parameters()))
     # --- train.py:158-169
     G.zero_grad(); D.zero_grad()
-    predict = D(fake_image, step=step, alpha=alpha)
+    predict = D(fake_image, *la, step=step, alpha=alpha)
     loss = -predict.mean()
     loss.backward()
     out["gen_loss"] = loss.detach().clone()
@@ -93,7 +91,7 @@ def run_case(name):
 if __name__ == "__main__":
     torch.set_num_threads(8)
     only = sys.argv[1:]
-    for name in list(common.CASES) + list(common.CORRECT_CASES) + list(common.MNIST_CASES):
+    for name in list(common.CASES) + list(common.CORRECT_CASES) + list(common.MNIST_CASES) + list(common.COND_CASES):
         if only and name not in only and common.family(name) not in only:
             continue
         res = run_case(name)

@@ -1,5 +1,6 @@
 """The Correct* rewiring (progan_modules.py:479-598: cifar_train.py / proper_cifar_train.py
-models) and the mnist_pggan.py models (BASELINE config 0) through the product modules, pinned to golden vectors recorded from the REAL
+models), the mnist_pggan.py models (BASELINE config 0) and the class-conditional Correct* models
+(:601-775, BASELINE configs 3 and 5) through the product modules, pinned to golden vectors recorded from the REAL
 reference classes: forward outputs, gradient penalty, every parameter gradient and the
 parameters after torch.optim.Adam(betas=(0, .99)) steps, EMA included.
 
@@ -24,9 +25,11 @@ def _run_case(name, precision, device):
     g_opt = optim.Adam(G.parameters(), lr=0.001, betas=(0.0, 0.99))
     d_opt = optim.Adam(D.parameters(), lr=0.001, betas=(0.0, 0.99))
     real, z, eps = inp["real"].to(device), inp["z"].to(device), inp["eps"].to(device)
-    res, fake = helpers.product_train_step(G, D, real, z, eps, inp["step"], inp["alpha"], fused_gp=False)
+    label = inp["label"].to(device) if inp["label"] is not None else None
+    res, fake = helpers.product_train_step(G, D, real, z, eps, inp["step"], inp["alpha"], fused_gp=False,
+                                           label=label)
     d_opt.step()
-    loss, g_grads = helpers.product_g_phase(G, D, fake, inp["step"], inp["alpha"])
+    loss, g_grads = helpers.product_g_phase(G, D, fake, inp["step"], inp["alpha"], label=label)
     g_opt.step()
     with torch.no_grad():
         for (k, pr), (_, pg) in zip(Grun.named_parameters(), G.named_parameters()):
@@ -54,7 +57,7 @@ def _check(name, res, loss, g_grads, G, D, Grun, tol):
             assert float((common.summarize(p, k) - s).norm()) <= tol * float(s.norm()) + 1e-7, (tag, k)
 
 
-@pytest.mark.parametrize("name", list(common.CORRECT_CASES) + list(common.MNIST_CASES))
+@pytest.mark.parametrize("name", list(common.CORRECT_CASES) + list(common.MNIST_CASES) + list(common.COND_CASES))
 def test_correct_variants_match_reference_golden_cpu(name):
     prev = progan_b200.set_kernels(EmulKernels())
     try:
@@ -79,7 +82,7 @@ def test_correct_state_dict_layout():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", list(common.CORRECT_CASES) + list(common.MNIST_CASES))
+@pytest.mark.parametrize("name", list(common.CORRECT_CASES) + list(common.MNIST_CASES) + list(common.COND_CASES))
 def test_correct_variants_cuda_check_mode_and_bf16(name):
     K = progan_b200.get_kernels()
     K.conv_impl, K.wgrad_tc = "simt", False
