@@ -94,7 +94,9 @@ def test_correct_variants_cuda_check_mode_and_bf16(name):
     K.invalidate_packs()
     inp, res16, loss16, _, _, _, _ = _run_case(name, "bf16", "cuda")
     assert helpers.rel(res16["fake"], res["fake"]) < 1e-2
-    assert helpers.rel(res16["real_predict"], res["real_predict"]) < 2e-2
+    # D outputs are O(0.1) scalars per sample (batch 2-4): absolute + relative bound
+    dp = (res16["real_predict"] - res["real_predict"]).abs().max()
+    assert float(dp) <= 2e-2 * float(res["real_predict"].abs().max()) + 2e-2
     assert helpers.rel(res16["grad_x_hat"], res["grad_x_hat"]) < 0.3         # bf16 LeakyReLU mask flips: 3-20 %
     # (||g|| - 1)^2 amplifies the relative error of ||g|| near 1: absolute + relative bound
     assert abs(float(res16["grad_penalty"]) - float(res["grad_penalty"])) <= 0.2 * float(res["grad_penalty"]) + 0.1
