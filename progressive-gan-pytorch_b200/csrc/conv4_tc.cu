@@ -202,39 +202,61 @@ conv4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       mbar_wait(wres_bar, 0);
       tc_fence_after();
     }
-    int as = 0, ws = 0, acc = 0;
-    uint32_t aph = 0, wph = 0, acc_phase = 0;
-    for (int sb = cid * CL; sb < p.num_super; sb += ncl * CL) {
-      mbar_wait(tempty(acc), acc_phase ^ 1u);
-      tc_fence_after();
-      const uint32_t d_base = tmem_base + (uint32_t)(acc * acc_stride);
-#pragma unroll
-      for (int cb = 0; cb < NCB; ++cb) {
+    // The tensor pipe queues only ~2 MMAs (measured: every ~100 cycles the issuing thread spends
+    // in a barrier wait between two MMAs shows up as a bubble), so the loop is software-pipelined:
+    // ONE thread is elected for the whole kernel, and the barrier waits that the NEXT tap /
+    // channel block / tile needs are performed just before the LAST TWO MMAs of the current tap,
+    // i.e. while two instructions are still in flight.
+    if (elect_one_sync()) {
+      int as = 0, ws = 0, acc = 0;
+      uint32_t aph = 0, wph = 0, acc_phase = 0;
+      const int stride = ncl * CL;
+      int sb = cid * CL;
+      if (sb < p.num_super) {               // prologue: what the very first MMA needs
+        mbar_wait(tempty(acc), acc_phase ^ 1u);
         mbar_wait(afull(as), aph);
+        if (!RES) mbar_wait(wfull(ws), wph);
         tc_fence_after();
-        const uint32_t a16 = ((smem_a + (uint32_t)(as * MT) * kBoxPad) >> 4) | lbo_lo;
-        const uint32_t w16 = (smem_w >> 4) | lbo_lo;
-        if (elect_one_sync()) {
-          int wsl = ws;
-          uint32_t wphl = wph;
+      }
+      for (; sb < p.num_super; sb += stride) {
+        const bool has_next_tile = sb + stride < p.num_super;
+        const uint32_t d_base = tmem_base + (uint32_t)(acc * acc_stride);
+#pragma unroll
+        for (int cb = 0; cb < NCB; ++cb) {
+          const uint32_t a16 = ((smem_a + (uint32_t)(as * MT) * kBoxPad) >> 4) | lbo_lo;
+          const uint32_t w16 = (smem_w >> 4) | lbo_lo;
+          const int as_next = (as + 1 == p.a_stages) ? 0 : as + 1;
+          const uint32_t aph_next = (as + 1 == p.a_stages) ? (aph ^ 1u) : aph;
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
             const int dh = tap / 3, dw = tap % 3;
-            uint32_t b16;
-            if (RES) {
-              b16 = w16 + (uint32_t)(tap * NCB + cb) * wtile16;
-            } else {
-              mbar_wait(wfull(wsl), wphl);
-              tc_fence_after();
-              b16 = w16 + (uint32_t)wsl * wtile16;
-            }
-            constexpr uint32_t dummy = 0; (void)dummy;
+            const uint32_t b16 = RES ? w16 + (uint32_t)(tap * NCB + cb) * wtile16
+                                     : w16 + (uint32_t)ws * wtile16;
             const uint32_t a_off16 = ((uint32_t)(dh * 10 + dw) * row_bytes) >> 4;
-            if (!(p.dbg & 16))          // experiment: no MMAs
+            constexpr int NM = MT * nk;                  // MMAs of one tap
+            constexpr int SPLIT = NM > 2 ? NM - 2 : 0;   // the waits go in front of the last two
+            const int ws_next = (ws + 1 == p.w_stages) ? 0 : ws + 1;
+            const uint32_t wph_next = (ws + 1 == p.w_stages) ? (wph ^ 1u) : wph;
+            // barriers the next tap / block / tile needs: polled ONCE in front of the last two
+            // MMAs (hidden behind the in-flight ones when they are already complete, the common
+            // case when MMA-bound), waited for after this tap's commits otherwise — a blocking
+            // wait in front of the last MMAs would delay this tile's own completion
+            const bool last_of_tile = (tap == 8) && (cb == NCB - 1);
+            const bool need_w = !RES && !(last_of_tile && !has_next_tile);
+            const bool need_a = (tap == 8) && (cb < NCB - 1 || has_next_tile);
+            const bool need_t = last_of_tile && has_next_tile;
+            const uint32_t t_par = acc ? (acc_phase ^ 1u) ^ 1u : acc_phase ^ 1u;
+            bool ok_w = !need_w, ok_a = !need_a, ok_t = !need_t;
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-#pragma unroll
-              for (int k = 0; k < nk; ++k) {
+            for (int j = 0; j < NM; ++j) {
+              if (j == SPLIT && (!RES || tap == 8)) {
+                if (need_w) ok_w = mbar_try_wait(wfull(ws_next), wph_next);
+                if (need_a) ok_a = mbar_try_wait(afull(as_next), aph_next);
+                if (need_t) ok_t = mbar_try_wait(tempty(acc ^ 1), t_par);
+                tc_fence_after();
+              }
+              const int mt = j / nk, k = j % nk;
+              if (!(p.dbg & 16)) {       // experiment: no MMAs
                 const uint64_t ad = ((uint64_t)hi_a << 32) |
                                     (uint64_t)(a16 + (uint32_t)mt * box16 + a_off16 + (uint32_t)(k * 2));
                 const uint64_t bd = ((uint64_t)hi_b << 32) | (uint64_t)(b16 + (uint32_t)(k * 2));
@@ -242,23 +264,29 @@ conv4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
               }
             }
             if (!RES) {
-              if (CL == 1) umma_commit(wempty(wsl));
-              else umma_commit_mc(wempty(wsl), cmask);
-              if (++wsl == p.w_stages) { wsl = 0; wphl ^= 1u; }
+              if (CL == 1) umma_commit(wempty(ws));
+              else umma_commit_mc(wempty(ws), cmask);
+              ws = ws_next;
+              wph = wph_next;
+            }
+            if (tap == 8) {
+              umma_commit(aempty(as));
+              if (cb == NCB - 1) umma_commit(tfull(acc));
+            }
+            if (!(ok_w && ok_a && ok_t)) {
+              if (!ok_w) mbar_wait(wfull(ws), wph);            // ws / wph already advanced
+              if (!ok_a) mbar_wait(afull(as_next), aph_next);
+              if (!ok_t) mbar_wait(tempty(acc ^ 1), t_par);
+              tc_fence_after();
             }
           }
-          umma_commit(aempty(as));
-          if (cb == NCB - 1) umma_commit(tfull(acc));
+          as = as_next;
+          aph = aph_next;
         }
-        __syncwarp();
-        if (!RES) {                       // every lane tracks the ring position (9 slots per block)
-          ws += 9;
-          while (ws >= p.w_stages) { ws -= p.w_stages; wph ^= 1u; }
-        }
-        if (++as == p.a_stages) { as = 0; aph ^= 1u; }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
+    __syncwarp();
   } else if (warp >= 4) {
     // ===================== epilogue (8 warps) =====================
     // Two warps per TMEM lane quadrant, each owning half of the channel columns of its 32
