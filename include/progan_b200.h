@@ -205,6 +205,14 @@ int pg_mbstd_bwd_bwd(const void *t, const void *dout, const void *x, float *stat
                      void *cot_dout, void *cot_x, int N, int C, int Cp, int dtype,
                      void *stream);
 
+/* ---- losses: train.py:126-139 (critic, with the 0.001 drift term) / :162-167 (generator) ----
+ * d: critic outputs, the n_real real samples first, then n_fake fake ones (fp32).
+ *   n_real > 0:  L = -(mean d_r - drift*mean d_r^2) + mean d_f;  metric[0] += mean d_r - drift*mean d_r^2 - mean d_f
+ *   n_real = 0:  L = -mean d;                                     metric[0] += L
+ * seed[n] = dL/dd[n] (what the reference passes implicitly through .backward(one/mone)). */
+int pg_wgan_loss(const float *d, float *seed, float *metric, int n_real, int n_fake, float drift,
+                 void *stream);
+
 /* ---- WGAN-GP pieces: train.py:142-150 ---------------------------------------*/
 /* x_hat = eps[n]*real + (1-eps[n])*fake  (all fp32 [N,D])                    */
 int pg_interp_xhat(const float *real, const float *fake, const float *eps, float *out,

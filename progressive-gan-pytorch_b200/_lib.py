@@ -49,6 +49,7 @@ SIGNATURES = {
     "pg_mbstd_fwd": [P, P, P, c_int, c_int, c_int, c_int, P],
     "pg_mbstd_bwd": [P, P, P, P, c_int, c_int, c_int, c_int, P],
     "pg_mbstd_bwd_bwd": [P, P, P, P, P, P, c_int, c_int, c_int, c_int, P],
+    "pg_wgan_loss": [P, P, P, c_int, c_int, c_float, P],
     "pg_interp_xhat": [P, P, P, P, c_int, c_ll, P],
     "pg_gp_fwd": [P, P, P, c_int, c_ll, c_float, P],
     "pg_gp_bwd": [P, P, P, P, c_int, c_ll, c_float, P],

@@ -45,6 +45,37 @@ gp_norm_kernel(const float *__restrict__ g, float *__restrict__ norms, long long
   if (threadIdx.x == 0) norms[blockIdx.x] = sqrtf(s);
 }
 
+// Critic / generator losses of the loop body and their gradient seeds in one small launch
+// (train.py:126-139,162-167): d = D outputs [n_real + n_fake] (real half first),
+//   L = -(mean d_r - drift * mean d_r^2) + mean d_f      seed_n = dL/dd_n
+//   metric[0] += mean d_r - drift * mean d_r^2 - mean d_f   (what the reference logs as disc loss)
+// n_real = 0: generator form  L = -mean d,  metric[0] += L.
+__global__ void __launch_bounds__(256)
+wgan_loss_kernel(const float *__restrict__ d, float *__restrict__ seed, float *__restrict__ metric,
+                 int n_real, int n_fake, float drift) {
+  __shared__ float red[32];
+  float sr = 0.f, sr2 = 0.f, sf = 0.f;
+  const float ir = n_real > 0 ? 1.f / (float)n_real : 0.f, ifk = 1.f / (float)n_fake;
+  for (int n = threadIdx.x; n < n_real + n_fake; n += blockDim.x) {
+    const float v = d[n];
+    if (n < n_real) {
+      sr += v;
+      sr2 += v * v;
+      seed[n] = (-1.f + 2.f * drift * v) * ir;
+    } else {
+      sf += v;
+      seed[n] = n_real > 0 ? ifk : -ifk;
+    }
+  }
+  sr = block_sum(sr, red);
+  sr2 = block_sum(sr2, red);
+  sf = block_sum(sf, red);
+  if (threadIdx.x == 0 && metric != nullptr) {
+    if (n_real > 0) *metric += sr * ir - drift * sr2 * ir - sf * ifk;
+    else *metric += -sf * ifk;
+  }
+}
+
 __global__ void gp_loss_kernel(const float *__restrict__ norms, float *__restrict__ gp, int N,
                                float lambda) {
   __shared__ float red[32];
@@ -198,4 +229,11 @@ extern "C" int pg_adam_multi(float *p, const float *g, float *m, float *v, const
   pg::adam_multi_kernel<<<nchunks, 256, 0, (cudaStream_t)stream>>>(
       p, g, m, v, (const int4 *)chunks, steps_dev, lr, beta1, beta2, eps, grad_scale);
   PG_CHECK_LAUNCH("pg_adam_multi");
+}
+
+extern "C" int pg_wgan_loss(const float *d, float *seed, float *metric, int n_real, int n_fake,
+                            float drift, void *stream) {
+  PG_CHECK_ARG(d && seed && n_real >= 0 && n_fake > 0, "pg_wgan_loss: bad arguments");
+  pg::wgan_loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(d, seed, metric, n_real, n_fake, drift);
+  PG_CHECK_LAUNCH("pg_wgan_loss");
 }

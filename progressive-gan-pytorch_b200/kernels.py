@@ -607,6 +607,19 @@ class CudaKernels:
         return cot_dout, cot_x
 
     # ------------------------------------------------------------- WGAN-GP
+    def wgan_loss(self, d, n_real, drift, metric=None):
+        """Gradient seed of the critic loss (n_real > 0: real outputs first, train.py:126-139) or
+        of the generator loss (n_real = 0, :162-167) w.r.t. the critic outputs d; the logged loss
+        value is added to the device scalar `metric`."""
+        _chk(d, "d", torch.float32)
+        n = d.numel()
+        seed = torch.empty_like(d)
+        if metric is not None:
+            _chk(metric, "metric", torch.float32)
+        self._call("pg_wgan_loss", d.data_ptr(), seed.data_ptr(), _ptr(metric), int(n_real), n - int(n_real),
+                   float(drift), self._stream())
+        return seed
+
     def interp_xhat(self, real, fake, eps):
         _chk(real, "real", torch.float32)
         _chk(fake, "fake", torch.float32)

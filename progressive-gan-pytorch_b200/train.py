@@ -207,6 +207,7 @@ class Trainer:
         self._side = torch.cuda.Stream() if (overlap_wgrad and dev.type == "cuda") else None
         self._gp_stream = torch.cuda.Stream() if (overlap_passes and dev.type == "cuda") else None
         self._copy_stream = None
+        self._ones = {}
         self._g_params = list(generator.parameters())
         self._r_params = list(g_running.parameters()) if g_running is not None else []
 
@@ -287,32 +288,32 @@ class Trainer:
         with (torch.cuda.stream(s2) if s2 is not None else _NullCtx()):
             x_hat = K.interp_xhat(real, fake.detach(), st["eps"].reshape(-1)).requires_grad_(True)
             hat = D(x_hat, step=step, alpha=alpha)
-            (g,) = torch.autograd.grad(outputs=hat.sum(), inputs=x_hat, create_graph=True)
+            # d(sum_n hat_n)/dx_hat (train.py:146) with an explicit unit seed: no sum kernel and no
+            # expand in its backward
+            ones = self._ones.get(tuple(hat.shape))
+            if ones is None:
+                ones = self._ones[tuple(hat.shape)] = torch.ones_like(hat)
+            (g,) = torch.autograd.grad(outputs=hat, inputs=x_hat, grad_outputs=ones, create_graph=True)
             gp = F_.gradient_penalty(g, self.gp_lambda)
             gp.backward()
         both = D(torch.cat([real, fake.detach()]), step=step, alpha=alpha, mbstd_group=B)
-        real_raw, fake_raw = both[:B], both[B:]
-        real_predict = real_raw.mean() - self.drift * (real_raw ** 2).mean()
-        fake_predict = fake_raw.mean()
-        (fake_predict - real_predict).backward()
+        # loss value (-> metric) and dL/d(outputs) in one launch, then backward from that seed
+        both.backward(K.wgan_loss(both.detach(), B, self.drift, self.metrics["disc_loss"]))
         if s2 is not None:
             cur.wait_stream(s2)
         K.flush_wgrads()
         st["fake"] = fake
         st["gp"] = gp.detach()
-        st["d_loss"] = (real_predict - fake_predict).detach()
 
     def _seg_g(self, st):
         K = get_kernels()
         self._adam(self.bD, st["planD"])
         self.metrics["grad_penalty"].add_(st["gp"])
-        self.metrics["disc_loss"].add_(st["d_loss"])
         # ---- G phase (D already updated, train.py:158-169)
         self.bG.g.zero_()
-        loss = -self.D(st["fake"], step=st["step"], alpha=st["alpha"]).mean()
-        loss.backward(inputs=st["planG"]["params"])
+        out = self.D(st["fake"], step=st["step"], alpha=st["alpha"])
+        out.backward(K.wgan_loss(out.detach(), 0, 0.0, self.metrics["gen_loss"]), inputs=st["planG"]["params"])
         K.flush_wgrads()
-        st["g_loss"] = loss.detach()
 
     def _seg_end(self, st):
         K = get_kernels()
@@ -320,7 +321,6 @@ class Trainer:
         if self.bR is not None:
             K.ema(self.bR.p, self.bG.p, self.ema_decay)
             K.drop_packs(self._r_params)
-        self.metrics["gen_loss"].add_(st["g_loss"])
 
     # ------------------------------------------------------------------ public
     def _stage_host_inputs(self, real, z, eps):

@@ -301,6 +301,23 @@ class EmulKernels:
         return cot_dout.to(dout.dtype), cot_x.contiguous().to(x.dtype)
 
     # ---- WGAN-GP
+    def wgan_loss(self, d, n_real, drift, metric=None):
+        self.launches += 1
+        flat = d.reshape(-1)
+        n = flat.numel()
+        seed = torch.empty_like(flat)
+        if n_real > 0:
+            dr, df = flat[:n_real], flat[n_real:]
+            seed[:n_real] = (-1.0 + 2.0 * drift * dr) / n_real
+            seed[n_real:] = 1.0 / (n - n_real)
+            val = dr.mean() - drift * (dr * dr).mean() - df.mean()
+        else:
+            seed[:] = -1.0 / n
+            val = -flat.mean()
+        if metric is not None:
+            metric.add_(val.to(metric.dtype))
+        return seed.view_as(d)
+
     def interp_xhat(self, real, fake, eps):
         self.launches += 1
         e = eps.view(-1, *([1] * (real.dim() - 1)))

@@ -371,3 +371,23 @@ def test_conv_fused_avgpool_matches_separate_kernel(KE, cfg, epi):
     assert torch.equal(y, y2)
     assert torch.equal(yp, K.avgpool2(y2))
     K.conv_impl = "simt"
+
+
+@pytest.mark.parametrize("n_real,n_fake", [(64, 64), (5, 3), (0, 64), (0, 7)])
+def test_wgan_loss_seed_matches_autograd(KE, n_real, n_fake):
+    """pg_wgan_loss: loss value and dL/d(outputs) of train.py:126-139 / 162-167 vs torch autograd."""
+    K, E = KE
+    d = rnd(n_real + n_fake, 1, seed=5).requires_grad_(True)
+    if n_real:
+        dr, df = d[:n_real], d[n_real:]
+        real_predict = dr.mean() - 0.001 * (dr ** 2).mean()
+        loss, logged = -real_predict + df.mean(), real_predict - df.mean()
+    else:
+        loss = -d.mean()
+        logged = loss
+    (g,) = torch.autograd.grad(loss, d)
+    metric = torch.full((), 0.25, device=DEV)
+    seed = K.wgan_loss(d.detach(), n_real, 0.001, metric)
+    torch.cuda.synchronize()
+    assert helpers.rel(seed, g) < 1e-6
+    assert abs(float(metric) - 0.25 - float(logged)) < 1e-5
