@@ -31,6 +31,18 @@ pw_expand_kernel(const float *__restrict__ img, const float *__restrict__ w,
   const I total = (I)N * HW * nch;
   constexpr int UN = 4;                       // independent elements per thread: bytes in flight
   const I stride = (I)gridDim.x * (I)blockDim.x;
+  // blockDim (256) is a multiple of nch (C/8 <= 256, power of two in this network), so a thread
+  // always works on the same 8-channel group: its weights and bias live in registers and the
+  // loop body has no shared-memory reads at all
+  const bool fixed_group = (256 % (int)nch) == 0;
+  const int cj_fixed = (int)(((I)blockIdx.x * (I)blockDim.x + (I)threadIdx.x) % nch);
+  float wr[kMaxK][8], br[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    br[e] = sb[cj_fixed * 8 + e];
+#pragma unroll
+    for (int k = 0; k < kMaxK; ++k) wr[k][e] = (k < K) ? sw[k * C + cj_fixed * 8 + e] : 0.f;
+  }
   for (I i0 = (I)blockIdx.x * (I)blockDim.x + (I)threadIdx.x; i0 < total; i0 += stride * UN) {
     float xin[UN][kMaxK];
     I pixs[UN];
@@ -50,14 +62,24 @@ pw_expand_kernel(const float *__restrict__ img, const float *__restrict__ w,
     for (int u = 0; u < UN; ++u) {
       if (i0 + (I)u * stride >= total) break;
       F8 o;
+      if (fixed_group) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int c = cjs[u] * 8 + e;
-        float v = sb[c];
+        for (int e = 0; e < 8; ++e) {
+          float v = br[e];
 #pragma unroll
-        for (int k = 0; k < kMaxK; ++k)
-          if (k < K) v = fmaf(xin[u][k], sw[k * C + c], v);
-        o.v[e] = v;
+          for (int k = 0; k < kMaxK; ++k) v = fmaf(xin[u][k], wr[k][e], v);
+          o.v[e] = v;
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int c = cjs[u] * 8 + e;
+          float v = sb[c];
+#pragma unroll
+          for (int k = 0; k < kMaxK; ++k)
+            if (k < K) v = fmaf(xin[u][k], sw[k * C + c], v);
+          o.v[e] = v;
+        }
       }
       st8(act + (long long)pixs[u] * C + (long long)cjs[u] * 8, o);
     }
@@ -82,6 +104,12 @@ pw_reduce_kernel(const T *__restrict__ act, const float *__restrict__ w,
   const I Pr = ((P + ppb - 1) / ppb) * ppb;
   constexpr int UN = 4;                       // pixels per sub-warp in flight
   const I pstride = (I)gridDim.x * ppb;
+  // one chunk per lane (C <= 8*TPP): the lane's weights stay in registers
+  float wr[kMaxK][8];
+#pragma unroll
+  for (int k = 0; k < kMaxK; ++k)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) wr[k][e] = (k < K && sub < nch) ? sw[k * C + sub * 8 + e] : 0.f;
   for (I pix0 = (I)blockIdx.x * ppb + (I)(threadIdx.x / TPP); pix0 < Pr; pix0 += pstride * UN) {
     float acc[UN][kMaxK];
     typename RawOf<T>::type raw[UN];
@@ -97,14 +125,24 @@ pw_reduce_kernel(const T *__restrict__ act, const float *__restrict__ w,
 #pragma unroll
       for (int k = 0; k < kMaxK; ++k) acc[u][k] = 0.f;
       if (pix < P) {
-        for (int ch = sub; ch < nch; ch += TPP) {
-          F8 v = one ? unpack8(raw[u]) : ld8(act + (long long)pix * C + (long long)ch * 8);
+        if (one) {
+          if (sub < nch) {
+            const F8 v = unpack8(raw[u]);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int c = ch * 8 + e;
+            for (int e = 0; e < 8; ++e)
 #pragma unroll
-            for (int k = 0; k < kMaxK; ++k)
-              if (k < K) acc[u][k] = fmaf(v.v[e], sw[k * C + c], acc[u][k]);
+              for (int k = 0; k < kMaxK; ++k) acc[u][k] = fmaf(v.v[e], wr[k][e], acc[u][k]);
+          }
+        } else {
+          for (int ch = sub; ch < nch; ch += TPP) {
+            F8 v = ld8(act + (long long)pix * C + (long long)ch * 8);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int c = ch * 8 + e;
+#pragma unroll
+              for (int k = 0; k < kMaxK; ++k)
+                if (k < K) acc[u][k] = fmaf(v.v[e], sw[k * C + c], acc[u][k]);
+            }
           }
         }
       }
