@@ -75,6 +75,24 @@ def _g_active(G, step, fading):
     return names
 
 
+def _generic_groups(model):
+    """(name, [params]) per top-level child (one per element of a ModuleList): the bucket layout
+    for the model families other than train.py's Generator/Discriminator (Correct*, mnist,
+    conditional).  Which groups are live for a (step, fading) is found by a probe pass."""
+    groups = []
+    for name, child in model.named_children():
+        if isinstance(child, torch.nn.ModuleList):
+            for i, sub in enumerate(child):
+                ps = list(sub.parameters())
+                if ps:
+                    groups.append(("%s.%d" % (name, i), ps))
+        else:
+            ps = list(child.parameters())
+            if ps:
+                groups.append((name, ps))
+    return groups
+
+
 class _NullCtx:
     def __enter__(self):
         return None
@@ -188,11 +206,18 @@ class Trainer:
         self.use_graph = use_graph
         # multi-GPU: three graphs per iteration with the NCCL all-reduces between the replays
         self.segment_graphs = (self.world > 1) if segment_graphs is None else bool(segment_graphs)
-        self.bD = FlatBucket(_d_groups(discriminator), betas[0])
-        self.bG = FlatBucket(_g_groups(generator), betas[0])
+        from .progan_modules import Discriminator as _BaseD, Generator as _BaseG
+        # train.py's own models get the hand-ordered buckets (live set = two contiguous ranges);
+        # every other mirrored family a generic layout + a probe pass for the live set
+        self._generic = not (type(generator) is _BaseG and type(discriminator) is _BaseD)
+        d_groups = _generic_groups if self._generic else _d_groups
+        g_groups = _generic_groups if self._generic else _g_groups
+        self._active_cache = {}
+        self.bD = FlatBucket(d_groups(discriminator), betas[0])
+        self.bG = FlatBucket(g_groups(generator), betas[0])
         self.bR = None
         if g_running is not None:
-            self.bR = FlatBucket(_g_groups(g_running), 0.0)
+            self.bR = FlatBucket(g_groups(g_running), 0.0)
             for p in g_running.parameters():
                 p.requires_grad_(False)
                 p.grad = None
@@ -249,11 +274,11 @@ class Trainer:
             K = get_kernels()
             F_.DIRECT_GRADS, K.defer_wgrad, K.wgrad_side_stream = self.prev
 
-    def _iteration(self, real, z, eps, step, alpha, fading):
+    def _iteration(self, real, z, eps, step, alpha, fading, label=None):
         """alpha: fp32 device scalar tensor when fading else the python number.  The iteration
         is three segments separated by the two gradient all-reduces (the segments are what a
         multi-GPU run captures as CUDA graphs; the collectives stay outside the graphs)."""
-        st = self._state(real, z, eps, step, alpha, fading)
+        st = self._state(real, z, eps, step, alpha, fading, label)
         with self._fast_paths(self._side):
             self._seg_d(st)
             self._allreduce(self.bD, st["planD"])
@@ -261,10 +286,37 @@ class Trainer:
             self._allreduce(self.bG, st["planG"])
             self._seg_end(st)
 
-    def _state(self, real, z, eps, step, alpha, fading):
-        return dict(real=real, z=z, eps=eps, step=step, alpha=alpha,
-                    planD=self.bD.plan(_d_active(self.D, step, fading)),
-                    planG=self.bG.plan(_g_active(self.G, step, fading)))
+    def _active(self, step, alpha, fading, label=None):
+        """(live D groups, live G groups) for this (step, fading)."""
+        if not self._generic:
+            return _d_active(self.D, step, fading), _g_active(self.G, step, fading)
+        key = (step, fading)
+        ent = self._active_cache.get(key)
+        if ent is None:
+            # probe: which parameters does d D(G(z)) / d theta reach?  (batch 2, zeros; plain
+            # autograd.grad with allow_unused — nothing is accumulated anywhere)
+            dev = self.bD.p.device
+            z = torch.zeros(2, self.G.input_dim, device=dev)
+            la = (label[:1].expand(2).contiguous(),) if label is not None else ()
+            prev = F_.DIRECT_GRADS
+            F_.DIRECT_GRADS = False
+            try:
+                with torch.enable_grad():
+                    out = self.D(self.G(z, *la, step=step, alpha=alpha), *la, step=step, alpha=alpha)
+                    ps = list(self.D.parameters()) + list(self.G.parameters())
+                    gs = torch.autograd.grad(out.sum(), ps, allow_unused=True)
+            finally:
+                F_.DIRECT_GRADS = prev
+            used = {id(p_) for p_, g_ in zip(ps, gs) if g_ is not None}
+            ent = tuple([n for n, grp in b.group_params.items() if any(id(p_) in used for p_ in grp)]
+                        for b in (self.bD, self.bG))
+            self._active_cache[key] = ent
+        return ent
+
+    def _state(self, real, z, eps, step, alpha, fading, label=None):
+        namesD, namesG = self._active(step, alpha, fading, label)
+        return dict(real=real, z=z, eps=eps, step=step, alpha=alpha, label=label,
+                    planD=self.bD.plan(namesD), planG=self.bG.plan(namesG))
 
     def _seg_d(self, st):
         # ---- D phase.  D(real) and D(fake) (train.py:126-139) run as ONE pass over
@@ -273,9 +325,11 @@ class Trainer:
         K = get_kernels()
         G, D = self.G, self.D
         real, step, alpha = st["real"], st["step"], st["alpha"]
+        la = (st["label"],) if st.get("label") is not None else ()      # conditional families
+        la2 = (torch.cat([st["label"], st["label"]]),) if la else ()
         self.bD.g.zero_()
         B = real.shape[0]
-        fake = G(st["z"], step=step, alpha=alpha)
+        fake = G(st["z"], *la, step=step, alpha=alpha)
         # The gradient-penalty pass (train.py:142-151) and the real/fake pass are independent
         # given `fake`: they run as two concurrent chains (streams; parallel branches of the
         # captured graph).  Every gradient kernel accumulates atomically (workspaces, bias sums),
@@ -287,7 +341,7 @@ class Trainer:
             s2.wait_stream(cur)
         with (torch.cuda.stream(s2) if s2 is not None else _NullCtx()):
             x_hat = K.interp_xhat(real, fake.detach(), st["eps"].reshape(-1)).requires_grad_(True)
-            hat = D(x_hat, step=step, alpha=alpha)
+            hat = D(x_hat, *la, step=step, alpha=alpha)
             # d(sum_n hat_n)/dx_hat (train.py:146) with an explicit unit seed: no sum kernel and no
             # expand in its backward
             ones = self._ones.get(tuple(hat.shape))
@@ -296,7 +350,7 @@ class Trainer:
             (g,) = torch.autograd.grad(outputs=hat, inputs=x_hat, grad_outputs=ones, create_graph=True)
             gp = F_.gradient_penalty(g, self.gp_lambda)
             gp.backward()
-        both = D(torch.cat([real, fake.detach()]), step=step, alpha=alpha, mbstd_group=B)
+        both = D(torch.cat([real, fake.detach()]), *la2, step=step, alpha=alpha, mbstd_group=B)
         # loss value (-> metric) and dL/d(outputs) in one launch, then backward from that seed
         both.backward(K.wgan_loss(both.detach(), B, self.drift, self.metrics["disc_loss"]))
         if s2 is not None:
@@ -311,7 +365,8 @@ class Trainer:
         self.metrics["grad_penalty"].add_(st["gp"])
         # ---- G phase (D already updated, train.py:158-169)
         self.bG.g.zero_()
-        out = self.D(st["fake"], step=st["step"], alpha=st["alpha"])
+        la = (st["label"],) if st.get("label") is not None else ()
+        out = self.D(st["fake"], *la, step=st["step"], alpha=st["alpha"])
         out.backward(K.wgan_loss(out.detach(), 0, 0.0, self.metrics["gen_loss"]), inputs=st["planG"]["params"])
         K.flush_wgrads()
 
@@ -351,36 +406,39 @@ class Trainer:
         self._stg_key = key
         return stg
 
-    def step(self, real, z, eps, step, alpha):
+    def step(self, real, z, eps, step, alpha, label=None):
         """One full iteration: real [B,3,R,R] fp32, z [B,zdim], eps [B,1,1,1] (drawn by the caller
         on the CPU generator, train.py:133,142) — device tensors, or host tensors (pinned for an
         asynchronous copy), which are then transferred on a copy stream."""
         host = (not real.is_cuda) and self.bD.p.is_cuda
         if host:
             real, z, eps = self._stage_host_inputs(real, z, eps)
-        self._step_device(real, z, eps, step, alpha)
+        if label is not None and not label.is_cuda and self.bD.p.is_cuda:
+            label = label.to(self.bD.p.device, non_blocking=True)
+        self._step_device(real, z, eps, step, alpha, label)
         if host:                             # staging set free again once this iteration has read it
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream())
             self._stg_free[self._stg_key] = ev
 
-    def _step_device(self, real, z, eps, step, alpha):
+    def _step_device(self, real, z, eps, step, alpha, label=None):
         fading = 0 <= alpha < 1
         if fading:
             self.alpha_dev.fill_(float(alpha))
         a = self.alpha_dev if fading else alpha
         if not self.use_graph:
-            self._iteration(real, z, eps, step, a, fading)
+            self._iteration(real, z, eps, step, a, fading, label)
         else:
-            self._graph_step(real, z, eps, step, a, fading)
+            self._graph_step(real, z, eps, step, a, fading, label)
         self.iterations += 1
 
-    def _graph_step(self, real, z, eps, step, a, fading):
-        key = (step, fading, tuple(real.shape))
+    def _graph_step(self, real, z, eps, step, a, fading, label=None):
+        key = (step, fading, tuple(real.shape), label is not None)
         ent = self._graphs.get(key)
         K = get_kernels()
         if ent is None:
             sreal, sz, seps = real.clone(), z.clone(), eps.clone()
+            slabel = label.clone() if label is not None else None
             # warm up on a side stream (allocator + lazy init), restoring state afterwards
             state = [self.bD.p, self.bD.v, self.bD.steps, self.bG.p, self.bG.v, self.bG.steps]
             state += [b.m for b in (self.bD, self.bG) if b.m is not None]
@@ -391,7 +449,7 @@ class Trainer:
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
                 for _ in range(2):
-                    self._iteration(sreal, sz, seps, step, a, fading)
+                    self._iteration(sreal, sz, seps, step, a, fading, slabel)
             torch.cuda.current_stream().wait_stream(s)
             for dst, src in zip(state, snap):
                 dst.copy_(src)
@@ -405,11 +463,11 @@ class Trainer:
             if not self.segment_graphs:
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph):
-                    self._iteration(sreal, sz, seps, step, a, fading)
+                    self._iteration(sreal, sz, seps, step, a, fading, slabel)
                 graphs = [graph]
             else:
                 # one graph per segment; the NCCL all-reduces run between the replays
-                st = self._state(sreal, sz, seps, step, a, fading)
+                st = self._state(sreal, sz, seps, step, a, fading, slabel)
                 graphs, pool = [], None
                 for seg in (self._seg_d, self._seg_g, self._seg_end):
                     gph = torch.cuda.CUDAGraph()
@@ -419,11 +477,13 @@ class Trainer:
                     pool = gph.pool()
                     graphs.append(gph)
                 del st
-            ent = (graphs, sreal, sz, seps, self.bD.plan(_d_active(self.D, step, fading)),
-                   self.bG.plan(_g_active(self.G, step, fading)))
+            namesD, namesG = self._active(step, a, fading, slabel)
+            ent = (graphs, sreal, sz, seps, self.bD.plan(namesD), self.bG.plan(namesG), slabel)
             self._graphs[key] = ent
             # the capture itself did not execute anything
-        graphs, sreal, sz, seps, planD, planG = ent
+        graphs, sreal, sz, seps, planD, planG, slabel = ent
+        if slabel is not None:
+            slabel.copy_(label, non_blocking=True)
         sreal.copy_(real, non_blocking=True)
         sz.copy_(z, non_blocking=True)
         seps.copy_(eps, non_blocking=True)

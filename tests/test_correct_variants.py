@@ -100,3 +100,51 @@ def test_correct_variants_cuda_check_mode_and_bf16(name):
     assert helpers.rel(res16["grad_x_hat"], res["grad_x_hat"]) < 0.3         # bf16 LeakyReLU mask flips: 3-20 %
     # (||g|| - 1)^2 amplifies the relative error of ||g|| near 1: absolute + relative bound
     assert abs(float(res16["grad_penalty"]) - float(res["grad_penalty"])) <= 0.2 * float(res["grad_penalty"]) + 0.1
+
+
+@pytest.mark.parametrize("name", ["c2_a0.5", "c4_a0.5", "m2_a0.5", "m3_a0.25", "k2_a0.5_eq", "k3_a0.25", "k5_a0.5"])
+def test_trainer_generic_families_match_golden_cpu(name):
+    """progan_b200.Trainer (flat buckets, fused Adam/EMA, one D pass over cat([real, fake]), direct
+    gradient accumulation) on the other model families: generic bucket layout + probe for the live
+    parameter set, against the goldens of the real reference loop."""
+    from test_trainer import check_against_golden
+    prev = progan_b200.set_kernels(EmulKernels())
+    try:
+        inp = common.make_inputs(name)
+        G, D = helpers.build_models(inp, "fp32", name=name)
+        Grun, _ = helpers.build_models(inp, "fp32", name=name)
+        tr = progan_b200.Trainer(G, D, Grun)
+        tr.step(inp["real"], inp["z"], inp["eps"], inp["step"], inp["alpha"], label=inp["label"])
+        check_against_golden(name, tr, G, D, Grun, 2e-4)
+    finally:
+        progan_b200.set_kernels(prev)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["c3_a0.25", "m2_a0.5", "k3_a0.25"])
+def test_trainer_generic_families_cuda(name):
+    """The same on the CUDA kernels: fp32 check mode against the goldens, and the bf16 product
+    path eager vs CUDA-graph replay."""
+    from test_trainer import check_against_golden
+    K = progan_b200.get_kernels()
+    K.conv_impl, K.wgrad_tc = "simt", False
+    K.invalidate_packs()
+    inp = common.make_inputs(name)
+    dev = "cuda"
+    lab = inp["label"].to(dev) if inp["label"] is not None else None
+    G, D = helpers.build_models(inp, "fp32", device=dev, name=name)
+    Grun, _ = helpers.build_models(inp, "fp32", device=dev, name=name)
+    tr = progan_b200.Trainer(G, D, Grun)
+    tr.step(inp["real"].to(dev), inp["z"].to(dev), inp["eps"].to(dev), inp["step"], inp["alpha"], label=lab)
+    check_against_golden(name, tr, G, D, Grun, 1e-3)
+    K.conv_impl, K.wgrad_tc = "tc", True
+    res = []
+    for use_graph in (False, True):
+        K.invalidate_packs()
+        G, D = helpers.build_models(inp, "bf16", device=dev, name=name)
+        tr = progan_b200.Trainer(G, D, None, use_graph=use_graph)
+        tr.step(inp["real"].to(dev), inp["z"].to(dev), inp["eps"].to(dev), inp["step"], inp["alpha"], label=lab)
+        torch.cuda.synchronize()
+        res.append(tr)
+    assert helpers.rel(res[1].bD.p, res[0].bD.p) < 1e-5
+    assert helpers.rel(res[1].bG.p, res[0].bG.p) < 1e-5
