@@ -4,7 +4,9 @@ Drop-in for the hot path of gwilczynski95/Progressive-GAN-pytorch:
     from progan_b200 import Generator, Discriminator      # instead of progan_modules
 """
 from .kernels import ConvOp, get_kernels, set_kernels
-from .progan_modules import (ConditionalCorrectDiscriminatorWgangp, ConditionalCorrectGenerator, ConvBlock,
+from .progan_modules import (ConditionalCorrectDiscriminatorAda, ConditionalCorrectDiscriminatorWgangp,
+                             ConditionalCorrectGenerator, ConditionalCorrectGeneratorAda,
+                             ConditionalDiscriminatorWgangp, ConditionalGenerator, ConvBlock,
                              CorrectDiscriminator, CorrectGenerator, Discriminator, EqualEmbed,
                              EqualConv2d, EqualConvTranspose2d, EqualLinear, Generator, MnistConvBlock,
                              PixelNorm,
@@ -14,6 +16,7 @@ from .train import ProgressiveSchedule, Trainer
 from . import mnist_pggan
 
 __all__ = ["Generator", "Discriminator", "CorrectGenerator", "CorrectDiscriminator", "mnist_pggan", "ConditionalCorrectGenerator",
-           "ConditionalCorrectDiscriminatorWgangp", "EqualEmbed", "ConvBlock", "EqualConv2d", "EqualConvTranspose2d",
+           "ConditionalCorrectDiscriminatorWgangp", "ConditionalGenerator", "ConditionalDiscriminatorWgangp",
+           "ConditionalCorrectGeneratorAda", "ConditionalCorrectDiscriminatorAda", "EqualEmbed", "ConvBlock", "EqualConv2d", "EqualConvTranspose2d",
            "EqualLinear", "PixelNorm", "ConvOp", "get_kernels", "set_kernels",
            "set_default_precision", "gradient_penalty", "Trainer", "ProgressiveSchedule"]

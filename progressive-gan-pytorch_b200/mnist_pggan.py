@@ -5,7 +5,7 @@ use_mnist_conv_blocks=True)` (:83-137).  Same kernels as progan_modules; same co
 arguments, attributes, forward signatures and state-dict keys/shapes/order as the reference —
 including its quirks: LeakyReLU(0.1) after the input layer (:21), `max_step = 3` (:35), and the
 two dead `mnist_progression_*` blocks the discriminator carries for checkpoint compatibility
-(:93-97)."""
+(:93-97) — plus the class-conditional variants of conditional_mnist_wgan_train.py (:140-345)."""
 import torch
 from torch import nn
 
@@ -39,6 +39,9 @@ class Generator(nn.Module, _AlphaMixin):
         self.to_rgb_32 = EqualConv2d(c, 1, 1)
         self.max_step = 3
 
+    def _latent_dim(self):
+        return self.input_dim
+
     def _output(self, feat1, feat2, head1, head2, alpha, fading, dt):
         out = _to_rgb(feat2, head2, dt)
         if fading:
@@ -51,7 +54,7 @@ class Generator(nn.Module, _AlphaMixin):
             step = self.max_step
         dt = _act_dtype(self.precision)
         fading = torch.is_tensor(alpha) or (0 <= alpha < 1)
-        z = input.reshape(-1, 1, 1, self.input_dim).to(dt).contiguous()
+        z = input.reshape(-1, 1, 1, self._latent_dim()).to(dt).contiguous()
         out_4 = _fused_layer(z, self.input_layer[0], 0.1, True)          # slope 0.1 (:21)
         out_4 = self.progression_4(out_4)
         out_8 = self.progression_8(F_.upsample2(out_4))
@@ -105,3 +108,92 @@ class Discriminator(nn.Module, _AlphaMixin):
         C = out.shape[-1]
         d = F_.PwFwd.apply(out, lin.weight_orig, lin.bias, "reduce", C, 1, 1, C, self.linear.scale, dt)
         return d.view(-1, 1)
+
+
+class ConditionalGenerator(Generator):
+    """mnist_pggan.ConditionalGenerator (mnist_pggan.py:140-221; conditional_mnist_wgan_train.py):
+    cat(normalize(z), normalize(embedding[y])) in front of Generator's wiring; embedding_dim =
+    input_code_dim."""
+
+    def __init__(self, input_code_dim=128, num_of_classes=10, in_channel=64, pixel_norm=True, tanh=True,
+                 use_mnist_conv_blocks=True, precision=None):
+        nn.Module.__init__(self)
+        self.input_dim = input_code_dim
+        self.in_channel = in_channel
+        self.tanh = tanh
+        self.use_mnist_conv_blocks = use_mnist_conv_blocks
+        self.num_of_classes = num_of_classes
+        self.embedding_dim = input_code_dim
+        self.pixel_norm = pixel_norm
+        self.precision = precision or _pm._DEFAULT_PRECISION
+        c = in_channel
+        self.embedding = nn.Embedding(num_of_classes, self.embedding_dim)
+        self.input_layer = nn.Sequential(EqualConvTranspose2d(input_code_dim + self.embedding_dim, c, 4, 1, 0),
+                                         PixelNorm(), _LeakyMarker(0.1))
+        block = MnistConvBlock if use_mnist_conv_blocks else ConvBlock
+        self.progression_4 = block(c, c, 3, 1, pixel_norm=pixel_norm)
+        self.progression_8 = block(c, c, 3, 1, pixel_norm=pixel_norm)
+        self.progression_16 = block(c, c, 3, 1, pixel_norm=pixel_norm)
+        self.progression_32 = block(c, c, 3, 1, pixel_norm=pixel_norm)
+        self.to_rgb_8 = EqualConv2d(c, 1, 1)
+        self.to_rgb_16 = EqualConv2d(c, 1, 1)
+        self.to_rgb_32 = EqualConv2d(c, 1, 1)
+        self.max_step = 3
+
+    def _latent_dim(self):
+        return self.input_dim + self.embedding_dim
+
+    def forward(self, input, label, step=0, alpha=-1):
+        nrm = torch.nn.functional.normalize
+        data_in = torch.cat([nrm(input), nrm(self.embedding(label)).to(input.dtype)], 1)   # (:192-196)
+        return Generator.forward(self, data_in, step, alpha)
+
+
+class ConditionalDiscriminatorWgangp(nn.Module, _AlphaMixin):
+    """mnist_pggan.ConditionalDiscriminatorWgangp (mnist_pggan.py:224-286): the label enters as a
+    second image channel (an R*R embedding per resolution) in front of every from_rgb."""
+
+    def __init__(self, feat_dim=64, num_of_classes=10, use_mnist_conv_blocks=True, precision=None):
+        super().__init__()
+        self.feat_dim = feat_dim
+        self.num_of_classes = num_of_classes
+        self.use_mnist_conv_blocks = use_mnist_conv_blocks
+        self.precision = precision or _pm._DEFAULT_PRECISION
+        f = feat_dim
+        block = MnistConvBlock if use_mnist_conv_blocks else ConvBlock
+        self.progression = nn.ModuleList([block(f, f, 3, 1), block(f, f, 3, 1), block(f, f, 3, 1),
+                                          ConvBlock(f + 1, f, 3, 1, 4, 0)])
+        self.embeddings = nn.ModuleList([nn.Embedding(num_of_classes, r * r) for r in (32, 16, 8, 4)])
+        self.from_rgb = nn.ModuleList([EqualConv2d(1 + 1, f, 1) for _ in range(4)])
+        self.n_layer = len(self.progression)
+        self.linear = EqualLinear(f, 1)
+
+    def forward(self, input_data, label, step=0, alpha=-1, mbstd_group=None):
+        out, dt = _pm._critic_trunk(self, input_data, step, alpha, mbstd_group, 0,
+                                    lambda img, index: _pm._label_plane(self, img, label, index))
+        return _pm._critic_head(self, out, dt).view(-1, 1)
+
+
+class ConditionalDiscriminatorAda(nn.Module, _AlphaMixin):
+    """mnist_pggan.ConditionalDiscriminatorAda (mnist_pggan.py:289-345): projection critic, the
+    label enters through <h, normalize(embedding[y])>; returns shape [B]."""
+
+    def __init__(self, feat_dim=64, num_of_classes=10, use_mnist_conv_blocks=True, precision=None):
+        super().__init__()
+        self.feat_dim = feat_dim
+        self.num_of_classes = num_of_classes
+        self.embedding_dim = feat_dim
+        self.use_mnist_conv_blocks = use_mnist_conv_blocks
+        self.precision = precision or _pm._DEFAULT_PRECISION
+        f = feat_dim
+        block = MnistConvBlock if use_mnist_conv_blocks else ConvBlock
+        self.progression = nn.ModuleList([block(f, f, 3, 1), block(f, f, 3, 1), block(f, f, 3, 1),
+                                          ConvBlock(f + 1, f, 3, 1, 4, 0)])
+        self.embedding = nn.Embedding(num_of_classes, embedding_dim=self.embedding_dim)
+        self.from_rgb = nn.ModuleList([EqualConv2d(1, f, 1) for _ in range(4)])
+        self.n_layer = len(self.progression)
+        self.linear = EqualLinear(f, 1)
+
+    def forward(self, input_data, label, step=0, alpha=-1, mbstd_group=None):
+        out, dt = _pm._critic_trunk(self, input_data, step, alpha, mbstd_group, 0)
+        return _pm._projection_score(self, out, label, dt)

@@ -308,6 +308,9 @@ class CorrectGenerator(nn.Module, _AlphaMixin):
         self.to_rgb_32 = EqualConv2d(c, 3, 1)
         self.max_step = max_step
 
+    def _latent_dim(self):
+        return self.input_dim
+
     def _output(self, feat1, feat2, head1, head2, alpha, fading, dt):
         """(:512-521): blend with the upsampled previous head iff 0 <= alpha < 1, then tanh."""
         out = _to_rgb(feat2, head2, dt)
@@ -321,7 +324,7 @@ class CorrectGenerator(nn.Module, _AlphaMixin):
             step = self.max_step
         dt = _act_dtype(self.precision)
         fading = torch.is_tensor(alpha) or (0 <= alpha < 1)
-        z = input.reshape(-1, 1, 1, self.input_dim).to(dt).contiguous()
+        z = input.reshape(-1, 1, 1, self._latent_dim()).to(dt).contiguous()
         # the stem applies PixelNorm after both convs whatever `pixel_norm` says (:487-494)
         out_4 = _fused_layer(z, self.progression_4[0], 0.2, True)
         out_4 = _fused_layer(out_4, self.progression_4[3], 0.2, True)
@@ -518,3 +521,196 @@ class ConditionalCorrectDiscriminatorWgangp(nn.Module, _AlphaMixin):
         C = out.shape[-1]
         d = F_.PwFwd.apply(out, lin.weight_orig, lin.bias, "reduce", C, 1, 1, C, self.linear.scale, dt)
         return d.view(-1, 1)
+
+
+def _critic_trunk(m, input, step, alpha, mbstd_group, last, plane=None):
+    """Body shared by the remaining critics: from_rgb at resolution `step`, the blocks down to the
+    4x4 one (reached at i == `last`: 0 for the wiring of Discriminator, 1 for the Correct* wiring),
+    fade-in blend with the from_rgb of the halved input at the first block, minibatch-stddev in
+    front of the last block.  `plane(img, index)` appends the label plane where the class has
+    one.  Returns the [B,1,1,C] feature in front of the linear head."""
+    dt = _act_dtype(m.precision)
+    fading = torch.is_tensor(alpha) or (0 <= alpha < 1)
+    x = input.contiguous()
+    if x.dtype != _img_dtype(m.precision):
+        x = x.to(_img_dtype(m.precision))
+    out = None
+    for i in range(step, last - 1, -1):
+        index = m.n_layer - i - 1 + last
+        if i == step:
+            out = _from_rgb(plane(x, index) if plane else x, m.from_rgb[index], dt)
+        if i == last:
+            out = F_.Mbstd.apply(out, F_.K().mbstd_channels(out.shape[-1], out.dtype), mbstd_group)
+        out = m.progression[index](out, pool=(i > last))
+        if i > last and i == step and fading:
+            half = F_.avgpool2(x, "nchw")
+            skip = _from_rgb(plane(half, index + 1) if plane else half, m.from_rgb[index + 1], dt)
+            out = F_.Blend.apply(skip, out, m._alpha(alpha, out.device))
+    return out, dt
+
+
+def _critic_head(m, out, dt):
+    lin = m.linear.linear
+    C = out.shape[-1]
+    return F_.PwFwd.apply(out, lin.weight_orig, lin.bias, "reduce", C, 1, 1, C, m.linear.scale, dt)
+
+
+def _projection_score(m, out, label, dt):
+    """Projection critic (progan_modules.py:909-913, mnist_pggan.py:338-343):
+    D(x, y) = linear(h) + <h, normalize(embedding[y])>, returned with shape [B]."""
+    embed = torch.nn.functional.normalize(m.embedding(label))
+    proj = (out.reshape(out.shape[0], -1).to(embed.dtype) * embed).sum(dim=-1)
+    return _critic_head(m, out, dt).view(-1) + proj.to(torch.float32)
+
+
+def _label_plane(m, img, label, index):
+    plane = m.embeddings[index](label).to(img.dtype).view(-1, 1, img.shape[-2], img.shape[-1])
+    return torch.cat([img, plane], 1).contiguous()
+
+
+class ConditionalGenerator(Generator):
+    """Class-conditional form of Generator (progan_modules.py:314-404; conditional_cifar10_wgan_train.py):
+    a plain nn.Embedding of dimension num_of_classes is concatenated to z in front of the input
+    layer; everything behind it is Generator's wiring (step 1 = 8 px ... 6 = 256 px)."""
+
+    def __init__(self, input_code_dim=128, num_of_classes=10, in_channel=128, pixel_norm=True, tanh=True,
+                 max_step=6, precision=None):
+        nn.Module.__init__(self)
+        self.input_dim = input_code_dim
+        self.in_channel = in_channel
+        self.tanh = tanh
+        self.pixel_norm = pixel_norm
+        self.num_of_classes = num_of_classes
+        self.embedding_dim = num_of_classes
+        self.precision = precision or _DEFAULT_PRECISION
+        c = in_channel
+        self.embedding = nn.Embedding(num_of_classes, self.embedding_dim)
+        self.input_layer = nn.Sequential(EqualConvTranspose2d(input_code_dim + self.embedding_dim, c, 4, 1, 0),
+                                         PixelNorm(), _LeakyMarker(0.2))
+        self.progression_4 = ConvBlock(c, c, 3, 1, pixel_norm=pixel_norm)
+        self.progression_8 = ConvBlock(c, c, 3, 1, pixel_norm=pixel_norm)
+        self.progression_16 = ConvBlock(c, c, 3, 1, pixel_norm=pixel_norm)
+        self.progression_32 = ConvBlock(c, c, 3, 1, pixel_norm=pixel_norm)
+        self.progression_64 = ConvBlock(c, c // 2, 3, 1, pixel_norm=pixel_norm)
+        self.progression_128 = ConvBlock(c // 2, c // 4, 3, 1, pixel_norm=pixel_norm)
+        self.progression_256 = ConvBlock(c // 4, c // 4, 3, 1, pixel_norm=pixel_norm)
+        self.to_rgb_8 = EqualConv2d(c, 3, 1)
+        self.to_rgb_16 = EqualConv2d(c, 3, 1)
+        self.to_rgb_32 = EqualConv2d(c, 3, 1)
+        self.to_rgb_64 = EqualConv2d(c // 2, 3, 1)
+        self.to_rgb_128 = EqualConv2d(c // 4, 3, 1)
+        self.to_rgb_256 = EqualConv2d(c // 4, 3, 1)
+        self.max_step = max_step
+
+    def _latent(self, input, label):
+        return torch.cat([input, self.embedding(label).to(input.dtype)], 1)               # (:370-371)
+
+    def forward(self, input, label, step=0, alpha=-1):
+        if step > self.max_step:
+            step = self.max_step
+        if step < 1:
+            return None
+        dt = _act_dtype(self.precision)
+        fading = torch.is_tensor(alpha) or (0 <= alpha < 1)
+        z = self._latent(input, label).reshape(-1, 1, 1, self.input_dim + self.embedding_dim).to(dt).contiguous()
+        feat = self.progression_4(_fused_layer(z, self.input_layer[0], 0.2, True))
+        prev = None
+        blocks, heads = self._blocks(), self._heads()
+        for s in range(1, step + 1):
+            prev = feat
+            feat = blocks[s - 1](F_.upsample2(feat))
+        out = _to_rgb(feat, heads[step - 1], dt)
+        if step >= 2 and fading:
+            skip = F_.upsample2(_to_rgb(prev, heads[step - 2], dt), "nchw")
+            out = F_.Blend.apply(skip, out, self._alpha(alpha, out.device))
+        return F_.Tanh.apply(out) if self.tanh else out
+
+
+class ConditionalDiscriminatorWgangp(nn.Module, _AlphaMixin):
+    """Class-conditional form of Discriminator (progan_modules.py:407-476): a per-resolution
+    nn.Embedding of R*R values is appended to the image as a 4th channel in front of from_rgb (and
+    of the fade-in skip from_rgb); seven blocks, step 0 = 4 px ... 6 = 256 px."""
+
+    def __init__(self, feat_dim=128, num_of_classes=10, precision=None):
+        super().__init__()
+        self.feat_dim = feat_dim
+        self.num_of_classes = num_of_classes
+        self.precision = precision or _DEFAULT_PRECISION
+        f = feat_dim
+        self.progression = nn.ModuleList([ConvBlock(f // 4, f // 4, 3, 1), ConvBlock(f // 4, f // 2, 3, 1),
+                                          ConvBlock(f // 2, f, 3, 1), ConvBlock(f, f, 3, 1),
+                                          ConvBlock(f, f, 3, 1), ConvBlock(f, f, 3, 1),
+                                          ConvBlock(f + 1, f, 3, 1, 4, 0)])
+        self.embeddings = nn.ModuleList([nn.Embedding(num_of_classes, r * r)
+                                         for r in (256, 128, 64, 32, 16, 8, 4)])
+        self.from_rgb = nn.ModuleList([EqualConv2d(3 + 1, c_, 1) for c_ in (f // 4, f // 4, f // 2, f, f, f, f)])
+        self.n_layer = len(self.progression)
+        self.linear = EqualLinear(f, 1)
+
+    def forward(self, input, label, step=0, alpha=-1, mbstd_group=None):
+        out, dt = _critic_trunk(self, input, step, alpha, mbstd_group, 0,
+                                lambda img, index: _label_plane(self, img, label, index))
+        return _critic_head(self, out, dt).view(-1, 1)
+
+
+class ConditionalCorrectGeneratorAda(CorrectGenerator):
+    """ADA-style conditional generator (progan_modules.py:778-854): cat(normalize(z),
+    normalize(embedding[y])) in front of CorrectGenerator's wiring (step 1 = 4 px ... 4 = 32 px)."""
+
+    def __init__(self, input_code_dim=512, num_of_classes=10, in_channel=512, pixel_norm=True, tanh=False,
+                 max_step=4, precision=None):
+        nn.Module.__init__(self)
+        self.input_dim = input_code_dim
+        self.in_channel = in_channel
+        self.tanh = tanh
+        self.pixel_norm = pixel_norm
+        self.num_of_classes = num_of_classes
+        self.embedding_dim = input_code_dim
+        self.precision = precision or _DEFAULT_PRECISION
+        c = in_channel
+        self.embedding = nn.Embedding(num_of_classes, embedding_dim=self.embedding_dim)
+        self.progression_4 = nn.Sequential(
+            EqualConvTranspose2d(input_code_dim + self.embedding_dim, c, 4, 1, 0), PixelNorm(),
+            _LeakyMarker(0.2), EqualConv2d(c, c, 3, padding=1), PixelNorm(), _LeakyMarker(0.2))
+        self.progression_8 = ConvBlock(c, c, 3, 1, pixel_norm=pixel_norm)
+        self.progression_16 = ConvBlock(c, c, 3, 1, pixel_norm=pixel_norm)
+        self.progression_32 = ConvBlock(c, c, 3, 1, pixel_norm=pixel_norm)
+        self.to_rgb_4 = EqualConv2d(c, 3, 1)
+        self.to_rgb_8 = EqualConv2d(c, 3, 1)
+        self.to_rgb_16 = EqualConv2d(c, 3, 1)
+        self.to_rgb_32 = EqualConv2d(c, 3, 1)
+        self.max_step = max_step
+
+    def _latent_dim(self):
+        return self.input_dim + self.embedding_dim
+
+    def forward(self, input, label, step=0, alpha=-1):
+        nrm = torch.nn.functional.normalize
+        data_in = torch.cat([nrm(input), nrm(self.embedding(label)).to(input.dtype)], 1)  # (:830-833)
+        return CorrectGenerator.forward(self, data_in, step, alpha)
+
+
+class ConditionalCorrectDiscriminatorAda(nn.Module, _AlphaMixin):
+    """Projection critic on CorrectDiscriminator's wiring (progan_modules.py:857-915): plain
+    3-channel from_rgb, the label enters only through <h, normalize(embedding[y])> added to the
+    linear score; returns shape [B]."""
+
+    def __init__(self, feat_dim=512, num_of_classes=10, precision=None):
+        super().__init__()
+        self.feat_dim = feat_dim
+        self.num_of_classes = num_of_classes
+        self.embedding_dim = feat_dim
+        self.precision = precision or _DEFAULT_PRECISION
+        f = feat_dim
+        self.embedding = nn.Embedding(num_of_classes, embedding_dim=self.embedding_dim)
+        self.progression = nn.ModuleList([ConvBlock(f, f, 3, 1), ConvBlock(f, f, 3, 1),
+                                          ConvBlock(f, f, 3, 1), ConvBlock(f + 1, f, 3, 1, 4, 0)])
+        self.from_rgb = nn.ModuleList([EqualConv2d(3, f, 1) for _ in range(4)])
+        self.n_layer = len(self.progression)
+        self.linear = EqualLinear(f, 1)
+
+    def forward(self, input, label, step=0, alpha=-1, mbstd_group=None):
+        if step < 1:
+            raise RuntimeError("ConditionalCorrectDiscriminatorAda: step must be >= 1")
+        out, dt = _critic_trunk(self, input, step, alpha, mbstd_group, 1)
+        return _projection_score(self, out, label, dt)

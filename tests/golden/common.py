@@ -54,64 +54,84 @@ COND_CASES = {
 }
 
 
+# the remaining conditional rewirings; same tuple layout as COND_CASES (do_equal_embed unused)
+# progan_modules.ConditionalGenerator / ConditionalDiscriminatorWgangp (:314-476): step 0 = 4 px
+CONDBASE_CASES = {
+    "b1_a1.0": (32, 16, 1, 1.0, 4, False, True, 10, False),
+    "b2_a0.5": (32, 16, 2, 0.5, 4, True, True, 10, False),
+    "b3_a0.25_nopn": (32, 32, 3, 0.25, 2, False, False, 7, False),
+}
+# progan_modules.ConditionalCorrectGeneratorAda / ConditionalCorrectDiscriminatorAda (:778-915)
+ADA_CASES = {
+    "a1_a1.0": (32, 16, 1, 1.0, 4, False, True, 10, False),
+    "a2_a0.5": (32, 16, 2, 0.5, 4, False, True, 10, False),
+    "a2_a0.5_tanh": (32, 16, 2, 0.5, 4, True, True, 10, False),
+    "a4_a0.25": (32, 32, 4, 0.25, 2, False, True, 14, False),
+}
+# mnist_pggan.ConditionalGenerator with ConditionalDiscriminatorWgangp / ConditionalDiscriminatorAda
+MCOND_CASES = {
+    "n1_a1.0": (32, 16, 1, 1.0, 4, True, True, 10, False),
+    "n3_a0.5": (32, 16, 3, 0.5, 2, True, True, 10, False),
+}
+MADA_CASES = {
+    "p2_a0.5": (32, 16, 2, 0.5, 4, True, True, 10, False),
+    "p3_a1.0_nopn": (32, 32, 3, 1.0, 2, False, False, 10, False),
+}
+
+# family -> (cases, generator class, critic class, lives in mnist_pggan, first resolution, image channels)
+FAMILIES = {
+    "base": (CASES, "Generator", "Discriminator", False, 8, 3),
+    "correct": (CORRECT_CASES, "CorrectGenerator", "CorrectDiscriminator", False, 4, 3),
+    "mnist": (MNIST_CASES, "Generator", "Discriminator", True, 8, 1),
+    "cond": (COND_CASES, "ConditionalCorrectGenerator", "ConditionalCorrectDiscriminatorWgangp", False, 4, 3),
+    "condbase": (CONDBASE_CASES, "ConditionalGenerator", "ConditionalDiscriminatorWgangp", False, 8, 3),
+    "ada": (ADA_CASES, "ConditionalCorrectGeneratorAda", "ConditionalCorrectDiscriminatorAda", False, 4, 3),
+    "mcond": (MCOND_CASES, "ConditionalGenerator", "ConditionalDiscriminatorWgangp", True, 8, 1),
+    "mada": (MADA_CASES, "ConditionalGenerator", "ConditionalDiscriminatorAda", True, 8, 1),
+}
+VARIANT_CASES = [n for f, v in FAMILIES.items() if f != "base" for n in v[0]]
+ALL_CASES = list(CASES) + VARIANT_CASES
+
+
 def family(name):
-    if name in CORRECT_CASES:
-        return "correct"
-    if name in MNIST_CASES:
-        return "mnist"
-    return "cond" if name in COND_CASES else "base"
+    for fam, v in FAMILIES.items():
+        if name in v[0]:
+            return fam
+    raise KeyError(name)
+
+
+def classes(mod, name):
+    """(Generator class, Discriminator class) of `mod` — the reference's progan_modules (the
+    mnist families live in its sibling module mnist_pggan) or the mirror package."""
+    _, g, d, in_mnist, _, _ = FAMILIES[family(name)]
+    if in_mnist:
+        if hasattr(mod, "mnist_pggan"):
+            mod = mod.mnist_pggan
+        else:
+            import mnist_pggan as mod
+    return getattr(mod, g), getattr(mod, d)
 
 
 def build(mod, name, inp, **extra):
     """(G, D) instances of the case's model family from `mod` (reference module or mirror)."""
     GC, DC = classes(mod, name)
-    if family(name) == "cond":
-        G = GC(input_code_dim=inp["z_dim"], num_of_classes=inp["num_classes"], in_channel=inp["channel"],
-               pixel_norm=inp["pixel_norm"], tanh=inp["tanh"], max_step=6,
-               do_equal_embed=inp["equal_embed"], **extra)
-        D = DC(feat_dim=inp["channel"], num_of_classes=inp["num_classes"],
-               do_equal_embed=inp["equal_embed"], **extra)
-        return G, D
-    G = GC(input_code_dim=inp["z_dim"], in_channel=inp["channel"], pixel_norm=inp["pixel_norm"],
-           tanh=inp["tanh"], **extra)
-    return G, DC(feat_dim=inp["channel"], **extra)
-
-
-def classes(mod, name):
-    """(Generator class, Discriminator class) of `mod` — the reference's progan_modules (the
-    mnist family lives in its sibling module mnist_pggan) or the mirror package."""
     fam = family(name)
-    if fam == "correct":
-        return mod.CorrectGenerator, mod.CorrectDiscriminator
+    gk = dict(input_code_dim=inp["z_dim"], in_channel=inp["channel"], pixel_norm=inp["pixel_norm"],
+              tanh=inp["tanh"])
+    dk = dict(feat_dim=inp["channel"])
+    if inp["num_classes"]:
+        gk["num_of_classes"] = dk["num_of_classes"] = inp["num_classes"]
     if fam == "cond":
-        return mod.ConditionalCorrectGenerator, mod.ConditionalCorrectDiscriminatorWgangp
-    if fam == "mnist":
-        if hasattr(mod, "mnist_pggan"):
-            return mod.mnist_pggan.Generator, mod.mnist_pggan.Discriminator
-        import mnist_pggan
-        return mnist_pggan.Generator, mnist_pggan.Discriminator
-    return mod.Generator, mod.Discriminator
+        gk.update(max_step=6, do_equal_embed=inp["equal_embed"])
+        dk.update(do_equal_embed=inp["equal_embed"])
+    return GC(**gk, **extra), DC(**dk, **extra)
 
 
-def model_shapes(channel, z_dim, pixel_norm, fam="base", ncls=10, eq=False):
+def model_shapes(name, inp):
     """state-dict key -> shape, taken from the host mirror (identical to the reference's;
     make_golden.py asserts that)."""
     import progan_b200
-    if fam in ("correct", "mnist", "cond"):
-        if fam == "cond":
-            G = progan_b200.ConditionalCorrectGenerator(z_dim, ncls, channel, pixel_norm=pixel_norm,
-                                                        max_step=6, do_equal_embed=eq)
-            D = progan_b200.ConditionalCorrectDiscriminatorWgangp(channel, ncls, do_equal_embed=eq)
-        elif fam == "correct":
-            G = progan_b200.CorrectGenerator(input_code_dim=z_dim, in_channel=channel, pixel_norm=pixel_norm)
-            D = progan_b200.CorrectDiscriminator(feat_dim=channel)
-        else:
-            G = progan_b200.mnist_pggan.Generator(input_code_dim=z_dim, in_channel=channel, pixel_norm=pixel_norm)
-            D = progan_b200.mnist_pggan.Discriminator(feat_dim=channel)
-        return ({k: tuple(v.shape) for k, v in G.state_dict().items()},
-                {k: tuple(v.shape) for k, v in D.state_dict().items()})
-    G = progan_b200.Generator(input_code_dim=z_dim, in_channel=channel, pixel_norm=pixel_norm)
-    D = progan_b200.Discriminator(feat_dim=channel)
+    G, D = build(progan_b200, name, inp)
     return ({k: tuple(v.shape) for k, v in G.state_dict().items()},
             {k: tuple(v.shape) for k, v in D.state_dict().items()})
 
@@ -127,20 +147,23 @@ def make_state(shapes, seed):
 
 
 def make_inputs(name):
-    spec = CASES.get(name) or CORRECT_CASES.get(name) or MNIST_CASES.get(name) or COND_CASES[name]
+    fam = family(name)
+    cases, _, _, _, res0, img_ch = FAMILIES[fam]
+    spec = cases[name]
     ch, zd, step, alpha, B, tanh, pn = spec[:7]
     ncls, eq = (spec[7], spec[8]) if len(spec) > 7 else (0, False)
-    gs, ds = model_shapes(ch, zd, pn, family(name), ncls, eq)
+    inp = dict(step=step, alpha=alpha, tanh=tanh, pixel_norm=pn, channel=ch, z_dim=zd, num_classes=ncls,
+               equal_embed=eq)
+    gs, ds = model_shapes(name, inp)
     G_state, D_state = make_state(gs, 100), make_state(ds, 200)
     g = torch.Generator().manual_seed(1234)
-    R = 2 * 2 ** step if family(name) in ("correct", "cond") else 4 * 2 ** step
-    real = torch.rand(B, 1 if family(name) == "mnist" else 3, R, R, generator=g) * 2 - 1
+    R = (res0 // 2) * 2 ** step
+    real = torch.rand(B, img_ch, R, R, generator=g) * 2 - 1
     z = torch.randn(B, zd, generator=g)
     eps = torch.rand(B, 1, 1, 1, generator=g)
     label = torch.randint(0, ncls, (B,), generator=g) if ncls else None     # drawn last: older fixtures unchanged
-    return dict(G=G_state, D=D_state, real=real, z=z, eps=eps, step=step, alpha=alpha,
-                tanh=tanh, pixel_norm=pn, channel=ch, z_dim=zd, label=label, num_classes=ncls,
-                equal_embed=eq)
+    inp.update(G=G_state, D=D_state, real=real, z=z, eps=eps, label=label)
+    return inp
 
 
 def summarize(t, key):

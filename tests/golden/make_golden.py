@@ -91,7 +91,7 @@ def run_case(name):
 if __name__ == "__main__":
     torch.set_num_threads(8)
     only = sys.argv[1:]
-    for name in list(common.CASES) + list(common.CORRECT_CASES) + list(common.MNIST_CASES) + list(common.COND_CASES):
+    for name in common.ALL_CASES:
         if only and name not in only and common.family(name) not in only:
             continue
         res = run_case(name)

@@ -1,6 +1,7 @@
 """The Correct* rewiring (progan_modules.py:479-598: cifar_train.py / proper_cifar_train.py
 models), the mnist_pggan.py models (BASELINE config 0) and the class-conditional Correct* models
-(:601-775, BASELINE configs 3 and 5) through the product modules, pinned to golden vectors recorded from the REAL
+(:601-775, BASELINE configs 3 and 5) and the remaining conditional rewirings (:314-476, :778-915,
+mnist_pggan.py:140-345: label plane, normalised latent, projection critic) through the product modules, pinned to golden vectors recorded from the REAL
 reference classes: forward outputs, gradient penalty, every parameter gradient and the
 parameters after torch.optim.Adam(betas=(0, .99)) steps, EMA included.
 
@@ -57,7 +58,7 @@ def _check(name, res, loss, g_grads, G, D, Grun, tol):
             assert float((common.summarize(p, k) - s).norm()) <= tol * float(s.norm()) + 1e-7, (tag, k)
 
 
-@pytest.mark.parametrize("name", list(common.CORRECT_CASES) + list(common.MNIST_CASES) + list(common.COND_CASES))
+@pytest.mark.parametrize("name", common.VARIANT_CASES)
 def test_correct_variants_match_reference_golden_cpu(name):
     prev = progan_b200.set_kernels(EmulKernels())
     try:
@@ -82,7 +83,7 @@ def test_correct_state_dict_layout():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", list(common.CORRECT_CASES) + list(common.MNIST_CASES) + list(common.COND_CASES))
+@pytest.mark.parametrize("name", common.VARIANT_CASES)
 def test_correct_variants_cuda_check_mode_and_bf16(name):
     K = progan_b200.get_kernels()
     K.conv_impl, K.wgrad_tc = "simt", False
@@ -102,7 +103,9 @@ def test_correct_variants_cuda_check_mode_and_bf16(name):
     assert abs(float(res16["grad_penalty"]) - float(res["grad_penalty"])) <= 0.2 * float(res["grad_penalty"]) + 0.1
 
 
-@pytest.mark.parametrize("name", ["c2_a0.5", "c4_a0.5", "m2_a0.5", "m3_a0.25", "k2_a0.5_eq", "k3_a0.25", "k5_a0.5"])
+@pytest.mark.parametrize("name", ["c2_a0.5", "c4_a0.5", "m2_a0.5", "m3_a0.25", "k2_a0.5_eq", "k3_a0.25", "k5_a0.5",
+                                  "b2_a0.5", "b3_a0.25_nopn", "a2_a0.5", "a4_a0.25", "n3_a0.5", "p2_a0.5",
+                                  "p3_a1.0_nopn"])
 def test_trainer_generic_families_match_golden_cpu(name):
     """progan_b200.Trainer (flat buckets, fused Adam/EMA, one D pass over cat([real, fake]), direct
     gradient accumulation) on the other model families: generic bucket layout + probe for the live
@@ -121,7 +124,7 @@ def test_trainer_generic_families_match_golden_cpu(name):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["c3_a0.25", "m2_a0.5", "k3_a0.25"])
+@pytest.mark.parametrize("name", ["c3_a0.25", "m2_a0.5", "k3_a0.25", "b2_a0.5", "a4_a0.25", "p2_a0.5"])
 def test_trainer_generic_families_cuda(name):
     """The same on the CUDA kernels: fp32 check mode against the goldens, and the bf16 product
     path eager vs CUDA-graph replay."""
