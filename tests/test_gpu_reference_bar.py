@@ -1,0 +1,95 @@
+"""GPU: the reference bar of SURVEY §8(d) — the oracle loop (fp32 restatement of train.py:122-169,
+pinned to the reference by the goldens) run on the SAME B200 through PyTorch/cuDNN, in torch's
+default fp32 mode (cuDNN convs may use TF32) and under bf16 autocast (NCHW images: the loop's
+`grad_x_hat.view(b, -1)`, train.py:148, rejects a channels_last x_hat), timed next to the product's Trainer on BASELINE config 4 (128 px, batch 64, alpha 0.5).
+
+Gate: the product's iteration is faster than the stronger (bf16) cuDNN bar.  The measured numbers
+are written to gpurun_out/gpu_reference_bar.json when that directory exists (copied to profiles/)."""
+import json
+import os
+
+import pytest
+import torch
+
+import progan_b200
+from oracle import progan_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+B, RES, STEP, ALPHA = 64, 128, 5, 0.5
+WARM, ITERS = 3, 8
+
+
+def _inputs():
+    g = torch.Generator().manual_seed(1234)
+    real = (torch.rand(B, 3, RES, RES, generator=g) * 2 - 1).to(DEV)
+    z = torch.randn(B, 128, generator=g).to(DEV)
+    eps = torch.rand(B, 1, 1, 1, generator=g).to(DEV)
+    return real, z, eps
+
+
+def _time(fn):
+    for _ in range(WARM):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(ITERS):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / ITERS
+
+
+def _oracle_ms(autocast):
+    torch.manual_seed(0)
+    with torch.device("cpu"):
+        G = progan_b200.Generator(128, 128, tanh=False)
+        D = progan_b200.Discriminator(128)
+    PG, PD, PR = O.params_of(G, device=DEV), O.params_of(D, device=DEV), O.params_of(G, False, device=DEV)
+    optG, optD = O.AdamState(PG), O.AdamState(PD)
+    real, z, eps = _inputs()
+
+    def it():
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            O.train_iteration(PG, PD, PR, optG, optD, real, z, eps, STEP, ALPHA)
+
+    prev = torch.backends.cudnn.benchmark
+    torch.backends.cudnn.benchmark = True          # give cuDNN its autotuned algorithms
+    try:
+        return _time(it)
+    finally:
+        torch.backends.cudnn.benchmark = prev
+
+
+def _product_ms():
+    K = progan_b200.get_kernels()
+    K.conv_impl, K.wgrad_tc = "tc", True
+    K.invalidate_packs()
+    torch.manual_seed(0)
+    G = progan_b200.Generator(128, 128, tanh=False, precision="bf16").to(DEV)
+    D = progan_b200.Discriminator(128, precision="bf16").to(DEV)
+    Grun = progan_b200.Generator(128, 128, tanh=False, precision="bf16").to(DEV)
+    tr = progan_b200.Trainer(G, D, Grun, use_graph=True)
+    real, z, eps = _inputs()
+    return _time(lambda: tr.step(real, z, eps, STEP, ALPHA))
+
+
+def test_product_beats_the_cudnn_reference_bar():
+    fp32 = _oracle_ms(False)
+    torch.cuda.empty_cache()
+    bf16 = _oracle_ms(True)
+    torch.cuda.empty_cache()
+    prod = _product_ms()
+    rec = {"workload": "train.py G(128,128)/D(128) step 5 (128px) alpha=0.5 batch 64, full iteration",
+           "oracle_cudnn_fp32_tf32": {"ms_per_step": round(fp32, 3), "img_per_s": round(B / fp32 * 1e3, 1)},
+           "oracle_cudnn_bf16_autocast": {"ms_per_step": round(bf16, 3),
+                                                         "img_per_s": round(B / bf16 * 1e3, 1)},
+           "product_bf16_tcgen05_graph": {"ms_per_step": round(prod, 3), "img_per_s": round(B / prod * 1e3, 1)},
+           "iters": ITERS, "warmup": WARM, "timing": "CUDA events"}
+    print(json.dumps(rec))
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, "gpu_reference_bar.json"), "w") as f:
+            json.dump(rec, f, indent=1)
+    assert prod < bf16 and prod < fp32, rec
