@@ -96,7 +96,10 @@ int pg_conv_wgrad_simt(const void *x, const void *dy, float *dw, int N, int H,
  * valid conv of D's last block (x viewed as [N,1,1,16*C]) and the 4x4
  * ConvTranspose of G's input layer (y viewed as [N,1,1,16*C]) run through this
  * form.  Same epilogues as the SIMT kernel; PixelNorm is taken over one N tile;
- * bias[c % bias_mod]; r_out:[N*H*W*n_tiles].                                  */
+ * bias[c % bias_mod]; r_out:[N*H*W*n_tiles].  Layers wider than 256 channels
+ * (512: the Correct* defaults) run with several N tiles of 256, bias_mod a
+ * multiple of Cout_tile (tile t adds bias[(t*Cout_tile + c) % bias_mod]) and a
+ * LINEAR/LRELU epilogue; their PixelNorm is pg_pn_lrelu_fwd.                   */
 int pg_conv_tc(const void *x, const void *wp, const float *bias, void *y,
                float *r_out, int N, int H, int W, int Cin, int Cout_total,
                int Cout_tile, int taps, int bias_mod, float scale, int epi,
@@ -118,6 +121,7 @@ int pg_conv_tc_actbwd(const void *x, const void *wp, void *da, int N, int H, int
                       float slope, int use_pn, float *colsum, void *stream);
 /* weight gradient on tcgen05: dw fp32 (logical dims Cin_log/Cout_log, parameter
  * layout by swap_io/flip) is overwritten; workspace is taps*Cin*Cout floats.
+ * Cout a multiple of 32 up to 256, or of 256 up to 1024 (dy tiles of 256 channels).
  * flat == 0: 3x3 pad 1 (taps == 9).  flat == 1: x is [N,1,1,taps*Cin] and tap t
  * addresses channel block t (weight gradient of the GEMM forms above).
  * accumulate == 1: dw += result (gradient accumulation straight into the flat bucket).
@@ -141,6 +145,11 @@ int pg_wgrad_unpack_multi(const PgUnpackEntry *table, int n, void *stream);
 
 /* ---- PixelNorm + LeakyReLU derivatives: progan_modules.py:54-60,138 ------
  * y is the stored post-activation, r the stored per-pixel rsqrt.            */
+/* stand-alone forward (PixelNorm.forward :58-60 + LeakyReLU :138) for layers wider than one
+ * conv N tile (more than 256 output channels): y = lrelu(a * r), r = rsqrt(mean_c a^2 + 1e-8)
+ * written to r[P] when use_pn (else r unused, y = lrelu(a)).  a and y may alias. */
+int pg_pn_lrelu_fwd(const void *a, void *y, float *r, long long P, int C, float slope, int use_pn,
+                    int dtype, void *stream);
 /* pool_h/pool_w != 0: dy is the gradient of the 2x2-average-pooled activation
  * ([N,H/2,W/2,C]); the x1/4 expansion (avgpool backward) is fused.  colsum (nullable, fp32
  * [C], zero-initialised) += per-channel sum of da = bias gradient of the conv in front.

@@ -17,19 +17,28 @@ ap.add_argument("--res", type=int, default=128)
 ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--alpha", type=float, default=0.5)
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--correct", type=int, default=0, help="channel width of CorrectGenerator/Discriminator "
+                "(step = log2(res) - 1) instead of train.py's models")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 step = {8: 1, 16: 2, 32: 3, 64: 4, 128: 5, 256: 6}[a.res]
 K = progan_b200.get_kernels()
 K.conv_impl, K.wgrad_tc = "tc", True
 torch.manual_seed(0)
-G = progan_b200.Generator(128, 128, tanh=False).to(dev)
-D = progan_b200.Discriminator(128).to(dev)
-Gr = progan_b200.Generator(128, 128, tanh=False).to(dev)
+zdim = 128
+if a.correct:
+    zdim, step = a.correct, step + 1
+    G = progan_b200.CorrectGenerator(zdim, a.correct).to(dev)
+    D = progan_b200.CorrectDiscriminator(a.correct).to(dev)
+    Gr = progan_b200.CorrectGenerator(zdim, a.correct).to(dev)
+else:
+    G = progan_b200.Generator(128, 128, tanh=False).to(dev)
+    D = progan_b200.Discriminator(128).to(dev)
+    Gr = progan_b200.Generator(128, 128, tanh=False).to(dev)
 tr = progan_b200.Trainer(G, D, Gr, use_graph=False)
 g = torch.Generator().manual_seed(1234)
 real = (torch.rand(a.batch, 3, a.res, a.res, generator=g) * 2 - 1).to(dev)
-z = torch.randn(a.batch, 128, generator=g).to(dev)
+z = torch.randn(a.batch, zdim, generator=g).to(dev)
 eps = torch.rand(a.batch, 1, 1, 1, generator=g).to(dev)
 for _ in range(2):
     tr.step(real, z, eps, step, a.alpha)

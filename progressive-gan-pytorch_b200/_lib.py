@@ -31,6 +31,7 @@ SIGNATURES = {
     "pg_conv_tc_actbwd": [P, P, P, c_int, c_int, c_int, c_int, c_int, c_float, P, P, c_float, c_int, P, P],
     "pg_conv_wgrad_tc": [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                          c_float, c_int, c_int, c_int, P],
+    "pg_pn_lrelu_fwd": [P, P, P, c_ll, c_int, c_float, c_int, c_int, P],
     "pg_pn_lrelu_bwd": [P, P, P, P, c_ll, c_int, c_float, c_int, c_int, c_int, P, P, c_int, P],
     "pg_pn_lrelu_bwd_bwd": [P, P, P, P, P, P, c_ll, c_int, c_float, c_int, c_int, c_int, c_int, P],
     "pg_colsum": [P, P, c_ll, c_int, c_int, P],

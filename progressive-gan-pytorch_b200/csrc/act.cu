@@ -321,8 +321,21 @@ colsum_kernel(const T *__restrict__ x, float *__restrict__ out, long long P, int
   const int cj = threadIdx.x % nch, rj = threadIdx.x / nch;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (rj < rows) {
-    for (long long pix = (long long)blockIdx.x * rows + rj; pix < P;
-         pix += (long long)gridDim.x * rows) {
+    using Raw = typename RawOf<T>::type;
+    const long long stride = (long long)gridDim.x * rows;
+    long long pix = (long long)blockIdx.x * rows + rj;
+    for (; pix + 3 * stride < P; pix += 4 * stride) {      // four independent loads in flight
+      Raw raw[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) raw[u] = ldraw8(x + (pix + u * stride) * C + (long long)cj * 8);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const F8 v = unpack8(raw[u]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += v.v[e];
+      }
+    }
+    for (; pix < P; pix += stride) {
       F8 v = ld8(x + pix * C + (long long)cj * 8);
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[e] += v.v[e];
@@ -350,6 +363,72 @@ static void pg_encode_pool(int *h, int *w) {
     *h |= lh << 16;
     *w |= lw << 16;
   }
+}
+
+// Stand-alone forward y = lrelu(a * rsqrt(mean_c a^2 + 1e-8)) with the per-pixel statistic r
+// written for the backward kernels: the activation of layers too wide for the conv epilogue
+// (more than 256 output channels = several N tiles).  One warp per pixel, MAXV 16-byte vectors
+// per lane kept in registers between the reduction and the store (C <= 256 * MAXV).
+template <typename T, int MAXV>
+__global__ void __launch_bounds__(256)
+pn_lrelu_fwd_kernel(const T *__restrict__ a, T *__restrict__ y, float *__restrict__ r, long long P,
+                    int C, float slope, int use_pn) {
+  using Raw = typename RawOf<T>::type;
+  const int lane = threadIdx.x & 31;
+  const int nch = C >> 3;
+  const long long wpb = blockDim.x >> 5;
+  for (long long pix = blockIdx.x * wpb + (threadIdx.x >> 5); pix < P; pix += gridDim.x * wpb) {
+    Raw raw[MAXV];
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int ch = lane + i * 32;
+      if (ch < nch) raw[i] = ldraw8(a + pix * C + (long long)ch * 8);
+    }
+    F8 v[MAXV];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      if (lane + i * 32 < nch) {
+        v[i] = unpack8(raw[i]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) ss = fmaf(v[i].v[e], v[i].v[e], ss);
+      }
+    }
+    float rs = 1.f;
+    if (use_pn) {
+      rs = rsqrtf(warp_sum(ss) / (float)C + 1e-8f);
+      if (lane == 0) r[pix] = rs;
+    }
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int ch = lane + i * 32;
+      if (ch < nch) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float pv = v[i].v[e] * rs;
+          v[i].v[e] = pv > 0.f ? pv : pv * slope;
+        }
+        st8(y + pix * C + (long long)ch * 8, v[i]);
+      }
+    }
+  }
+}
+
+extern "C" int pg_pn_lrelu_fwd(const void *a, void *y, float *r, long long P, int C, float slope,
+                               int use_pn, int dtype, void *stream) {
+  PG_CHECK_ARG(a && y && (r || !use_pn), "pg_pn_lrelu_fwd: null pointer");
+  PG_CHECK_ARG(P > 0 && C > 0 && C % 8 == 0 && C <= 1024, "pg_pn_lrelu_fwd: need C %% 8 == 0, C <= 1024 (C=%d)", C);
+  const long long want = (P + 7) / 8;
+  const int grid = (int)(want < 148 * 8 ? want : 148 * 8);
+  PG_DISPATCH_DTYPE(dtype, T, {
+    if (C <= 256)
+      pn_lrelu_fwd_kernel<T, 1><<<grid, 256, 0, (cudaStream_t)stream>>>((const T *)a, (T *)y, r, P, C, slope, use_pn);
+    else if (C <= 512)
+      pn_lrelu_fwd_kernel<T, 2><<<grid, 256, 0, (cudaStream_t)stream>>>((const T *)a, (T *)y, r, P, C, slope, use_pn);
+    else
+      pn_lrelu_fwd_kernel<T, 4><<<grid, 256, 0, (cudaStream_t)stream>>>((const T *)a, (T *)y, r, P, C, slope, use_pn);
+  });
+  PG_CHECK_LAUNCH("pg_pn_lrelu_fwd");
 }
 
 extern "C" int pg_pn_lrelu_bwd(const void *dy, const void *y, const float *r, void *da,

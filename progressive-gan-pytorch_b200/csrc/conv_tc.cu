@@ -83,6 +83,7 @@ struct ConvTcParams {
   float scale, slope;
   const float *bias;
   int bias_mod;              // bias[c % bias_mod]
+  int bias_per_tile;         // N tile nt uses bias[(nt * Cout + c) % bias_mod] (bias_mod > Cout)
   float *r_out;
 };
 
@@ -240,6 +241,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       const int th = (pt / p.tiles_w) % p.tiles_h;
       const int tn = pt / (p.tiles_w * p.tiles_h);
       const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
+      if (p.bias_per_tile) {      // wide outputs: every N tile has its own slice of the bias
+        asm volatile("bar.sync 1, 128;" ::: "memory");     // previous tile's reads are done
+        for (int c = et; c < p.Cout; c += 128) bias_ptr[c] = p.bias[(nt * p.Cout + c) % p.bias_mod];
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_addr =
@@ -348,9 +354,14 @@ extern "C" int pg_conv_tc(const void *x, const void *wp, const float *bias, void
   PG_CHECK_ARG(Cout_total % Cout == 0, "pg_conv_tc: Cout_total %d not a multiple of the tile %d",
                Cout_total, Cout);
   const int n_tiles = Cout_total / Cout;
-  PG_CHECK_ARG(!bias || (bias_mod > 0 && (n_tiles == 1 ? bias_mod == Cout : Cout % bias_mod == 0)),
+  const bool bias_per_tile = bias && n_tiles > 1 && bias_mod > Cout && bias_mod % Cout == 0;
+  PG_CHECK_ARG(!bias || bias_per_tile ||
+                   (bias_mod > 0 && (n_tiles == 1 ? bias_mod == Cout : Cout % bias_mod == 0)),
                "pg_conv_tc: bias_mod %d incompatible with the N tiling", bias_mod);
   PG_CHECK_ARG(epi != PG_EPI_PN_LRELU || r_out, "pg_conv_tc: PN epilogue needs r_out");
+  PG_CHECK_ARG(epi != PG_EPI_PN_LRELU || n_tiles == 1 || (taps == 1 && !bias_per_tile),
+               "pg_conv_tc: PixelNorm over more channels than one N tile (<= 256): use "
+               "PG_EPI_LINEAR + pg_pn_lrelu_fwd (Cout_total %d, tile %d)", Cout_total, Cout);
   PG_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)wp & 15) == 0 && ((uintptr_t)y & 15) == 0,
                "pg_conv_tc: pointers must be 16-byte aligned");
   if (taps == 9 && n_tiles == 1) {   // newer kernel generations where the shape allows
@@ -389,6 +400,7 @@ extern "C" int pg_conv_tc(const void *x, const void *wp, const float *bias, void
   p.tmem_cols = pow2_ge(2 * Cout);
   p.epi = epi; p.scale = scale; p.slope = slope; p.bias = bias; p.bias_mod = bias_mod > 0 ? bias_mod : 1;
   p.r_out = r_out;
+  p.bias_per_tile = bias_per_tile ? 1 : 0;
   const int out_bytes = 128 * Cout * 2;
   const int misc = 1024 /*align slack*/ + 8 * (2 * 8 + 4) + 16 + Cout * 4 + 64;
   const int budget = 227 * 1024;

@@ -86,7 +86,10 @@ pw_expand_kernel(const float *__restrict__ img, const float *__restrict__ w,
   }
 }
 
-template <typename T, int TPP, typename I>
+// CPL = 16-byte chunks per lane (C <= 8*TPP*CPL): chunk 0 multiplies weights held in registers,
+// further chunks (C > 256) read theirs from shared memory; every load of the UN pixels is
+// issued before the arithmetic.
+template <typename T, int TPP, typename I, int CPL>
 __global__ void __launch_bounds__(256)
 pw_reduce_kernel(const T *__restrict__ act, const float *__restrict__ w,
                  const float *__restrict__ bias, float *__restrict__ img, int N, I HW,
@@ -112,12 +115,15 @@ pw_reduce_kernel(const T *__restrict__ act, const float *__restrict__ w,
     for (int e = 0; e < 8; ++e) wr[k][e] = (k < K && sub < nch) ? sw[k * C + sub * 8 + e] : 0.f;
   for (I pix0 = (I)blockIdx.x * ppb + (I)(threadIdx.x / TPP); pix0 < Pr; pix0 += pstride * UN) {
     float acc[UN][kMaxK];
-    typename RawOf<T>::type raw[UN];
-    const bool one = nch <= TPP;              // the usual case: one 16-byte chunk per lane
+    typename RawOf<T>::type raw[UN][CPL];
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
       const I pix = pix0 + (I)u * pstride;
-      if (one && pix < P && sub < nch) raw[u] = ldraw8(act + (long long)pix * C + (long long)sub * 8);
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) {
+        const int ch = sub + i * TPP;
+        if (pix < P && ch < nch) raw[u][i] = ldraw8(act + (long long)pix * C + (long long)ch * 8);
+      }
     }
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
@@ -125,23 +131,29 @@ pw_reduce_kernel(const T *__restrict__ act, const float *__restrict__ w,
 #pragma unroll
       for (int k = 0; k < kMaxK; ++k) acc[u][k] = 0.f;
       if (pix < P) {
-        if (one) {
-          if (sub < nch) {
-            const F8 v = unpack8(raw[u]);
 #pragma unroll
-            for (int e = 0; e < 8; ++e)
+        for (int i = 0; i < CPL; ++i) {
+          const int ch = sub + i * TPP;
+          if (ch < nch) {
+            const F8 v = unpack8(raw[u][i]);
+            if (i == 0) {
 #pragma unroll
-              for (int k = 0; k < kMaxK; ++k) acc[u][k] = fmaf(v.v[e], wr[k][e], acc[u][k]);
-          }
-        } else {
-          for (int ch = sub; ch < nch; ch += TPP) {
-            F8 v = ld8(act + (long long)pix * C + (long long)ch * 8);
+              for (int e = 0; e < 8; ++e)
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int c = ch * 8 + e;
+                for (int k = 0; k < kMaxK; ++k) acc[u][k] = fmaf(v.v[e], wr[k][e], acc[u][k]);
+            } else {
 #pragma unroll
               for (int k = 0; k < kMaxK; ++k)
-                if (k < K) acc[u][k] = fmaf(v.v[e], sw[k * C + c], acc[u][k]);
+                if (k < K) {
+                  const float4 w0 = *reinterpret_cast<const float4 *>(sw + k * C + ch * 8);
+                  const float4 w1 = *reinterpret_cast<const float4 *>(sw + k * C + ch * 8 + 4);
+                  float a_ = acc[u][k];
+                  a_ = fmaf(v.v[0], w0.x, a_); a_ = fmaf(v.v[1], w0.y, a_);
+                  a_ = fmaf(v.v[2], w0.z, a_); a_ = fmaf(v.v[3], w0.w, a_);
+                  a_ = fmaf(v.v[4], w1.x, a_); a_ = fmaf(v.v[5], w1.y, a_);
+                  a_ = fmaf(v.v[6], w1.z, a_); a_ = fmaf(v.v[7], w1.w, a_);
+                  acc[u][k] = a_;
+                }
             }
           }
         }
@@ -286,21 +298,24 @@ extern "C" int pg_pw_reduce(const void *act, const float *w, const float *bias, 
   const size_t smem = (size_t)K * C * sizeof(float);
   const long long P = (long long)N * HW;
   cudaStream_t s = (cudaStream_t)stream;
-#define PG_LAUNCH_PWR(TPP)                                                                  \
+#define PG_LAUNCH_PWR(TPP, CPL)                                                             \
   {                                                                                         \
     const int grid = bw_grid(P, 256 / TPP);                                                 \
     if (P + (long long)grid * 256 < (1ll << 31))                                            \
-      pw_reduce_kernel<T, TPP, unsigned><<<grid, 256, smem, s>>>(                           \
+      pw_reduce_kernel<T, TPP, unsigned, CPL><<<grid, 256, smem, s>>>(                      \
           (const T *)act, w, bias, img, N, (unsigned)HW, K, C, w_sc, w_sk, scale);          \
     else                                                                                    \
-      pw_reduce_kernel<T, TPP, long long><<<grid, 256, smem, s>>>(                          \
+      pw_reduce_kernel<T, TPP, long long, CPL><<<grid, 256, smem, s>>>(                     \
           (const T *)act, w, bias, img, N, HW, K, C, w_sc, w_sk, scale);                    \
   }
   PG_DISPATCH_DTYPE(dtype, T, {
-    if (nch <= 4) PG_LAUNCH_PWR(4)
-    else if (nch <= 8) PG_LAUNCH_PWR(8)
-    else if (nch <= 16) PG_LAUNCH_PWR(16)
-    else PG_LAUNCH_PWR(32)
+    if (nch <= 4) PG_LAUNCH_PWR(4, 1)
+    else if (nch <= 8) PG_LAUNCH_PWR(8, 1)
+    else if (nch <= 16) PG_LAUNCH_PWR(16, 1)
+    else if (nch <= 32) PG_LAUNCH_PWR(32, 1)
+    else if (nch <= 64) PG_LAUNCH_PWR(32, 2)
+    else if (nch <= 128) PG_LAUNCH_PWR(32, 4)
+    else PG_LAUNCH_PWR(32, 8)
   });
 #undef PG_LAUNCH_PWR
   PG_CHECK_LAUNCH("pg_pw_reduce");

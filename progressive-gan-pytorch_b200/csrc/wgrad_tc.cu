@@ -23,7 +23,8 @@ namespace pg {
 namespace tc {
 
 struct WgradTcParams {
-  int N, H, W, Cin, Cout;      // physical channel counts of x (per tap) and dy
+  int N, H, W, Cin, Cout;      // physical channel counts of x (per tap) and of ONE dy tile (<= 256)
+  int Cout_total;              // channels of dy; blockIdx.z = dy tile (wide layers: 512 = 2 x 256)
   int taps, flat;              // flat: taps address channel blocks of x ([N,1,1,taps*Cin]), no shift
   int group_stride;            // TMEM columns reserved per tap group (>= Cout)
   int bw, bh, bn, tiles_w, tiles_h, num_tiles;
@@ -60,6 +61,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pass = blockIdx.y;
+  const int co_off = (int)blockIdx.z * p.Cout;
   const int g0 = pass * p.gpp;
   const int g1 = min(g0 + p.gpp, p.total_groups);
   const int ngroups = g1 - g0;
@@ -101,7 +103,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         mbar_expect_tx(dyfull(ds), dy_bytes);
         for (int a = 0; a < p.n_atoms_n; ++a)
           tma_load_4d(smem_dy0 + (uint32_t)ds * dy_bytes + (uint32_t)(a * p.atom_n_bytes), &tmap_dy,
-                      dyfull(ds), a * p.atomN, w0, h0, n0);
+                      dyfull(ds), co_off + a * p.atomN, w0, h0, n0);
         if (++ds == 2) {
           ds = 0;
           dphase ^= 1u;
@@ -199,7 +201,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           tmem_ld32(t_addr + (uint32_t)c0, v);   // warp-collective: all lanes participate
           tmem_ld_wait();
           if (tap < p.taps) {
-            float *dst = p.dwp + ((size_t)tap * p.Cout + c0) * p.Cin + ci;
+            float *dst = p.dwp + ((size_t)tap * p.Cout_total + co_off + c0) * p.Cin + ci;
 #pragma unroll
             for (int j = 0; j < 32; ++j) atomicAdd(dst + (size_t)j * p.Cin, __uint_as_float(v[j]));
           }
@@ -266,7 +268,11 @@ using namespace pg;
 
 extern "C" int pg_wgrad_unpack_multi(const PgUnpackEntry *table, int n, void *stream) {
   PG_CHECK_ARG(table && n > 0 && n <= 65535, "pg_wgrad_unpack_multi: bad table");
-  dim3 grid(64, (unsigned)n);
+  // the kernel is grid-stride per entry: ~16 blocks per SM over all entries, at least 64 per entry
+  // (entries range from 9 K floats to 2.4 M for a 512 x 512 layer)
+  int gx = 16 * sm_count() / n;
+  if (gx < 64) gx = 64;
+  dim3 grid((unsigned)gx, (unsigned)n);
   tc::wgrad_unpack_multi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(table);
   PG_CHECK_LAUNCH("pg_wgrad_unpack_multi");
 }
@@ -286,15 +292,20 @@ extern "C" int pg_conv_wgrad_tc(const void *x, const void *dy, float *dw, float 
   PG_CHECK_ARG(N > 0 && H > 0 && W > 0, "pg_conv_wgrad_tc: bad dims");
   PG_CHECK_ARG(!flat || (H == 1 && W == 1), "pg_conv_wgrad_tc: flat mode needs H == W == 1");
   PG_CHECK_ARG(Cin % 32 == 0 && Cin >= 32, "pg_conv_wgrad_tc: Cin %% 32 != 0 (%d)", Cin);
-  PG_CHECK_ARG(Cout % 32 == 0 && Cout >= 32 && Cout <= 256,
-               "pg_conv_wgrad_tc: Cout must be a multiple of 32 in [32,256] (%d)", Cout);
-  PG_CHECK_ARG(Cin_log <= Cin && Cout_log <= Cout && Cin_log > 0 && Cout_log > 0,
+  PG_CHECK_ARG(Cout % 32 == 0 && Cout >= 32 && (Cout <= 256 || (Cout % 256 == 0 && Cout <= 1024)),
+               "pg_conv_wgrad_tc: Cout must be a multiple of 32 in [32,256] or of 256 up to 1024 (%d)",
+               Cout);
+  const int Cout_total = Cout;
+  if (Cout > 256) Cout = 256;            // dy tiles of 256 channels over blockIdx.z
+  const int co_tiles = Cout_total / Cout;
+  PG_CHECK_ARG(Cin_log <= Cin && Cout_log <= Cout_total && Cin_log > 0 && Cout_log > 0,
                "pg_conv_wgrad_tc: logical dims exceed physical dims");
   PG_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)dy & 15) == 0,
                "pg_conv_wgrad_tc: pointers must be 16-byte aligned");
   cudaStream_t s = (cudaStream_t)stream;
   tc::WgradTcParams p;
   p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.taps = taps; p.flat = flat;
+  p.Cout_total = Cout_total;
   p.bw = W < 16 ? W : 16;
   {
     int rem = 128 / p.bw;
@@ -340,8 +351,9 @@ extern "C" int pg_conv_wgrad_tc(const void *x, const void *dy, float *dw, float 
     if (int rc = make_tmap_bf16(&tx, x, 4, dims, str, box, p.atomM * 2, "pg_conv_wgrad_tc(x)")) return rc;
   }
   {
-    uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-    uint64_t str[3] = {(uint64_t)Cout * 2, (uint64_t)W * Cout * 2, (uint64_t)H * W * Cout * 2};
+    uint64_t dims[4] = {(uint64_t)Cout_total, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    uint64_t str[3] = {(uint64_t)Cout_total * 2, (uint64_t)W * Cout_total * 2,
+                       (uint64_t)H * W * Cout_total * 2};
     uint32_t box[4] = {(uint32_t)p.atomN, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
     if (int rc = make_tmap_bf16(&tdy, dy, 4, dims, str, box, p.atomN * 2, "pg_conv_wgrad_tc(dy)")) return rc;
   }
@@ -357,28 +369,28 @@ extern "C" int pg_conv_wgrad_tc(const void *x, const void *dy, float *dw, float 
   }
   const bool deferred = accumulate == 2;
   if (!deferred) {
-    cudaError_t e = cudaMemsetAsync(workspace, 0, (size_t)taps * Cin * Cout * sizeof(float), s);
+    cudaError_t e = cudaMemsetAsync(workspace, 0, (size_t)taps * Cin * Cout_total * sizeof(float), s);
     if (e != cudaSuccess) {
       set_error("pg_conv_wgrad_tc: cudaMemsetAsync: %s", cudaGetErrorString(e));
       return PG_ERR_CUDA;
     }
   }
   int rc2 = PG_ERR_UNSUPPORTED;
-  if (!flat && taps == 9) {  // newer kernel generations where the shape allows
+  if (!flat && taps == 9 && co_tiles == 1) {  // newer kernel generations where the shape allows
     rc2 = wgrad4_tc_launch(x, dy, workspace, N, H, W, Cin, Cout, s);
     if (rc2 == PG_ERR_UNSUPPORTED) rc2 = wgrad3_tc_launch(x, dy, workspace, N, H, W, Cin, Cout, s);
   }
   if (rc2 != PG_OK && rc2 != PG_ERR_UNSUPPORTED) return rc2;
   if (rc2 == PG_ERR_UNSUPPORTED) {
-    int gx = sm_count() / passes;
+    int gx = sm_count() / (passes * co_tiles);
     if (gx > p.num_tiles) gx = p.num_tiles;
     if (gx < 1) gx = 1;
-    dim3 grid(gx, passes);
+    dim3 grid(gx, passes, co_tiles);
     tc::wgrad_tc_kernel<<<grid, tc::kWgThreads, smem, s>>>(tx, tdy, p);
   }
   const int total = taps * Cin_log * Cout_log;
   if (!deferred)
   tc::wgrad_unpack_kernel<<<(total + 255) / 256, 256, 0, s>>>(workspace, dw, Cin_log, Cout_log, Cin,
-                                                             Cout, taps, scale, swap_io, flip, accumulate);
+                                                             Cout_total, taps, scale, swap_io, flip, accumulate);
   PG_CHECK_LAUNCH("pg_conv_wgrad_tc");
 }

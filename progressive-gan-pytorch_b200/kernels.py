@@ -100,6 +100,7 @@ class CudaKernels:
         self.lib = _lib.load()
         self.conv_impl = "tc"          # "tc": tcgen05 where the shape allows; "simt": always CUDA cores
         self.wgrad_tc = True           # tcgen05 weight-gradient kernels (False: CUDA-core wgrad)
+        self.wide_tc = True            # 3x3 convs with 512/768/1024 output channels on tcgen05 (N tiles of 256)
         self.launches = 0              # kernels launched through this shim (bench `gpu_launches`)
         self._packs = {}               # id(param) -> [weakref, version, {variant: (tensor, pack args)}]
         self._pack_tables = {}         # ids of a parameter set -> (signature, device table, n)
@@ -135,13 +136,16 @@ class CudaKernels:
         cin, cout = op.cin_phys(wshape), op.cout_phys(wshape)
         if cin % 32 or cout % 32:
             return None
-        if op.k == 3 and op.pad == 1 and cout <= 256:
+        def fits(c):            # above 256 channels: N tiles of 256, PixelNorm as its own kernel
+            return c <= 256 or (self.wide_tc and c % 256 == 0 and c <= 1024)
+
+        if op.k == 3 and op.pad == 1 and fits(cout):
             return "conv3"
         if op.xpad or op.ypad:
             return None
-        if op.pad == 0 and H == op.k and W == op.k and cout <= 256:
+        if op.pad == 0 and H == op.k and W == op.k and fits(cout):
             return "valid"
-        if op.pad == op.k - 1 and H == 1 and W == 1 and cout <= 256 and cin <= 256:
+        if op.pad == op.k - 1 and H == 1 and W == 1 and fits(cout) and fits(cin):
             return "full"
         return None
 
@@ -247,16 +251,33 @@ class CudaKernels:
             wp = self.packed(w, op, WL_CO_TAP_CI, torch.bfloat16)
             if pool_out and H % 16 == 0 and W % 8 == 0 and cout in (32, 64, 128) and not (op.xpad or op.ypad):
                 yp = torch.empty((N, H // 2, W // 2, cout), device=x.device, dtype=x.dtype)
-            self._call("pg_conv_tc", x.data_ptr(), wp.data_ptr(), _ptr(bias), y.data_ptr(), _ptr(r),
-                       N, H, W, cin, cout, cout, 9, nb, float(scale), epi, float(slope), _ptr(yp), st)
-        elif mode == "valid":      # [N, k*k*cin] x [cout, k*k*cin]^T
-            wp = self.packed(w, op, WL_CO_TAP_CI, torch.bfloat16)
-            self._call("pg_conv_tc", x.data_ptr(), wp.data_ptr(), _ptr(bias), y.data_ptr(), _ptr(r),
-                       N, 1, 1, k * k * cin, cout, cout, 1, nb, float(scale), epi, float(slope), None, st)
-        elif mode == "full":       # [N, cin] x [(pos, cout), cin]^T ; output position = flipped tap
-            wp = self.packed(w, op, WL_TAP_CO_CI, torch.bfloat16, flip=not op.flip)
-            self._call("pg_conv_tc", x.data_ptr(), wp.data_ptr(), _ptr(bias), y.data_ptr(), _ptr(r),
-                       N, 1, 1, cin, k * k * cout, cout, 1, nb, float(scale), epi, float(slope), None, st)
+            if cout > 256:
+                # wide layer (the Correct* defaults of 512): one pixel's channel vector spans several
+                # N tiles, so the conv writes the pre-activation and PixelNorm runs stand-alone
+                conv_epi = epi if epi != EPI_PN_LRELU else EPI_LINEAR
+                self._call("pg_conv_tc", x.data_ptr(), wp.data_ptr(), _ptr(bias), y.data_ptr(), None,
+                           N, H, W, cin, cout, 256, 9, nb, float(scale), conv_epi, float(slope), None, st)
+                if epi == EPI_PN_LRELU:
+                    self.pn_lrelu_fwd(y, slope, True, out=y, r=r)
+            else:
+                self._call("pg_conv_tc", x.data_ptr(), wp.data_ptr(), _ptr(bias), y.data_ptr(), _ptr(r),
+                           N, H, W, cin, cout, cout, 9, nb, float(scale), epi, float(slope), _ptr(yp), st)
+        elif mode in ("valid", "full"):
+            wide = cout > 256
+            conv_epi = EPI_LINEAR if (wide and epi == EPI_PN_LRELU) else epi
+            tile = 256 if wide else cout
+            if mode == "valid":    # [N, k*k*cin] x [cout, k*k*cin]^T
+                wp = self.packed(w, op, WL_CO_TAP_CI, torch.bfloat16)
+                self._call("pg_conv_tc", x.data_ptr(), wp.data_ptr(), _ptr(bias), y.data_ptr(),
+                           None if wide else _ptr(r), N, 1, 1, k * k * cin, cout, tile, 1, nb, float(scale),
+                           conv_epi, float(slope), None, st)
+            else:                  # [N, cin] x [(pos, cout), cin]^T ; output position = flipped tap
+                wp = self.packed(w, op, WL_TAP_CO_CI, torch.bfloat16, flip=not op.flip)
+                self._call("pg_conv_tc", x.data_ptr(), wp.data_ptr(), _ptr(bias), y.data_ptr(),
+                           None if wide else _ptr(r), N, 1, 1, cin, k * k * cout, tile, 1, nb, float(scale),
+                           conv_epi, float(slope), None, st)
+            if wide and epi == EPI_PN_LRELU:
+                self.pn_lrelu_fwd(y, slope, True, out=y, r=r)
         else:
             wp = self.packed(w, op, WL_TAP_CI_CO, x.dtype)
             self._call("pg_conv_fwd_simt", x.data_ptr(), wp.data_ptr(), _ptr(bias), y.data_ptr(),
@@ -422,11 +443,27 @@ class CudaKernels:
     def mbstd_channels(self, C, dtype):
         """Physical channel count of the minibatch-stddev output (C real + 1 statistic):
         padded to a multiple of 32 on the tensor-core path."""
-        if self.conv_impl == "tc" and dtype == torch.bfloat16 and C % 32 == 0 and C <= 256:
-            return ((C + 1 + 31) // 32) * 32
+        if self.conv_impl == "tc" and dtype == torch.bfloat16 and C % 32 == 0:
+            Cp = ((C + 1 + 31) // 32) * 32
+            if Cp <= 256:
+                return Cp
+            if self.wide_tc and C <= 768:      # wide layers tile the channels in blocks of 256
+                return ((C + 1 + 255) // 256) * 256
         return C + 1
 
     # ------------------------------------------------- PixelNorm + LeakyReLU
+    def pn_lrelu_fwd(self, a, slope, use_pn, out=None, r=None):
+        """(y, r): y = lrelu(a * r), r = rsqrt(mean_c a^2 + 1e-8) per pixel (None without PixelNorm).
+        The stand-alone form for layers too wide for the conv epilogue; out may alias a."""
+        _chk(a, "a", ndim=4)
+        C = a.shape[-1]
+        y = out if out is not None else torch.empty_like(a)
+        if use_pn and r is None:
+            r = torch.empty(a.shape[:-1], device=a.device, dtype=torch.float32)
+        self._call("pg_pn_lrelu_fwd", a.data_ptr(), y.data_ptr(), _ptr(r) if use_pn else None,
+                   a.numel() // C, C, float(slope), int(use_pn), _dt(a), self._stream())
+        return y, (r if use_pn else None)
+
     def pn_lrelu_bwd(self, dy, y, r, slope, use_pn, pool=False, want_colsum=False, colsum_out=None,
                      addend=None):
         """da = Jpn(a)^T (m*dy) [+ addend].  pool: dy is the gradient of avgpool2(y).  Returns

@@ -151,3 +151,43 @@ def test_trainer_generic_families_cuda(name):
         res.append(tr)
     assert helpers.rel(res[1].bD.p, res[0].bD.p) < 1e-5
     assert helpers.rel(res[1].bG.p, res[0].bG.p) < 1e-5
+
+
+@pytest.mark.gpu
+def test_wide_correct_models_tcgen05_vs_cuda_core():
+    """The Correct* defaults (512 channels, BASELINE configs 2/3/5): 3x3 convs wider than one
+    256-column N tile run as several N tiles with the stand-alone PixelNorm kernel, weight
+    gradients over dy tiles of 256 channels.  Same bf16 precision on the CUDA-core kernels is the
+    checker (only accumulation order and one extra bf16 rounding of the pre-activation differ)."""
+    K = progan_b200.get_kernels()
+    dev = "cuda"
+    g = torch.Generator().manual_seed(5)
+    B, step, alpha = 4, 3, 0.5
+    real = (torch.rand(B, 3, 16, 16, generator=g) * 2 - 1).to(dev)
+    z = torch.randn(B, 512, generator=g).to(dev)
+    eps = torch.rand(B, 1, 1, 1, generator=g).to(dev)
+    res = {}
+    try:
+        for wide in (False, True):
+            K.conv_impl, K.wgrad_tc, K.wide_tc = "tc", True, wide
+            K.invalidate_packs()
+            torch.manual_seed(0)
+            G = progan_b200.CorrectGenerator(512, 512, precision="bf16").to(dev)
+            D = progan_b200.CorrectDiscriminator(512, precision="bf16").to(dev)
+            K.launches = 0
+            r, fake = helpers.product_train_step(G, D, real, z, eps, step, alpha)
+            loss, g_grads = helpers.product_g_phase(G, D, fake, step, alpha)
+            torch.cuda.synchronize()
+            res[wide] = (r, g_grads)
+    finally:
+        K.wide_tc = True
+    (a, ga), (b, gb) = res[False], res[True]
+    assert helpers.rel(b["fake"], a["fake"]) < 1e-2
+    for k in ("real_predict", "hat_predict"):
+        assert float((b[k] - a[k]).abs().max()) <= 2e-2 * float(a[k].abs().max()) + 2e-2, k
+    assert helpers.rel(b["grad_x_hat"], a["grad_x_hat"]) < 0.3
+    assert abs(float(b["grad_penalty"]) - float(a["grad_penalty"])) <= 0.2 * float(a["grad_penalty"]) + 0.1
+    for k in a["d_grads"]:
+        assert helpers.rel(b["d_grads"][k], a["d_grads"][k]) < 0.3, k
+    for k in ga:
+        assert helpers.rel(gb[k], ga[k]) < 0.3, k
