@@ -49,12 +49,13 @@ if __name__ == "__main__":
     ap.add_argument("--step", type=int, default=4)
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--simt-iters", type=int, default=2)
+    ap.add_argument("--no-graph", action="store_true", help="eager launches (for an ncu launch list)")
     a = ap.parse_args()
     # 14 F_D + 3 F_G conv FLOPs per image (217.1 GFLOP/img at ch = 512, 32 px)
     gflop = {4: 217.1}.get(a.step)
     out = {"workload": "CorrectGenerator(512,512)/CorrectDiscriminator(512) step %d batch %d alpha 0.5"
                        % (a.step, a.batch)}
-    ms, m = run(True, a.batch, a.step, a.iters, True)
+    ms, m = run(True, a.batch, a.step, a.iters, not a.no_graph)
     out["tcgen05_wide"] = {"ms_per_step": round(ms, 2), "img_per_s": round(a.batch / ms * 1e3, 1), "metrics": m}
     if gflop:
         out["tcgen05_wide"]["tflops"] = round(a.batch * gflop / ms, 1)

@@ -246,16 +246,64 @@ wgrad_unpack_multi_kernel(const PgUnpackEntry *__restrict__ table) {
   const PgUnpackEntry e = table[blockIdx.y];
   const int total_p = e.Cin_p * e.Cout_p * e.taps;
   const int d1 = e.swap_io ? e.Cout : e.Cin;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total_p; i += gridDim.x * blockDim.x) {
+  float *__restrict__ ws = e.ws;
+  float *__restrict__ dw = e.dw;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+  if ((e.Cin_p & 3) == 0) {
+    // four consecutive ci per thread and two such groups in flight: 16-byte workspace accesses,
+    // the eight gradient loads issued before the eight stores (the scalar form is latency-bound:
+    // one 4-byte load in flight per thread)
+    const int total4 = total_p >> 2;
+    for (int i4 = tid; i4 < total4; i4 += 2 * nthr) {
+      float4 v[2];
+      float *dst[2][4];
+      float old[2][4];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int j4 = i4 + u * nthr;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j4 < total4) {
+          v[u] = reinterpret_cast<const float4 *>(ws)[j4];
+          reinterpret_cast<float4 *>(ws)[j4] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        const int i = j4 << 2;
+        const int ci = i % e.Cin_p;
+        const int co = (i / e.Cin_p) % e.Cout_p;
+        const int tap = i / (e.Cin_p * e.Cout_p);
+        const int st = e.flip ? (e.taps - 1 - tap) : tap;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          dst[u][j] = nullptr;
+          if (j4 < total4 && co < e.Cout && ci + j < e.Cin) {
+            const int i0 = e.swap_io ? ci + j : co, i1 = e.swap_io ? co : ci + j;
+            dst[u][j] = dw + ((size_t)i0 * d1 + i1) * e.taps + st;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) old[u][j] = dst[u][j] ? *dst[u][j] : 0.f;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const float vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (dst[u][j]) *dst[u][j] = fmaf(e.scale, vv[j], old[u][j]);
+      }
+    }
+    return;
+  }
+  for (int i = tid; i < total_p; i += nthr) {
     const int ci = i % e.Cin_p;
     const int co = (i / e.Cin_p) % e.Cout_p;
     const int tap = i / (e.Cin_p * e.Cout_p);
-    const float v = e.ws[i];
-    e.ws[i] = 0.f;
+    const float v = ws[i];
+    ws[i] = 0.f;
     if (ci < e.Cin && co < e.Cout) {
       const int st = e.flip ? (e.taps - 1 - tap) : tap;
       const int i0 = e.swap_io ? ci : co, i1 = e.swap_io ? co : ci;
-      float *dst = e.dw + ((size_t)i0 * d1 + i1) * e.taps + st;
+      float *dst = dw + ((size_t)i0 * d1 + i1) * e.taps + st;
       *dst += e.scale * v;
     }
   }
