@@ -206,6 +206,12 @@ class Trainer:
         self.use_graph = use_graph
         # multi-GPU: three graphs per iteration with the NCCL all-reduces between the replays
         self.segment_graphs = (self.world > 1) if segment_graphs is None else bool(segment_graphs)
+        if use_graph and self.world > 1 and not self.segment_graphs:
+            # tried on 2 x B200 (NCCL 2.28): with both all-reduces captured inside ONE graph next to
+            # the concurrent side-stream chains the run never completed; the collectives stay
+            # between three segment graphs
+            raise RuntimeError("progan_b200.Trainer: segment_graphs=False is not supported with "
+                               "world_size > 1 (all-reduces captured inside one CUDA graph hang)")
         from .progan_modules import Discriminator as _BaseD, Generator as _BaseG
         # train.py's own models get the hand-ordered buckets (live set = two contiguous ranges);
         # every other mirrored family a generic layout + a probe pass for the live set
