@@ -12,7 +12,7 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, name):
     for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golden")):
         sys.path.insert(0, p)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -23,25 +23,29 @@ def _worker(rank, world, port, out_dir):
     import progan_b200
     from emul_kernels import EmulKernels
     progan_b200.set_kernels(EmulKernels())
-    inp = common.make_inputs("s2_a0.5")
+    inp = common.make_inputs(name)
     g = torch.Generator().manual_seed(1234 + rank)          # per-rank shard
-    real = torch.rand(4, 3, 16, 16, generator=g) * 2 - 1
-    z = torch.randn(4, inp["z_dim"], generator=g)
-    eps = torch.rand(4, 1, 1, 1, generator=g)
-    G, D = helpers.build_models(inp, "fp32")
-    Gr, _ = helpers.build_models(inp, "fp32")
+    real = torch.rand(inp["real"].shape, generator=g) * 2 - 1
+    z = torch.randn(inp["z"].shape, generator=g)
+    eps = torch.rand(inp["eps"].shape, generator=g)
+    label = torch.randint(0, inp["num_classes"], inp["label"].shape, generator=g) if inp["num_classes"] else None
+    G, D = helpers.build_models(inp, "fp32", name=name)
+    Gr, _ = helpers.build_models(inp, "fp32", name=name)
     tr = progan_b200.Trainer(G, D, Gr)
     assert tr.world == world
-    tr.step(real, z, eps, 2, 0.5)
+    tr.step(real, z, eps, inp["step"], inp["alpha"], label=label)
     torch.save(dict(pD=tr.bD.p.clone(), pG=tr.bG.p.clone(), gD=tr.bD.g.clone(), gG=tr.bG.g.clone(),
-                    pR=tr.bR.p.clone(), real=real, z=z, eps=eps),
+                    pR=tr.bR.p.clone(), real=real, z=z, eps=eps, label=label),
                os.path.join(out_dir, "rank%d.pt" % rank))
     dist.destroy_process_group()
 
 
-def test_two_rank_data_parallel_step(tmp_path):
+@pytest.mark.parametrize("name", ["s2_a0.5", "k2_a0.5_eq", "p2_a0.5"])
+def test_two_rank_data_parallel_step(tmp_path, name):
+    """train.py's models (hand-ordered buckets), a class-conditional family (label plane, generic
+    buckets) and a projection critic, each rank with its own images, latents and labels."""
     port = 29500 + (os.getpid() % 2000)
-    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, str(tmp_path), name), nprocs=2, join=True)
     r0 = torch.load(tmp_path / "rank0.pt")
     r1 = torch.load(tmp_path / "rank1.pt")
     # replicas identical after the step
@@ -55,16 +59,17 @@ def test_two_rank_data_parallel_step(tmp_path):
     from emul_kernels import EmulKernels
     prev = progan_b200.set_kernels(EmulKernels())
     try:
-        inp = common.make_inputs("s2_a0.5")
+        inp = common.make_inputs(name)
         gsum = None
         for r in (r0, r1):
-            G, D = helpers.build_models(inp, "fp32")
-            res, _ = helpers.product_train_step(G, D, r["real"], r["z"], r["eps"], 2, 0.5)
+            G, D = helpers.build_models(inp, "fp32", name=name)
+            res, _ = helpers.product_train_step(G, D, r["real"], r["z"], r["eps"], inp["step"], inp["alpha"],
+                                                label=r["label"])
             tr = progan_b200.Trainer(G, D)          # flat view of the D grads in bucket order
             flat = torch.zeros_like(tr.bD.g)
-            for name, (a, b) in tr.bD.group_range.items():
+            for gname, (a, b) in tr.bD.group_range.items():
                 off = a
-                for p in tr.bD.group_params[name]:
+                for p in tr.bD.group_params[gname]:
                     key = [k for k, q in D.named_parameters() if q is p][0]
                     if key in res["d_grads"]:
                         flat[off:off + p.numel()] = res["d_grads"][key].reshape(-1)
