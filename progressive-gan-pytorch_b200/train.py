@@ -194,6 +194,41 @@ class ProgressiveSchedule:
         return 4 * 2 ** self.step
 
 
+class MiniStepSchedule:
+    """The (step, alpha) schedule of the `proper_*` / `conditional_proper_*` loops
+    (proper_cifar_train.py:77,157,165-189): every resolution step has a fade-in mini step and a
+    stabilisation mini step of `images_seen_per_mini_step // batch_size` iterations each (the
+    first resolution only stabilises); alpha = min(1, step_iteration / iterations_per_mini_step);
+    past max_step the counter is parked (the reference's `np.inf`) and alpha stays 1.
+
+    `next()` returns (step, alpha, new_resolution) like ProgressiveSchedule; the Correct* models
+    count step 1 = 4 px, so `resolution` = 2 * 2**step."""
+
+    def __init__(self, images_seen_per_mini_step, batch_size, init_step=1, max_step=4):
+        self.per_mini = images_seen_per_mini_step // batch_size
+        self.step, self.max_step = init_step, max_step
+        self.step_iteration = 0
+
+    def next(self):
+        it = self.step_iteration
+        alpha = 1 if it is None else min(1, it / self.per_mini)
+        new_res = False
+        if it is not None and ((it == self.per_mini and self.step == 1) or it == 2 * self.per_mini):
+            first = self.step == 1 and it == self.per_mini
+            alpha, self.step_iteration = 0, 0
+            self.step += 1
+            if not first and self.step > self.max_step:
+                alpha, self.step_iteration, self.step = 1, None, self.max_step
+            new_res = True
+        if self.step_iteration is not None:
+            self.step_iteration += 1
+        return self.step, alpha, new_res
+
+    @property
+    def resolution(self):
+        return 2 * 2 ** self.step
+
+
 class Trainer:
     def __init__(self, generator, discriminator, g_running=None, lr=1e-3, betas=(0.0, 0.99),
                  eps=1e-8, ema_decay=0.999, gp_lambda=10.0, drift=0.001, process_group=None,

@@ -110,3 +110,36 @@ def test_progressive_schedule_matches_reference_loop():
         iteration += 1
         assert sched.next() == (step, alpha, reload_data), i
         assert sched.resolution == 4 * 2 ** step
+
+
+@pytest.mark.parametrize("init_step,max_step,per_mini", [(1, 4, 5), (2, 3, 4), (1, 2, 3), (1, 1, 2)])
+def test_mini_step_schedule_matches_reference_loop(init_step, max_step, per_mini):
+    """MiniStepSchedule.next() against a literal transcription of proper_cifar_train.py:157-189
+    (the `np.inf` sentinel included)."""
+    import progan_b200
+    batch = 16
+    sched = progan_b200.MiniStepSchedule(per_mini * batch + 3, batch, init_step=init_step, max_step=max_step)
+    iterations_per_mini_step = (per_mini * batch + 3) // batch              # :77
+    step, step_iteration = init_step, 0                                      # :157
+    inf = float("inf")
+    for i in range(2 * per_mini * (max_step + 2)):
+        alpha = min(1, step_iteration / iterations_per_mini_step)            # :165
+        reload_data = False
+        if step_iteration == iterations_per_mini_step and step == 1:         # :167-171
+            alpha = 0
+            step_iteration = 0
+            step += 1
+            reload_data = True
+        elif step_iteration == 2 * iterations_per_mini_step:                 # :172-180
+            alpha = 0
+            step_iteration = 0
+            step += 1
+            if step > max_step:
+                alpha = 1
+                step_iteration = inf
+                step = max_step
+            reload_data = True
+        if step_iteration != inf:                                            # :188-189
+            step_iteration += 1
+        assert sched.next() == (step, alpha, reload_data), i
+        assert sched.resolution == 2 * 2 ** step
