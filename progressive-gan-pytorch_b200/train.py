@@ -232,8 +232,13 @@ class MiniStepSchedule:
 class Trainer:
     def __init__(self, generator, discriminator, g_running=None, lr=1e-3, betas=(0.0, 0.99),
                  eps=1e-8, ema_decay=0.999, gp_lambda=10.0, drift=0.001, process_group=None,
-                 use_graph=False, segment_graphs=None, overlap_wgrad=True, overlap_passes=True):
+                 use_graph=False, segment_graphs=None, overlap_wgrad=True, overlap_passes=True,
+                 n_critic=1):
         self.G, self.D, self.G_run = generator, discriminator, g_running
+        # the generator phase runs on iterations with (i + 1) % n_critic == 0 (train.py:158, 221)
+        self.n_critic = int(n_critic)
+        if self.n_critic < 1:
+            raise ValueError("progan_b200.Trainer: n_critic must be >= 1")
         self.lr, self.betas, self.eps = lr, betas, eps
         self.ema_decay, self.gp_lambda, self.drift = ema_decay, gp_lambda, drift
         self.pg = process_group
@@ -315,17 +320,20 @@ class Trainer:
             K = get_kernels()
             F_.DIRECT_GRADS, K.defer_wgrad, K.wgrad_side_stream = self.prev
 
-    def _iteration(self, real, z, eps, step, alpha, fading, label=None):
+    def _iteration(self, real, z, eps, step, alpha, fading, label=None, do_g=True):
         """alpha: fp32 device scalar tensor when fading else the python number.  The iteration
         is three segments separated by the two gradient all-reduces (the segments are what a
         multi-GPU run captures as CUDA graphs; the collectives stay outside the graphs)."""
-        st = self._state(real, z, eps, step, alpha, fading, label)
+        st = self._state(real, z, eps, step, alpha, fading, label, do_g)
         with self._fast_paths(self._side):
             self._seg_d(st)
             self._allreduce(self.bD, st["planD"])
-            self._seg_g(st)
-            self._allreduce(self.bG, st["planG"])
-            self._seg_end(st)
+            if do_g:
+                self._seg_g(st)
+                self._allreduce(self.bG, st["planG"])
+                self._seg_end(st)
+            else:
+                self._seg_d_end(st)
 
     def _active(self, step, alpha, fading, label=None):
         """(live D groups, live G groups) for this (step, fading)."""
@@ -354,9 +362,9 @@ class Trainer:
             self._active_cache[key] = ent
         return ent
 
-    def _state(self, real, z, eps, step, alpha, fading, label=None):
+    def _state(self, real, z, eps, step, alpha, fading, label=None, do_g=True):
         namesD, namesG = self._active(step, alpha, fading, label)
-        return dict(real=real, z=z, eps=eps, step=step, alpha=alpha, label=label,
+        return dict(real=real, z=z, eps=eps, step=step, alpha=alpha, label=label, do_g=do_g,
                     planD=self.bD.plan(namesD), planG=self.bG.plan(namesG))
 
     def _seg_d(self, st):
@@ -370,7 +378,9 @@ class Trainer:
         la2 = (torch.cat([st["label"], st["label"]]),) if la else ()
         self.bD.g.zero_()
         B = real.shape[0]
-        fake = G(st["z"], *la, step=step, alpha=alpha)
+        # critic-only iterations (n_critic > 1) never backpropagate into G: no graph is kept
+        with (_NullCtx() if st.get("do_g", True) else torch.no_grad()):
+            fake = G(st["z"], *la, step=step, alpha=alpha)
         # The gradient-penalty pass (train.py:142-151) and the real/fake pass are independent
         # given `fake`: they run as two concurrent chains (streams; parallel branches of the
         # captured graph).  Every gradient kernel accumulates atomically (workspaces, bias sums),
@@ -399,6 +409,11 @@ class Trainer:
         K.flush_wgrads()
         st["fake"] = fake
         st["gp"] = gp.detach()
+
+    def _seg_d_end(self, st):
+        # critic-only iteration: D update and the metric, no generator phase (train.py:155-158)
+        self._adam(self.bD, st["planD"])
+        self.metrics["grad_penalty"].add_(st["gp"])
 
     def _seg_g(self, st):
         K = get_kernels()
@@ -467,14 +482,15 @@ class Trainer:
         if fading:
             self.alpha_dev.fill_(float(alpha))
         a = self.alpha_dev if fading else alpha
+        do_g = (self.iterations + 1) % self.n_critic == 0
         if not self.use_graph:
-            self._iteration(real, z, eps, step, a, fading, label)
+            self._iteration(real, z, eps, step, a, fading, label, do_g)
         else:
-            self._graph_step(real, z, eps, step, a, fading, label)
+            self._graph_step(real, z, eps, step, a, fading, label, do_g)
         self.iterations += 1
 
-    def _graph_step(self, real, z, eps, step, a, fading, label=None):
-        key = (step, fading, tuple(real.shape), label is not None)
+    def _graph_step(self, real, z, eps, step, a, fading, label=None, do_g=True):
+        key = (step, fading, tuple(real.shape), label is not None, do_g)
         ent = self._graphs.get(key)
         K = get_kernels()
         if ent is None:
@@ -490,7 +506,7 @@ class Trainer:
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
                 for _ in range(2):
-                    self._iteration(sreal, sz, seps, step, a, fading, slabel)
+                    self._iteration(sreal, sz, seps, step, a, fading, slabel, do_g)
             torch.cuda.current_stream().wait_stream(s)
             for dst, src in zip(state, snap):
                 dst.copy_(src)
@@ -504,13 +520,14 @@ class Trainer:
             if not self.segment_graphs:
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph):
-                    self._iteration(sreal, sz, seps, step, a, fading, slabel)
+                    self._iteration(sreal, sz, seps, step, a, fading, slabel, do_g)
                 graphs = [graph]
             else:
                 # one graph per segment; the NCCL all-reduces run between the replays
-                st = self._state(sreal, sz, seps, step, a, fading, slabel)
+                st = self._state(sreal, sz, seps, step, a, fading, slabel, do_g)
                 graphs, pool = [], None
-                for seg in (self._seg_d, self._seg_g, self._seg_end):
+                for seg in ((self._seg_d, self._seg_g, self._seg_end) if do_g
+                            else (self._seg_d, self._seg_d_end)):
                     gph = torch.cuda.CUDAGraph()
                     with self._fast_paths(self._side), torch.cuda.graph(gph, pool=pool,
                                                               capture_error_mode="thread_local"):
@@ -534,8 +551,9 @@ class Trainer:
             graphs[0].replay()
             self._allreduce(self.bD, planD)
             graphs[1].replay()
-            self._allreduce(self.bG, planG)
-            graphs[2].replay()
+            if do_g:
+                self._allreduce(self.bG, planG)
+                graphs[2].replay()
 
     def read_metrics(self, reset=True):
         """One host sync for all three running sums (the reference syncs three times per

@@ -107,3 +107,32 @@ def test_trainer_fast_paths_match_plain_autograd(name):
                 got = snaps[0][off:off + p.numel()].view(p.shape)
                 assert helpers.rel(got, res["d_grads"][key]) < 5e-3, key   # fused bias sums are fp32, autograd sums bf16 dA
             off += p.numel()
+
+
+def test_n_critic_graph_replay_equals_eager():
+    """n_critic = 2: critic-only and full iterations are separate captured graphs (one or
+    segmented); four iterations replayed vs eager, and the generator moved exactly twice."""
+    K = progan_b200.get_kernels()
+    K.conv_impl, K.wgrad_tc = "tc", True
+    inp = common.make_inputs("s3_a0.25")
+    real, z, eps = inp["real"].to(DEV), inp["z"].to(DEV), inp["eps"].to(DEV)
+    runs = []
+    for use_graph, seg in ((False, None), (True, None), (True, True)):
+        K.invalidate_packs()
+        G, D = helpers.build_models(inp, "bf16", device=DEV)
+        tr = progan_b200.Trainer(G, D, None, use_graph=use_graph, segment_graphs=seg, n_critic=2)
+        g0 = tr.bG.p.clone()
+        for i in range(4):
+            tr.step(real, z, eps, inp["step"], inp["alpha"])
+            if i == 0:
+                torch.cuda.synchronize()
+                assert torch.equal(tr.bG.p, g0)             # critic-only iteration
+        torch.cuda.synchronize()
+        assert float(tr.bG.steps.max()) == 2.0 and float(tr.bD.steps.max()) == 4.0
+        runs.append(tr)
+    for other in runs[1:]:
+        assert helpers.rel(other.bD.p, runs[0].bD.p) < 2e-3
+        assert helpers.rel(other.bG.p, runs[0].bG.p) < 2e-3
+        me, mo = runs[0].read_metrics(reset=False), other.read_metrics(reset=False)
+        for k in me:
+            assert abs(me[k] - mo[k]) <= 1e-2 * abs(me[k]) + 5e-2, (k, me[k], mo[k])

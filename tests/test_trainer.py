@@ -69,3 +69,45 @@ def test_inactive_parameters_untouched_and_steps_per_group():
         if grp not in live:
             assert torch.equal(p.detach(), before[k]), k
     assert tr.iterations == 2
+
+
+@pytest.mark.parametrize("name,n_critic", [("s2_a0.5", 2), ("s3_a0.25", 3), ("k2_a0.5_eq", 2)])
+def test_n_critic_matches_reference_ordered_loop(name, n_critic):
+    """n_critic > 1 (train.py:158,221): the generator phase, its Adam step and the EMA run only on
+    iterations with (i + 1) % n_critic == 0; checked against the loop written with plain autograd
+    calls and torch.optim.Adam, four iterations."""
+    from torch import optim
+    inp = common.make_inputs(name)
+    lab = inp["label"]
+    G, D = helpers.build_models(inp, "fp32", name=name)
+    Grun, _ = helpers.build_models(inp, "fp32", name=name)
+    tr = progan_b200.Trainer(G, D, Grun, n_critic=n_critic)
+    G2, D2 = helpers.build_models(inp, "fp32", name=name)
+    Grun2, _ = helpers.build_models(inp, "fp32", name=name)
+    g_opt = optim.Adam(G2.parameters(), lr=0.001, betas=(0.0, 0.99))
+    d_opt = optim.Adam(D2.parameters(), lr=0.001, betas=(0.0, 0.99))
+    gen = torch.Generator().manual_seed(77)
+    gen_loss_sum, n_g = 0.0, 0
+    for i in range(4):
+        real = torch.rand(inp["real"].shape, generator=gen) * 2 - 1
+        z = torch.randn(inp["z"].shape, generator=gen)
+        eps = torch.rand(inp["eps"].shape, generator=gen)
+        tr.step(real, z, eps, inp["step"], inp["alpha"], label=lab)
+        res, fake = helpers.product_train_step(G2, D2, real, z, eps, inp["step"], inp["alpha"], label=lab)
+        d_opt.step()
+        if (i + 1) % n_critic == 0:
+            loss, _ = helpers.product_g_phase(G2, D2, fake, inp["step"], inp["alpha"], label=lab)
+            g_opt.step()
+            with torch.no_grad():
+                for (_, pr), (_, pg) in zip(Grun2.named_parameters(), G2.named_parameters()):
+                    pr.mul_(0.999).add_(pg, alpha=1 - 0.999)
+            gen_loss_sum += float(loss)
+            n_g += 1
+    assert tr.iterations == 4 and n_g == 4 // n_critic
+    for a, b in ((D, D2), (G, G2), (Grun, Grun2)):
+        for (k, p), (_, q) in zip(a.named_parameters(), b.named_parameters()):
+            assert helpers.rel(p, q) < 1e-5, k
+    m = tr.read_metrics()
+    assert abs(m["gen_loss"] - gen_loss_sum) <= 1e-4 * abs(gen_loss_sum) + 1e-6
+    with pytest.raises(ValueError):
+        progan_b200.Trainer(G, D, Grun, n_critic=0)
