@@ -49,6 +49,32 @@ def test_train_step_matches_oracle_fp64(name):
         assert helpers.rel(g_grads[k], v) < 1e-8, k
 
 
+@pytest.mark.parametrize("B", [1, 3])
+@pytest.mark.parametrize("name", ["s2_a0.5", "s3_a-1_nopn"])
+def test_edge_batch_sizes_match_oracle_fp64(name, B):
+    """Batch 1 (minibatch-stddev of a single sample: variance 0, sigma = sqrt(1e-8)) and an odd
+    batch, first- and second-order, against the oracle."""
+    inp = common.make_inputs(name)
+    step, alpha = inp["step"], inp["alpha"]
+    g = torch.Generator().manual_seed(5 + B)
+    real = (torch.rand(B, *inp["real"].shape[1:], generator=g) * 2 - 1).double()
+    z = torch.randn(B, inp["z_dim"], generator=g).double()
+    eps = torch.rand(B, 1, 1, 1, generator=g).double()
+    G, D = helpers.build_models(inp, "fp64", dtype=torch.float64)
+    res, fake = helpers.product_train_step(G, D, real, z, eps, step, alpha)
+    gen_loss, g_grads = helpers.product_g_phase(G, D, fake, step, alpha)
+    PG, PD = O.params_of(_to64(inp["G"])), O.params_of(_to64(inp["D"]))
+    ref, rfake = O.train_step(PG, PD, real, z, eps, step, alpha, inp["tanh"], inp["pixel_norm"])
+    rloss, rg = O.g_phase(PG, PD, rfake, step, alpha)
+    for k in ("real_predict", "fake", "hat_predict", "grad_x_hat", "grad_penalty", "disc_loss"):
+        assert helpers.rel(res[k], ref[k]) < 1e-9, k
+    for k, v in ref["d_grads"].items():
+        assert helpers.rel(res["d_grads"][k], v) < 1e-7, k
+    assert helpers.rel(gen_loss, rloss) < 1e-9
+    for k, v in rg.items():
+        assert helpers.rel(g_grads[k], v) < 1e-7, k
+
+
 def test_unfused_gp_chain_also_works():
     """The reference script's own torch expression for the penalty (train.py:148-150) must
     keep working on the product modules (drop-in)."""
