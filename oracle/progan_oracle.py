@@ -54,15 +54,21 @@ def eq_conv_transpose2d(P, prefix, x):
     return F.conv_transpose2d(x, w * eq_scale(w), P[prefix + '.conv.bias'], stride=1, padding=0)
 
 
-def conv_block(P, prefix, x, pixelnorm=True, pad2=1, taps=None):
-    """ConvBlock.forward, progan_modules.py:120-148.  Second conv is 4x4/pad0 for D's last block."""
+def conv_block(P, prefix, x, pixelnorm=True, pad2=1, taps=None, taps_in=None):
+    """ConvBlock.forward, progan_modules.py:120-148.  Second conv is 4x4/pad0 for D's last block.
+    taps: the activation after each conv+[PN]+LReLU; taps_in: the input each conv saw (for
+    teacher-forced per-layer comparisons)."""
     i2 = 3 if pixelnorm else 2
+    if taps_in is not None:
+        taps_in[prefix + '.conv.0'] = x
     a = eq_conv2d(P, prefix + '.conv.0', x, 1)
     if pixelnorm:
         a = pixel_norm(a)
     h = F.leaky_relu(a, 0.2)
     if taps is not None:
         taps[prefix + '.conv.0'] = h
+    if taps_in is not None:
+        taps_in[prefix + '.conv.%d' % i2] = h
     a = eq_conv2d(P, prefix + '.conv.%d' % i2, h, pad2)
     if pixelnorm:
         a = pixel_norm(a)
@@ -78,7 +84,7 @@ _G_BLOCKS = ['progression_8', 'progression_16', 'progression_32', 'progression_6
 _G_HEADS = ['to_rgb_8', 'to_rgb_16', 'to_rgb_32', 'to_rgb_64', 'to_rgb_128', 'to_rgb_256']
 
 
-def g_forward(P, z, step=0, alpha=-1, tanh=True, pixelnorm=True, max_step=6, taps=None):
+def g_forward(P, z, step=0, alpha=-1, tanh=True, pixelnorm=True, max_step=6, taps=None, taps_in=None):
     """Generator.forward, progan_modules.py:219-254 (+ progress :204-207, output :209-217)."""
     step = min(step, max_step)
     if step < 1:
@@ -88,11 +94,13 @@ def g_forward(P, z, step=0, alpha=-1, tanh=True, pixelnorm=True, max_step=6, tap
     feat = F.leaky_relu(pixel_norm(a), 0.2)          # input_layer always normalises (:181-184)
     if taps is not None:
         taps['input_layer'] = feat
-    feat = conv_block(P, 'progression_4', feat, pixelnorm, taps=taps)
+    if taps_in is not None:
+        taps_in['input_layer'] = z.view(-1, zdim, 1, 1)
+    feat = conv_block(P, 'progression_4', feat, pixelnorm, taps=taps, taps_in=taps_in)
     prev = None
     for s in range(1, step + 1):
         prev = feat
-        feat = conv_block(P, _G_BLOCKS[s - 1], up2(feat), pixelnorm, taps=taps)
+        feat = conv_block(P, _G_BLOCKS[s - 1], up2(feat), pixelnorm, taps=taps, taps_in=taps_in)
     out = eq_conv2d(P, _G_HEADS[step - 1], feat)
     if step >= 2 and 0 <= alpha < 1:                 # no blend at step 1 (:231-234)
         skip = up2(eq_conv2d(P, _G_HEADS[step - 2], prev))
@@ -103,7 +111,7 @@ def g_forward(P, z, step=0, alpha=-1, tanh=True, pixelnorm=True, max_step=6, tap
 
 
 # -------------------------------------------------------------- discriminator
-def d_forward(P, x, step=0, alpha=-1, n_layer=7, taps=None):
+def d_forward(P, x, step=0, alpha=-1, n_layer=7, taps=None, taps_in=None):
     """Discriminator.forward, progan_modules.py:282-311."""
     out = None
     for i in range(step, -1, -1):
@@ -117,7 +125,7 @@ def d_forward(P, x, step=0, alpha=-1, n_layer=7, taps=None):
             mean_std = out_std.mean().expand(out.size(0), 1, 4, 4)           # :291-292
             out = torch.cat([out, mean_std], 1)                              # :293
         out = conv_block(P, 'progression.%d' % index, out, True,
-                         pad2=0 if index == n_layer - 1 else 1, taps=taps)
+                         pad2=0 if index == n_layer - 1 else 1, taps=taps, taps_in=taps_in)
         if i > 0:
             out = down2(out)                                                 # :299
             if i == step and 0 <= alpha < 1:
@@ -127,6 +135,71 @@ def d_forward(P, x, step=0, alpha=-1, n_layer=7, taps=None):
     w = P['linear.linear.weight_orig']
     return F.linear(out, w * eq_scale(w), P['linear.linear.bias'])            # :307-309
 
+
+
+# ------------------------------------------------- Correct* rewiring (config 2)
+_C_BLOCKS = ['progression_8', 'progression_16', 'progression_32']
+_C_HEADS = ['to_rgb_4', 'to_rgb_8', 'to_rgb_16', 'to_rgb_32']
+
+
+def correct_g_forward(P, z, step=0, alpha=-1, tanh=False, pixelnorm=True, max_step=4, taps=None,
+                      taps_in=None):
+    """CorrectGenerator.forward, progan_modules.py:523-545 (output(): :512-521): step 1 = 4 px;
+    the 4x4 stem (ConvTranspose + conv, :487-494) always applies PixelNorm; with tanh the
+    step-2 path returns without the blend (:534-537)."""
+    step = min(step, max_step)
+    zdim = P['progression_4.0.conv.weight_orig'].shape[0]
+    if taps_in is not None:
+        taps_in['progression_4.0'] = z.view(-1, zdim, 1, 1)
+    h = F.leaky_relu(pixel_norm(eq_conv_transpose2d(P, 'progression_4.0', z.view(-1, zdim, 1, 1))), 0.2)
+    if taps is not None:
+        taps['progression_4.0'] = h
+    if taps_in is not None:
+        taps_in['progression_4.3'] = h
+    feat = F.leaky_relu(pixel_norm(eq_conv2d(P, 'progression_4.3', h, 1)), 0.2)
+    if taps is not None:
+        taps['progression_4.3'] = feat
+    if step < 1:
+        return None
+    prev = None
+    for s in range(2, step + 1):
+        prev = feat
+        feat = conv_block(P, _C_BLOCKS[s - 2], up2(feat), pixelnorm, taps=taps, taps_in=taps_in)
+    out = eq_conv2d(P, _C_HEADS[step - 1], feat)
+    if step >= 2 and 0 <= alpha < 1 and not (step == 2 and tanh):
+        out = (1 - alpha) * up2(eq_conv2d(P, _C_HEADS[step - 2], prev)) + alpha * out
+    return torch.tanh(out) if tanh else out
+
+
+def correct_d_forward(P, x, step=0, alpha=-1, n_layer=4, taps=None, taps_in=None):
+    """CorrectDiscriminator.forward, progan_modules.py:576-598: step 1 = 4 px, loop
+    range(step, 0, -1), minibatch-stddev before the last block, fade-in at every step > 1."""
+    out = None
+    for i in range(step, 0, -1):
+        index = n_layer - i
+        if i == step:
+            out = eq_conv2d(P, 'from_rgb.%d' % index, x)
+            if taps is not None:
+                taps['from_rgb.%d' % index] = out
+        if i == 1:
+            out_std = torch.sqrt(out.var(0, unbiased=False) + 1e-8)
+            out = torch.cat([out, out_std.mean().expand(out.size(0), 1, 4, 4)], 1)
+        out = conv_block(P, 'progression.%d' % index, out, True,
+                         pad2=0 if index == n_layer - 1 else 1, taps=taps, taps_in=taps_in)
+        if i > 1:
+            out = down2(out)
+            if i == step and 0 <= alpha < 1:
+                skip = eq_conv2d(P, 'from_rgb.%d' % (index + 1), down2(x))
+                out = (1 - alpha) * skip + alpha * out
+    out = out.squeeze(2).squeeze(2)
+    w = P['linear.linear.weight_orig']
+    return F.linear(out, w * eq_scale(w), P['linear.linear.bias'])
+
+
+FAMILY_FORWARDS = {
+    'base': (g_forward, d_forward),
+    'correct': (correct_g_forward, correct_d_forward),
+}
 
 # ------------------------------------------------------------------ train step
 def params_of(module_or_dict, requires_grad=True, device=None, dtype=None):
@@ -150,7 +223,7 @@ def _acc(store, P, keys=None):
 
 
 def train_step(PG, PD, real, z, eps, step, alpha, tanh=False, pixelnorm=True,
-               gp_lambda=10.0, want_taps=False):
+               gp_lambda=10.0, want_taps=False, family='base'):
     """One iteration of the hot loop, train.py:122-167, without the optimiser updates.
 
     Returns a dict with the three loss terms, x_hat, grad_x_hat, the D parameter gradients
@@ -159,17 +232,20 @@ def train_step(PG, PD, real, z, eps, step, alpha, tanh=False, pixelnorm=True,
     weights — the D update in between is the caller's business, see train_iteration).
     """
     out = {}
+    g_forward, d_forward = FAMILY_FORWARDS[family]
     for p in PD.values():
         p.grad = None
     for p in PG.values():
         p.grad = None
     b = real.size(0)
     taps_real = {} if want_taps else None
-    real_predict = d_forward(PD, real, step, alpha, taps=taps_real)
+    taps_real_in = {} if want_taps else None
+    real_predict = d_forward(PD, real, step, alpha, taps=taps_real, taps_in=taps_real_in)
     real_loss = real_predict.mean() - 0.001 * (real_predict ** 2).mean()      # :128-129
     (-real_loss).backward()                                                    # .backward(mone) :130
     taps_g = {} if want_taps else None
-    fake = g_forward(PG, z, step, alpha, tanh, pixelnorm, taps=taps_g)        # :135
+    taps_g_in = {} if want_taps else None
+    fake = g_forward(PG, z, step, alpha, tanh, pixelnorm, taps=taps_g, taps_in=taps_g_in)   # :135
     fake_predict = d_forward(PD, fake.detach(), step, alpha).mean()           # :136-138
     fake_predict.backward()                                                    # :139
     x_hat = (eps * real.data + (1 - eps) * fake.detach().data).requires_grad_(True)   # :142-144
@@ -186,14 +262,16 @@ def train_step(PG, PD, real, z, eps, step, alpha, tanh=False, pixelnorm=True,
     if want_taps:
         out['taps_d_real'] = {k: v.detach() for k, v in taps_real.items()}
         out['taps_g'] = {k: v.detach() for k, v in taps_g.items()}
+        out['taps_d_real_in'] = {k: v.detach() for k, v in taps_real_in.items()}
+        out['taps_g_in'] = {k: v.detach() for k, v in taps_g_in.items()}
     return out, fake
 
 
-def g_phase(PG, PD, fake, step, alpha):
+def g_phase(PG, PD, fake, step, alpha, family='base'):
     """train.py:158-167: loss = -D(fake).mean() through the stored G graph."""
     for p in list(PG.values()) + list(PD.values()):
         p.grad = None
-    predict = d_forward(PD, fake, step, alpha)
+    predict = FAMILY_FORWARDS[family][1](PD, fake, step, alpha)
     loss = -predict.mean()
     loss.backward()
     return loss.detach(), {k: p.grad.clone() for k, p in PG.items() if p.grad is not None}
@@ -229,12 +307,12 @@ def ema_accumulate(P_running, P_src, decay=0.999):
 
 
 def train_iteration(PG, PD, PG_run, optG, optD, real, z, eps, step, alpha, tanh=False,
-                    pixelnorm=True):
+                    pixelnorm=True, family='base'):
     """Full iteration train.py:122-169 (n_critic = 1): D phase, D Adam, G phase with the
     updated D, G Adam, EMA."""
-    res, fake = train_step(PG, PD, real, z, eps, step, alpha, tanh, pixelnorm)
+    res, fake = train_step(PG, PD, real, z, eps, step, alpha, tanh, pixelnorm, family=family)
     optD.step(PD, res['d_grads'])
-    gen_loss, g_grads = g_phase(PG, PD, fake, step, alpha)
+    gen_loss, g_grads = g_phase(PG, PD, fake, step, alpha, family)
     optG.step(PG, g_grads)
     ema_accumulate(PG_run, PG)
     res['gen_loss'] = gen_loss

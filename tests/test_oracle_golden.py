@@ -17,15 +17,17 @@ def _close(a, b, tol, what):
     assert helpers.rel(a, b) < tol, what
 
 
-@pytest.mark.parametrize("name", list(common.CASES))
+@pytest.mark.parametrize("name", list(common.CASES) + list(common.CORRECT_CASES))
 def test_oracle_matches_golden(name):
+    """train.py's models (s*) and the Correct* rewiring of config 2 (c*, recorded from the real
+    CorrectGenerator / CorrectDiscriminator with proper_cifar_train.py's loop body)."""
     gold = torch.load(os.path.join(common.HERE, name + ".pt"), weights_only=True)
     inp = common.make_inputs(name)
     step, alpha = inp["step"], inp["alpha"]
     PG, PD, PGrun = O.params_of(inp["G"]), O.params_of(inp["D"]), O.params_of(inp["G"], False)
     optG, optD = O.AdamState(PG), O.AdamState(PD)
     res = O.train_iteration(PG, PD, PGrun, optG, optD, inp["real"], inp["z"], inp["eps"], step,
-                            alpha, inp["tanh"], inp["pixel_norm"])
+                            alpha, inp["tanh"], inp["pixel_norm"], family=common.family(name))
     for k in ("real_predict", "fake", "hat_predict", "grad_x_hat", "grad_penalty", "disc_loss",
               "gen_loss"):
         _close(res[k], gold[k], 2e-5, k)
