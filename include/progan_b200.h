@@ -176,9 +176,11 @@ int pg_pw_expand(const float *img, const float *w, const float *bias, void *act,
 int pg_pw_reduce(const void *act, const float *w, const float *bias, float *img,
                  int N, long long HW, int K, int C, int w_sc, int w_sk,
                  float scale, int dtype, void *stream);
-/* dw(c,k) += scale * sum_pix act[pix,c] img[k,pix]; dw zero-initialised      */
-int pg_pw_wgrad(const void *act, const float *img, float *dw, int N, long long HW,
-                int K, int C, int w_sc, int w_sk, float scale, int dtype,
+/* dw(c,k) += scale * sum_pix act[pix,c] img[k,pix]; dw zero-initialised.
+ * dbias (may be NULL): dbias[c] += sum_pix act[pix,c] — the bias gradient of a
+ * from_rgb layer, accumulated by the same pass over its output gradient      */
+int pg_pw_wgrad(const void *act, const float *img, float *dw, float *dbias, int N,
+                long long HW, int K, int C, int w_sc, int w_sk, float scale, int dtype,
                 void *stream);
 /* per-channel sum of an NCHW fp32 image tensor (to_rgb / linear bias grad)  */
 int pg_img_chansum(const float *img, float *out, int N, long long HW, int K,

@@ -37,7 +37,7 @@ SIGNATURES = {
     "pg_colsum": [P, P, c_ll, c_int, c_int, P],
     "pg_pw_expand": [P, P, P, P, c_int, c_ll, c_int, c_int, c_int, c_int, c_float, c_int, P],
     "pg_pw_reduce": [P, P, P, P, c_int, c_ll, c_int, c_int, c_int, c_int, c_float, c_int, P],
-    "pg_pw_wgrad": [P, P, P, c_int, c_ll, c_int, c_int, c_int, c_int, c_float, c_int, P],
+    "pg_pw_wgrad": [P, P, P, P, c_int, c_ll, c_int, c_int, c_int, c_int, c_float, c_int, P],
     "pg_img_chansum": [P, P, c_int, c_ll, c_int, P],
     "pg_avgpool2": [P, P, c_int, c_int, c_int, c_int, c_int, P],
     "pg_avgpool2_bwd": [P, P, c_int, c_int, c_int, c_int, c_int, P],

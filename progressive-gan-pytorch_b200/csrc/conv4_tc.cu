@@ -47,7 +47,7 @@ struct Conv4Params {
   int dbg;                             // experiment knobs (PG_DBG)
 };
 
-constexpr int kC4EpiThreads = 256;                 // 8 epilogue warps: 2 per TMEM lane quadrant
+constexpr int kC4EpiThreads = 256;                 // 8 epilogue warps: two groups of 4 (one per TMEM stage)
 constexpr int kC4Threads = 128 + kC4EpiThreads;    // + 4 control warps
 constexpr int kC4MaxA = 8, kC4MaxW = 12;
 
@@ -66,8 +66,10 @@ conv4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   const uint32_t smem_w = base;
   const uint32_t smem_a = base + w_bytes;
   const uint32_t smem_out = smem_a + (uint32_t)(p.a_stages * MT) * kBoxPad;
-  const uint32_t out_bytes = 128u * (uint32_t)COUT * 2u;
-  // pooled staging tile (32 pooled pixels x COUT) only when the launch asks for it
+  // one staging tile (128 pixels x min(COUT, 64) channels) per epilogue group, and one pooled
+  // staging tile (32 pooled pixels) per group when the launch asks for the fused average pool
+  constexpr uint32_t kHC = COUT > 64 ? 64u : (uint32_t)COUT;
+  constexpr uint32_t out_bytes = 2u * 128u * kHC * 2u;
   const uint32_t smem_pool = smem_out + out_bytes;
   const uint32_t bar_base = smem_pool + (p.pool ? out_bytes / 4u : 0u);
   auto afull = [&](int s) { return bar_base + 8u * (uint32_t)s; };
@@ -82,7 +84,6 @@ conv4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   uint8_t *gbase = smem_raw + (base - smem_u32(smem_raw));
   volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(gbase + (tmem_slot - base));
   float *bias_ptr = reinterpret_cast<float *>(gbase + (bias_s - base));
-  float *ss_buf = bias_ptr + 128;                    // [2][128] partial per-pixel reductions
   uint8_t *out_ptr = gbase + (smem_out - base);
   uint8_t *pool_ptr = gbase + (smem_pool - base);
 
@@ -109,7 +110,7 @@ conv4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull(a), 1);
-      mbar_init(tempty(a), kC4EpiThreads);
+      mbar_init(tempty(a), kC4EpiThreads / 2);     // the epilogue group that owns stage a
     }
     mbar_init(wres_bar, 1);
     fence_barrier_init();
@@ -288,64 +289,47 @@ conv4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     }
     __syncwarp();
   } else if (warp >= 4) {
-    // ===================== epilogue (8 warps) =====================
-    // Two warps per TMEM lane quadrant, each owning half of the channel columns of its 32
-    // pixels: one tcgen05.ld pass, values stay in registers; per-pixel reductions over the
-    // channels (PixelNorm sum of squares, <p,u> of the fused backward) are completed through a
-    // 1 KB smem exchange between the two halves.  (16 epilogue warps were measured slower.)
-    constexpr int CPT = COUT / 2;                 // columns per thread: 16 / 32 / 64
-    constexpr int out_chunk = (COUT % 64 == 0) ? 64 : 32;
-    constexpr int chunk_rows_bytes = out_chunk * 2;
-    constexpr int swz_bits = chunk_rows_bytes == 128 ? 3 : 2;
-    constexpr int n_chunks = COUT / out_chunk;
+    // ===================== epilogue: two independent groups of 4 warps =====================
+    // Group g owns accumulator stage g (the MMA warp alternates stages per super tile), so the
+    // two groups work on different tiles at the same time and never synchronise with each
+    // other.  Inside a group, warp q reads TMEM lane quadrant q and every thread owns ONE pixel
+    // with its WHOLE channel vector: the PixelNorm sum of squares (and <p,u> of the fused
+    // backward) is a per-thread reduction - no cross-warp exchange.  Each group has its own
+    // staging tile and issues its own TMA stores; the only synchronisation per tile is two
+    // 128-thread named barriers around the staging writes.  (The first version of this
+    // epilogue split a row's channels over two warps, exchanged partial sums through smem and
+    // shared ONE staging tile between all 8 warps: 1700 cycles per 128x32 tile, 3800-5000 per
+    // 128x128 tile - profiles/r2/diag_conv4_before.txt - which bound every layer with
+    // Cout <= 64.)  128 output channels are processed as two 64-column passes over TMEM (the
+    // second pass re-reads its columns; a TMEM read costs far less than the registers would).
+    constexpr int HC = COUT > 64 ? 64 : COUT;       // columns per pass = channels per staging tile
+    constexpr int NH = COUT / HC;                   // 1, or 2 for COUT = 128
+    constexpr int row_b = HC * 2;                   // staging row bytes: 64 or 128
+    constexpr int swz_bits = row_b == 128 ? 3 : 2;
+    const int g = (warp - 4) >> 2;                  // group = accumulator stage
     const int q = warp & 3;
-    const int part = (warp - 4) >> 2;             // 0..1
-    const int row = q * 32 + lane;                // tile row: pixel (hl = row/8, wl = row%8)
-    const int et = threadIdx.x - 128;             // 0..255
-    const int col0 = part * CPT;
+    const int row = q * 32 + lane;                  // tile row: pixel (hl = row/8, wl = row%8)
+    const int gt = (int)threadIdx.x - 128 - g * 128;   // 0..127 inside the group
+    const int bar_id = 1 + g;
+    uint8_t *stage_ptr = out_ptr + (size_t)g * 128 * row_b;
+    const uint32_t stage_s = smem_out + (uint32_t)g * 128u * (uint32_t)row_b;
+    uint8_t *pool_g = pool_ptr + (size_t)g * 32 * row_b;
+    const uint32_t pool_s = smem_pool + (uint32_t)g * 32u * (uint32_t)row_b;
     const float invC = 1.f / (float)COUT;
     const float scale = p.scale, slope = p.slope;
-    int acc = 0;
-    uint32_t acc_phase = 0;
     const float inv_slope = 1.f / slope;
-    float csum[2] = {0.f, 0.f};                   // ABW: this lane's share of the bias gradient
-    // ABW: this thread's slice of y_prev (and r_prev) for a tile is loaded one tile ahead, right
-    // after the previous tile's arithmetic, and prefetched into L2 two tiles ahead: the HBM
-    // latency hides behind the accumulator wait instead of sitting on the epilogue's critical path
-    uint4 yraw[ABW ? CPT / 8 : 1];
-    float rp = 1.f;
-    auto pix_of = [&](int tile) -> long long {
-      const int tw_ = tile % p.tiles_w;
-      const int th_ = (tile / p.tiles_w) % p.tiles_h;
-      const int n_ = tile / (p.tiles_w * p.tiles_h);
-      return ((long long)n_ * p.H + (th_ * 16 + (row >> 3))) * p.W + tw_ * 8 + (row & 7);
-    };
-    auto next_tile = [&](int sb_, int mt_, int ahead) -> int {     // flat successor, -1 past the end
-      for (int a = 0; a < ahead; ++a) {
-        if (++mt_ == MT) { mt_ = 0; sb_ += ncl * CL; }
-      }
-      return sb_ < p.num_super ? (sb_ + (int)rank) * MT + mt_ : -1;
-    };
-    auto load_y = [&](int tile) {
-      if (tile < 0) return;
-      const long long px = pix_of(tile);
-      const uint4 *yp = reinterpret_cast<const uint4 *>(p.y_prev + px * COUT + col0);
-#pragma unroll
-      for (int i = 0; i < CPT / 8; ++i) yraw[i] = __ldg(yp + i);
-      if (p.use_pn) rp = __ldg(p.r_prev + px);
-    };
-    auto prefetch_y = [&](int tile) {
-      if (tile < 0) return;
-      const char *yp = reinterpret_cast<const char *>(p.y_prev + pix_of(tile) * COUT + col0);
-#pragma unroll
-      for (int b = 0; b < CPT * 2; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(yp + b));
-    };
-    if (ABW) {
-      load_y(next_tile(cid * CL, 0, 0));
-      prefetch_y(next_tile(cid * CL, 0, 1));
-    }
-    for (int sb = cid * CL; sb < p.num_super; sb += ncl * CL) {
+    const bool pn = ABW ? (p.use_pn != 0) : (p.epi == PG_EPI_PN_LRELU);
+    const bool act = !ABW && p.epi != PG_EPI_LINEAR;
+    auto group_bar = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory"); };
+    float csum[2] = {0.f, 0.f};                     // ABW: this lane's share of the bias gradient
+    uint32_t ph = 0;
+    int it = 0;
+    for (int sb = cid * CL; sb < p.num_super; sb += ncl * CL, ++it) {
+      if ((it & 1) != g) continue;
       const int st = sb + (int)rank;
+      mbar_wait(tfull(g), ph);
+      ph ^= 1u;
+      tc_fence_after();
 #pragma unroll 1
       for (int mt = 0; mt < MT; ++mt) {
         const int tile = st * MT + mt;
@@ -354,62 +338,47 @@ conv4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         const int n = tile / (p.tiles_w * p.tiles_h);
         const int w0 = tw * 8, h0 = th * 16;
         const long long pix = ((long long)n * p.H + (h0 + (row >> 3))) * p.W + w0 + (row & 7);
-        if (ABW) prefetch_y(next_tile(sb, mt, 2));
-        if (mt == 0) {
-          mbar_wait(tfull(acc), acc_phase);
-          tc_fence_after();
-        }
         const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) +
-                                (uint32_t)(acc * acc_stride + mt * COUT + col0);
-        uint32_t vr[CPT];
-        float v[CPT];
-        float r = 1.f;
-        if (!ABW) {
-          // accumulator drain in 16-column pieces: the tcgen05.ld of piece c+1 is in flight while
-          // piece c is scaled and squared (TMEM reads are 64 B/clk per SM: the drain of a
-          // 128x128 fp32 tile alone is ~1000 cycles)
-          constexpr int CH = 16, NCHK = CPT / CH;
-          float ss = 0.f;
-          tmem_ld<CH>(t_addr, vr);
+                                (uint32_t)(g * acc_stride + mt * COUT);
+        float v[HC];                         // accumulators are loaded in place (one register set)
+        uint32_t *vr = reinterpret_cast<uint32_t *>(v);
+        // ---- pass 1: the first HC columns stay in registers
 #pragma unroll
-          for (int c = 0; c < NCHK; ++c) {
-            tmem_ld_wait();
-            if (c + 1 < NCHK) {
-              tmem_ld<CH>(t_addr + (uint32_t)((c + 1) * CH), vr + (c + 1) * CH);
-            } else if (mt == MT - 1) {   // accumulator stage fully read: hand it back to the MMA warp
-              tc_fence_before();
-              mbar_arrive(tempty(acc));
-            }
+        for (int c = 0; c < HC; c += 32) tmem_ld<32>(t_addr + (uint32_t)c, vr + c);
+        uint4 yraw[ABW ? HC / 8 : 1];
+        float rp = 1.f;
+        if constexpr (ABW) {   // stored activation of the layer in front (this thread's pixel)
+          const uint4 *yp = reinterpret_cast<const uint4 *>(p.y_prev + pix * COUT);
 #pragma unroll
-            for (int j = c * CH; j < (c + 1) * CH; j += 4) {
-              const float4 b4 = *reinterpret_cast<const float4 *>(bias_ptr + col0 + j);
-              v[j] = fmaf(__uint_as_float(vr[j]), scale, b4.x);
-              v[j + 1] = fmaf(__uint_as_float(vr[j + 1]), scale, b4.y);
-              v[j + 2] = fmaf(__uint_as_float(vr[j + 2]), scale, b4.z);
-              v[j + 3] = fmaf(__uint_as_float(vr[j + 3]), scale, b4.w);
-              ss = fmaf(v[j], v[j], ss);
-              ss = fmaf(v[j + 1], v[j + 1], ss);
-              ss = fmaf(v[j + 2], v[j + 2], ss);
-              ss = fmaf(v[j + 3], v[j + 3], ss);
-            }
-          }
-          if (p.dbg & 2) continue;       // experiment: accumulator drain only
-          if (p.epi == PG_EPI_PN_LRELU) {
-            ss_buf[part * 128 + row] = ss;
-            asm volatile("bar.sync 2, 256;" ::: "memory");
-            r = rsqrtf((ss_buf[row] + ss_buf[128 + row]) * invC + 1e-8f);
+          for (int i = 0; i < HC / 8; ++i) yraw[i] = __ldg(yp + i);
+          if (pn) rp = __ldg(p.r_prev + pix);
+        }
+        // the group's staging tile is free once its previous TMA store has read it
+        if (gt == 0) tma_store_wait_read0();
+        group_bar();
+        tmem_ld_wait();
+        if (NH == 1 && mt == MT - 1) {       // stage fully read: hand it back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(tempty(g));
+        }
+        float red = 0.f;                     // sum of squares (forward) or <p,u> (fused backward)
+        if constexpr (!ABW) {
+#pragma unroll
+          for (int j = 0; j < HC; j += 4) {
+            const float4 b4 = *reinterpret_cast<const float4 *>(bias_ptr + j);
+            v[j] = fmaf(__uint_as_float(vr[j]), scale, b4.x);
+            v[j + 1] = fmaf(__uint_as_float(vr[j + 1]), scale, b4.y);
+            v[j + 2] = fmaf(__uint_as_float(vr[j + 2]), scale, b4.z);
+            v[j + 3] = fmaf(__uint_as_float(vr[j + 3]), scale, b4.w);
+            red = fmaf(v[j], v[j], red);
+            red = fmaf(v[j + 1], v[j + 1], red);
+            red = fmaf(v[j + 2], v[j + 2], red);
+            red = fmaf(v[j + 3], v[j + 3], red);
           }
         } else {
-          tmem_ld<CPT>(t_addr, vr);
-          tmem_ld_wait();
-          if (mt == MT - 1) {            // accumulator stage fully read: hand it back to the MMA warp
-            tc_fence_before();
-            mbar_arrive(tempty(acc));
-          }
-          // da = r (u - p <p,u>/C), u = m * dh, (p, m) rebuilt from the stored activation
-          float s_pu = 0.f;
+          // u = m * dh; p and m rebuilt from the stored activation y = lrelu(p)
 #pragma unroll
-          for (int i = 0; i < CPT / 8; ++i) {
+          for (int i = 0; i < HC / 8; ++i) {
             const __nv_bfloat162 *h2 = reinterpret_cast<const __nv_bfloat162 *>(&yraw[i]);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -417,119 +386,143 @@ conv4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
               const int j = i * 8 + 2 * e;
               const float u0 = __uint_as_float(vr[j]) * scale * (yy.x > 0.f ? 1.f : slope);
               const float u1 = __uint_as_float(vr[j + 1]) * scale * (yy.y > 0.f ? 1.f : slope);
-              s_pu = fmaf(yy.x > 0.f ? yy.x : yy.x * inv_slope, u0, s_pu);
-              s_pu = fmaf(yy.y > 0.f ? yy.y : yy.y * inv_slope, u1, s_pu);
+              red = fmaf(yy.x > 0.f ? yy.x : yy.x * inv_slope, u0, red);
+              red = fmaf(yy.y > 0.f ? yy.y : yy.y * inv_slope, u1, red);
               v[j] = u0;
               v[j + 1] = u1;
             }
           }
-          if (p.use_pn) {
-            ss_buf[part * 128 + row] = s_pu;
-            asm volatile("bar.sync 2, 256;" ::: "memory");
-            const float k = (ss_buf[row] + ss_buf[128 + row]) * invC;
+        }
+        if (NH == 2 && !ABW) {
+          // columns HC..COUT-1 only contribute to the sum of squares in this pass
+          uint32_t tb[2][16];
+          tmem_ld<16>(t_addr + (uint32_t)HC, tb[0]);
 #pragma unroll
-            for (int i = 0; i < CPT / 8; ++i) {
-              const __nv_bfloat162 *h2 = reinterpret_cast<const __nv_bfloat162 *>(&yraw[i]);
+          for (int c = 0; c < HC / 16; ++c) {
+            tmem_ld_wait();
+            if (c + 1 < HC / 16) tmem_ld<16>(t_addr + (uint32_t)(HC + (c + 1) * 16), tb[(c + 1) & 1]);
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
+            for (int j = 0; j < 16; ++j) {
+              const float a = fmaf(__uint_as_float(tb[c & 1][j]), scale, bias_ptr[HC + c * 16 + j]);
+              red = fmaf(a, a, red);
+            }
+          }
+        }
+        if (p.dbg & 2) {                     // experiment: accumulator drain only
+          if (NH == 2 && mt == MT - 1) {
+            tc_fence_before();
+            mbar_arrive(tempty(g));
+          }
+          continue;
+        }
+        float r = 1.f;
+        if (!ABW && pn) r = rsqrtf(red * invC + 1e-8f);
+        const float kpu = red * invC;        // ABW with PixelNorm: <p,u>/C
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+          if (h == 1) {
+            // ---- pass 2 (COUT = 128): re-read columns HC.. and normalise them
+#pragma unroll
+            for (int c = 0; c < HC; c += 32) tmem_ld<32>(t_addr + (uint32_t)(HC + c), vr + c);
+            if (gt == 0) tma_store_wait_read0();     // first half's store has read the staging tile
+            group_bar();
+            tmem_ld_wait();
+            if (mt == MT - 1) {
+              tc_fence_before();
+              mbar_arrive(tempty(g));
+            }
+#pragma unroll
+            for (int j = 0; j < HC; ++j)
+              v[j] = fmaf(__uint_as_float(vr[j]), scale, bias_ptr[HC + j]);
+          }
+#pragma unroll
+          for (int i = 0; i < HC / 8; ++i) {                       // 8 channels = 16 bytes per store
+            uint32_t pk[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = i * 8 + 2 * e;
+              float a0, a1;
+              if constexpr (!ABW) {
+                a0 = v[j] * r;
+                a1 = v[j + 1] * r;
+                if (act) {
+                  a0 = a0 > 0.f ? a0 : a0 * slope;
+                  a1 = a1 > 0.f ? a1 : a1 * slope;
+                }
+              } else if (pn) {   // da = r (u - p <p,u>/C)
+                const __nv_bfloat162 *h2 = reinterpret_cast<const __nv_bfloat162 *>(&yraw[i]);
                 const float2 yy = __bfloat1622float2(h2[e]);
-                const int j = i * 8 + 2 * e;
-                v[j] = rp * fmaf(-(yy.x > 0.f ? yy.x : yy.x * inv_slope), k, v[j]);
-                v[j + 1] = rp * fmaf(-(yy.y > 0.f ? yy.y : yy.y * inv_slope), k, v[j + 1]);
+                a0 = rp * fmaf(-(yy.x > 0.f ? yy.x : yy.x * inv_slope), kpu, v[j]);
+                a1 = rp * fmaf(-(yy.y > 0.f ? yy.y : yy.y * inv_slope), kpu, v[j + 1]);
+                v[j] = a0;
+                v[j + 1] = a1;
+              } else {
+                a0 = v[j];
+                a1 = v[j + 1];
               }
+              __nv_bfloat162 hh = __floats2bfloat162_rn(a0, a1);
+              pk[e] = *reinterpret_cast<uint32_t *>(&hh);
             }
+            const uint32_t off = (uint32_t)row * (uint32_t)row_b + (uint32_t)i * 16u;
+            *reinterpret_cast<uint4 *>(stage_ptr + swz(off, swz_bits)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           }
-          load_y(next_tile(sb, mt, 1));          // yraw / rp are free again: fetch the next tile's
-        }
-        if (et == 0) tma_store_wait_read0();       // staging buffer free again?
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        {
-          const int chunk_i = col0 / out_chunk;
-          const int cin_chunk = col0 - chunk_i * out_chunk;
-          uint8_t *tile_base = out_ptr + (size_t)chunk_i * 128 * chunk_rows_bytes;
+          if (h == 0 && !ABW && pn) p.r_out[pix] = r;
+          fence_proxy_async_smem();
+          group_bar();
+          if (gt == 0 && !(p.dbg & 1)) {
+            tma_store_4d(&tmap_y, stage_s, h * HC, w0, h0, n);
+            tma_store_commit();
+          }
+          if (!ABW && p.pool) {
+            // 2x2 average pool of the staged tile (the reference's bilinear x0.5,
+            // progan_modules.py:299): 32 pooled pixels x HC/8 16-byte chunks over 128 threads
+            constexpr int CH8 = HC / 8;
+            for (int item = gt; item < 32 * CH8; item += 128) {
+              const int pp = item / CH8, c8 = item - pp * CH8;
+              const int ph_ = pp >> 2, pw = pp & 3;
+              const uint32_t cb = (uint32_t)c8 * 16u;
+              float acc8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int i = 0; i < CPT / 8; ++i) {                      // 8 channels = 16 bytes per store
-            uint32_t pk[4];
+              for (int q4 = 0; q4 < 4; ++q4) {
+                const int srow = (2 * ph_ + (q4 >> 1)) * 8 + 2 * pw + (q4 & 1);
+                const uint4 raw = *reinterpret_cast<const uint4 *>(
+                    stage_ptr + swz((uint32_t)srow * (uint32_t)row_b + cb, swz_bits));
+                const __nv_bfloat162 *h2 = reinterpret_cast<const __nv_bfloat162 *>(&raw);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float a0 = v[i * 8 + 2 * e] * r, a1 = v[i * 8 + 2 * e + 1] * r;
-              if (!ABW && p.epi != PG_EPI_LINEAR) {
-                a0 = a0 > 0.f ? a0 : a0 * slope;
-                a1 = a1 > 0.f ? a1 : a1 * slope;
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = __bfloat1622float2(h2[e]);
+                  acc8[2 * e] += f.x;
+                  acc8[2 * e + 1] += f.y;
+                }
               }
-              __nv_bfloat162 h = __floats2bfloat162_rn(a0, a1);
-              pk[e] = *reinterpret_cast<uint32_t *>(&h);
-            }
-            const uint32_t off = (uint32_t)row * (uint32_t)chunk_rows_bytes +
-                                 (uint32_t)cin_chunk * 2u + (uint32_t)i * 16u;
-            *reinterpret_cast<uint4 *>(tile_base + swz(off, swz_bits)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          }
-        }
-        if (!ABW && p.epi == PG_EPI_PN_LRELU && part == 0) p.r_out[pix] = r;
-        fence_proxy_async_smem();
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (et == 0 && !(p.dbg & 1)) {
-#pragma unroll
-          for (int ch = 0; ch < n_chunks; ++ch)
-            tma_store_4d(&tmap_y, smem_out + (uint32_t)ch * 128u * (uint32_t)chunk_rows_bytes,
-                         ch * out_chunk, w0, h0, n);
-          tma_store_commit();
-        }
-        if (!ABW && p.pool) {
-          // 2x2 average pool of the staged tile (the reference's bilinear x0.5,
-          // progan_modules.py:299): 32 pooled pixels x COUT/8 16-byte chunks over 256 threads
-          constexpr int CH8 = COUT / 8;
-          for (int item = et; item < 32 * CH8; item += kC4EpiThreads) {
-            const int pp = item / CH8, c8 = item - pp * CH8;
-            const int ph = pp >> 2, pw = pp & 3;
-            const int chunk_i = (c8 * 8) / out_chunk;
-            const uint32_t cb = (uint32_t)((c8 * 8) % out_chunk) * 2u;
-            const uint8_t *tb = out_ptr + (size_t)chunk_i * 128 * chunk_rows_bytes;
-            float acc8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-              const int srow = (2 * ph + (q4 >> 1)) * 8 + 2 * pw + (q4 & 1);
-              const uint4 raw = *reinterpret_cast<const uint4 *>(
-                  tb + swz((uint32_t)srow * (uint32_t)chunk_rows_bytes + cb, swz_bits));
-              const __nv_bfloat162 *h2 = reinterpret_cast<const __nv_bfloat162 *>(&raw);
+              uint32_t pk[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const float2 f = __bfloat1622float2(h2[e]);
-                acc8[2 * e] += f.x;
-                acc8[2 * e + 1] += f.y;
+                __nv_bfloat162 hh = __floats2bfloat162_rn(0.25f * acc8[2 * e], 0.25f * acc8[2 * e + 1]);
+                pk[e] = *reinterpret_cast<uint32_t *>(&hh);
               }
+              *reinterpret_cast<uint4 *>(pool_g + swz((uint32_t)pp * (uint32_t)row_b + cb, swz_bits)) =
+                  make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
-            uint32_t pk[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              __nv_bfloat162 h = __floats2bfloat162_rn(0.25f * acc8[2 * e], 0.25f * acc8[2 * e + 1]);
-              pk[e] = *reinterpret_cast<uint32_t *>(&h);
+            fence_proxy_async_smem();
+            group_bar();
+            if (gt == 0 && !(p.dbg & 1)) {
+              tma_store_4d(&tmap_yp, pool_s, h * HC, w0 >> 1, h0 >> 1, n);
+              tma_store_commit();
             }
-            uint8_t *pb = pool_ptr + (size_t)chunk_i * 32 * chunk_rows_bytes;
-            *reinterpret_cast<uint4 *>(pb + swz((uint32_t)pp * (uint32_t)chunk_rows_bytes + cb, swz_bits)) =
-                make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          }
-          fence_proxy_async_smem();
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          if (et == 0 && !(p.dbg & 1)) {
-#pragma unroll
-            for (int ch = 0; ch < n_chunks; ++ch)
-              tma_store_4d(&tmap_yp, smem_pool + (uint32_t)ch * 32u * (uint32_t)chunk_rows_bytes,
-                           ch * out_chunk, w0 >> 1, h0 >> 1, n);
-            tma_store_commit();
           }
         }
         if (ABW && p.colsum != nullptr) {
           // per-channel sum over the warp's 32 pixels by a halving butterfly: each step trades
-          // half of the remaining channels with the partner lane (CPT - 1 shuffles in total)
-          int nrem = CPT;
+          // half of the remaining channels with the partner lane (HC - 1 shuffles in total)
+          int nrem = HC;
 #pragma unroll
           for (int off = 16; off >= 1; off >>= 1) {
             if (nrem >= 2) {
               const int hn = nrem / 2;
               const bool up = (lane & off) != 0;
 #pragma unroll
-              for (int j = 0; j < CPT / 2; ++j) {
+              for (int j = 0; j < HC / 2; ++j) {
                 if (j < hn) {
                   const float send = up ? v[j] : v[j + hn];
                   const float keep = up ? v[j + hn] : v[j];
@@ -542,16 +535,15 @@ conv4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
             }
           }
           csum[0] += v[0];
-          if (CPT >= 64) csum[1] += v[1];
+          if (HC >= 64) csum[1] += v[1];
         }
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
     if (ABW && p.colsum != nullptr) {
       // channel owned by this lane after the butterfly (bit b of the lane picked the upper half
       // at the step with offset 2^b)
-      int ch = col0;
-      int hn = CPT / 2;
+      int ch = 0;
+      int hn = HC / 2;
 #pragma unroll
       for (int off = 16; off >= 1; off >>= 1) {
         if (hn >= 1) {
@@ -559,16 +551,14 @@ conv4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           hn >>= 1;
         }
       }
-      if (CPT >= 64) {
+      if (HC >= 64) {
         atomicAdd(p.colsum + ch, csum[0]);
         atomicAdd(p.colsum + ch + 1, csum[1]);
-      } else if (CPT == 32) {
-        atomicAdd(p.colsum + ch, csum[0]);
-      } else if ((lane & 1) == 0) {         // CPT = 16: the last step was a plain add
+      } else {
         atomicAdd(p.colsum + ch, csum[0]);
       }
     }
-    if (et == 0) tma_store_wait_all();
+    if (gt == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -631,7 +621,7 @@ int conv4_tc_launch(const void *x, const void *wp, const float *bias, void *y, f
                     cudaStream_t stream, const void *y_prev, const float *r_prev, float *colsum,
                     int use_pn, void *y_pool) {
   const bool abw = y_prev != nullptr;
-  if (abw && y_pool) return PG_ERR_UNSUPPORTED;
+  if (abw && (y_pool || Cout > 64)) return PG_ERR_UNSUPPORTED;
   if (const char *e = getenv("PG_CONV_V4"))
     if (atoi(e) == 0) return PG_ERR_UNSUPPORTED;
   int min_h = 16;
@@ -653,7 +643,8 @@ int conv4_tc_launch(const void *x, const void *wp, const float *bias, void *y, f
   p.pool = y_pool != nullptr;
   p.dbg = 0;
   if (const char *e = getenv("PG_DBG")) p.dbg = atoi(e);
-  const int out_bytes = 128 * Cout * 2 + (y_pool ? 32 * Cout * 2 : 0);   // staging (+ pooled tile)
+  const int hc = Cout > 64 ? 64 : Cout;      // channels per staging tile; one tile per epilogue group
+  const int out_bytes = 2 * 128 * hc * 2 + (y_pool ? 2 * 32 * hc * 2 : 0);   // staging (+ pooled tiles)
   const int misc = 1024 + 8 * (2 * tc::kC4MaxA + 2 * tc::kC4MaxW + 5) + 16 + 16 + 128 * 4 + 2 * 128 * 4 + 64;
   const int budget = 227 * 1024 - out_bytes - misc;
   const int wres = 9 * p.ncb * p.wtile_bytes;

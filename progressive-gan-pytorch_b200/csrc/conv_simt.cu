@@ -48,6 +48,33 @@ pack_weight_multi_kernel(const PgPackEntry *__restrict__ table) {
   const PgPackEntry e = table[blockIdx.y];
   const int Cout = e.swap_io ? e.d1 : e.d0;
   const int Cin = e.swap_io ? e.d0 : e.d1;
+  if (e.layout != PG_WL_TAP_CI_CO && e.taps <= 16) {
+    // ci-fastest operand layouts (the tcgen05 kernels): one thread per (co, ci) pair reads the
+    // taps of its pair as ONE contiguous run of the parameter and writes one element per tap,
+    // coalesced over ci.  (One thread per output element read the parameter 4 bytes at a time,
+    // `taps` floats apart: 0.11 of HBM.)
+    const long long pairs = (long long)e.co_pad * e.ci_pad;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < pairs;
+         i += (long long)gridDim.x * blockDim.x) {
+      const int ci = (int)(i % e.ci_pad), co = (int)(i / e.ci_pad);
+      float v[16];
+      const bool ok = ci < Cin && co < Cout;
+      const float *src = e.w + (e.swap_io ? ((long long)ci * e.d1 + co) : ((long long)co * e.d1 + ci)) * e.taps;
+#pragma unroll
+      for (int t = 0; t < 16; ++t)
+        if (t < e.taps) v[t] = ok ? src[t] : 0.f;
+#pragma unroll
+      for (int t = 0; t < 16; ++t)
+        if (t < e.taps) {
+          const int tap = e.flip ? (e.taps - 1 - t) : t;          // parameter tap t -> operand tap
+          const long long o = e.layout == PG_WL_CO_TAP_CI ? ((long long)co * e.taps + tap) * e.ci_pad + ci
+                                                          : ((long long)tap * e.co_pad + co) * e.ci_pad + ci;
+          if (e.dtype == PG_BF16) stf(reinterpret_cast<__nv_bfloat16 *>(e.out) + o, v[t]);
+          else stf(reinterpret_cast<float *>(e.out) + o, v[t]);
+        }
+    }
+    return;
+  }
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < e.total;
        i += (long long)gridDim.x * blockDim.x) {
     int co, ci, tap;

@@ -205,17 +205,38 @@ adam_multi_kernel(float *__restrict__ p, const float *__restrict__ g, float *__r
   const float bc1 = 1.f - powf(b1, t);
   const float bc2_sqrt = sqrtf(1.f - powf(b2, t));
   const float step_size = lr / bc1;
-  for (int i = threadIdx.x; i < c.y; i += blockDim.x) {
-    const long long j = (long long)c.x + i;
-    const float gi = g[j] * grad_scale;
-    float mi = gi;
-    if (m) {
-      mi = b1 * m[j] + (1.f - b1) * gi;
-      m[j] = mi;
+  // four independent elements per thread and iteration, every load issued before the arithmetic
+  // (one element per iteration left a single 4-byte load in flight per thread: 0.29 of HBM)
+  constexpr int UN = 4;
+  for (int i0 = threadIdx.x; i0 < c.y; i0 += blockDim.x * UN) {
+    float gi[UN], vi[UN], pi[UN], mi[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int i = i0 + u * blockDim.x;
+      if (i < c.y) {
+        const long long j = (long long)c.x + i;
+        gi[u] = g[j];
+        vi[u] = v[j];
+        pi[u] = p[j];
+        mi[u] = m ? m[j] : 0.f;
+      }
     }
-    const float vi = b2 * v[j] + (1.f - b2) * gi * gi;
-    v[j] = vi;
-    p[j] = p[j] - step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int i = i0 + u * blockDim.x;
+      if (i < c.y) {
+        const long long j = (long long)c.x + i;
+        const float gs = gi[u] * grad_scale;
+        float mm = gs;
+        if (m) {
+          mm = b1 * mi[u] + (1.f - b1) * gs;
+          m[j] = mm;
+        }
+        const float vv = b2 * vi[u] + (1.f - b2) * gs * gs;
+        v[j] = vv;
+        p[j] = pi[u] - step_size * (mm / (sqrtf(vv) / bc2_sqrt + eps));
+      }
+    }
   }
 }
 }  // namespace pg

@@ -16,7 +16,7 @@ constexpr int kMaxK = 4;
 // long long for tensors with more than 2^31 elements.
 template <typename T, typename I>
 __global__ void __launch_bounds__(256)
-pw_expand_kernel(const float *__restrict__ img, const float *__restrict__ w,
+pw_expand_generic_kernel(const float *__restrict__ img, const float *__restrict__ w,
                  const float *__restrict__ bias, T *__restrict__ act, int N, I HW,
                  int K, int C, int w_sc, int w_sk, float scale) {
   extern __shared__ float sw[];  // [K][C] then bias[C]
@@ -91,7 +91,7 @@ pw_expand_kernel(const float *__restrict__ img, const float *__restrict__ w,
 // issued before the arithmetic.
 template <typename T, int TPP, typename I, int CPL>
 __global__ void __launch_bounds__(256)
-pw_reduce_kernel(const T *__restrict__ act, const float *__restrict__ w,
+pw_reduce_generic_kernel(const T *__restrict__ act, const float *__restrict__ w,
                  const float *__restrict__ bias, float *__restrict__ img, int N, I HW,
                  int K, int C, int w_sc, int w_sk, float scale) {
   extern __shared__ float sw[];  // [K][C]
@@ -180,7 +180,7 @@ pw_reduce_kernel(const T *__restrict__ act, const float *__restrict__ w,
 // dw(c,k) += scale * sum_pix act[pix,c] * img[k,pix]
 template <typename T, typename I>
 __global__ void __launch_bounds__(256)
-pw_wgrad_kernel(const T *__restrict__ act, const float *__restrict__ img,
+pw_wgrad_generic_kernel(const T *__restrict__ act, const float *__restrict__ img,
                 float *__restrict__ dw, int N, I HW, int K, int C, int w_sc, int w_sk,
                 float scale) {
   extern __shared__ float sm[];  // [rows][K][C]
@@ -241,6 +241,274 @@ pw_wgrad_kernel(const T *__restrict__ act, const float *__restrict__ img,
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Warp-run forms (C = 8 * LPP * NCK channels, LPP = lanes per pixel in {1,2,4,8,16,32}): a warp
+// owns a run of 32 consecutive pixels.  On the image side lane l touches pixel l of the run
+// (one coalesced 128-byte access per image plane); on the activation side the warp moves
+// 512 contiguous bytes per instruction (32 / LPP pixels x LPP 16-byte chunks) and the
+// per-pixel image values travel between the two mappings by warp shuffles.  No integer
+// division per element (one per lane per run), weights in registers, every load of a batch
+// issued before the arithmetic.  (The generic kernels above gave each thread one 16-byte chunk
+// with its own strided image loads and ran at 0.3 of the HBM roofline.)
+template <typename T, int LPP, int NCK>
+__global__ void __launch_bounds__(256)
+pw_expand_kernel(const float *__restrict__ img, const float *__restrict__ w,
+                 const float *__restrict__ bias, T *__restrict__ act, int N, long long HW,
+                 int K, int w_sc, int w_sk, float scale) {
+  constexpr int C = 8 * LPP * NCK;
+  constexpr int PPW = 32 / LPP;                 // pixels per store instruction
+  __shared__ float sw[NCK > 1 ? (kMaxK + 1) * C : 1];
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LPP, slot = lane / LPP;
+  float wr[kMaxK][8], br[8];
+  if (NCK == 1) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      br[e] = bias ? bias[sub * 8 + e] : 0.f;
+#pragma unroll
+      for (int k = 0; k < kMaxK; ++k)
+        wr[k][e] = (k < K) ? w[(long long)(sub * 8 + e) * w_sc + (long long)k * w_sk] * scale : 0.f;
+    }
+  } else {
+    for (int i = threadIdx.x; i < kMaxK * C; i += blockDim.x) {
+      const int k = i / C, c = i - k * C;
+      sw[i] = (k < K) ? w[(long long)c * w_sc + (long long)k * w_sk] * scale : 0.f;
+    }
+    for (int c = threadIdx.x; c < C; c += blockDim.x) sw[kMaxK * C + c] = bias ? bias[c] : 0.f;
+    __syncthreads();
+  }
+  const long long P = (long long)N * HW;
+  const long long runs = (P + 31) >> 5;
+  const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  constexpr int UN = 2;                          // runs in flight per warp
+  for (long long run0 = warp0; run0 < runs; run0 += nwarps * UN) {
+    float xk[UN][kMaxK];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const long long pix = ((run0 + (long long)u * nwarps) << 5) + lane;
+      const bool ok = pix < P;
+      const long long n = ok ? pix / HW : 0;
+      const long long hw = pix - n * HW;
+#pragma unroll
+      for (int k = 0; k < kMaxK; ++k) xk[u][k] = (ok && k < K) ? img[(n * K + k) * HW + hw] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const long long base = (run0 + (long long)u * nwarps) << 5;
+#pragma unroll
+      for (int j = 0; j < LPP; ++j) {
+        const int pl = j * PPW + slot;
+        float xs[kMaxK];
+#pragma unroll
+        for (int k = 0; k < kMaxK; ++k) xs[k] = __shfl_sync(0xffffffffu, xk[u][k], pl);
+        const long long pp = base + pl;
+        if (pp < P) {
+#pragma unroll
+          for (int ck = 0; ck < NCK; ++ck) {
+            const int cg = sub + ck * LPP;
+            F8 o;
+            if (NCK == 1) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                float v = br[e];
+#pragma unroll
+                for (int k = 0; k < kMaxK; ++k) v = fmaf(xs[k], wr[k][e], v);
+                o.v[e] = v;
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                float v = sw[kMaxK * C + cg * 8 + e];
+#pragma unroll
+                for (int k = 0; k < kMaxK; ++k) v = fmaf(xs[k], sw[k * C + cg * 8 + e], v);
+                o.v[e] = v;
+              }
+            }
+            st8(act + pp * C + cg * 8, o);
+          }
+        }
+      }
+    }
+  }
+}
+
+template <typename T, int LPP, int NCK>
+__global__ void __launch_bounds__(256)
+pw_reduce_kernel(const T *__restrict__ act, const float *__restrict__ w,
+                 const float *__restrict__ bias, float *__restrict__ img, int N, long long HW,
+                 int K, int w_sc, int w_sk, float scale) {
+  constexpr int C = 8 * LPP * NCK;
+  constexpr int PPW = 32 / LPP;
+  constexpr int RB = (LPP * NCK <= 8) ? LPP : (8 / NCK > 0 ? 8 / NCK : 1);   // rounds per load batch
+  __shared__ float sw[NCK > 1 ? kMaxK * C : 1];
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LPP, slot = lane / LPP;
+  float wr[kMaxK][8];
+  if (NCK == 1) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+#pragma unroll
+      for (int k = 0; k < kMaxK; ++k)
+        wr[k][e] = (k < K) ? w[(long long)(sub * 8 + e) * w_sc + (long long)k * w_sk] * scale : 0.f;
+  } else {
+    for (int i = threadIdx.x; i < kMaxK * C; i += blockDim.x) {
+      const int k = i / C, c = i - k * C;
+      sw[i] = (k < K) ? w[(long long)c * w_sc + (long long)k * w_sk] * scale : 0.f;
+    }
+    __syncthreads();
+  }
+  float bk[kMaxK];
+#pragma unroll
+  for (int k = 0; k < kMaxK; ++k) bk[k] = (bias && k < K) ? bias[k] : 0.f;
+  const long long P = (long long)N * HW;
+  const long long runs = (P + 31) >> 5;
+  const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long run = warp0; run < runs; run += nwarps) {
+    const long long base = run << 5;
+    float keep[kMaxK];
+#pragma unroll
+    for (int k = 0; k < kMaxK; ++k) keep[k] = 0.f;
+#pragma unroll
+    for (int j0 = 0; j0 < LPP; j0 += RB) {
+      typename RawOf<T>::type raw[RB][NCK];
+#pragma unroll
+      for (int jj = 0; jj < RB; ++jj) {
+        const long long pp = base + (j0 + jj) * PPW + slot;
+#pragma unroll
+        for (int ck = 0; ck < NCK; ++ck)
+          if (pp < P) raw[jj][ck] = ldraw8(act + pp * C + (sub + ck * LPP) * 8);
+      }
+#pragma unroll
+      for (int jj = 0; jj < RB; ++jj) {
+        const int j = j0 + jj;
+        const long long pp = base + j * PPW + slot;
+        float acc[kMaxK];
+#pragma unroll
+        for (int k = 0; k < kMaxK; ++k) acc[k] = 0.f;
+        if (pp < P) {
+#pragma unroll
+          for (int ck = 0; ck < NCK; ++ck) {
+            const F8 v = unpack8(raw[jj][ck]);
+            if (NCK == 1) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+#pragma unroll
+                for (int k = 0; k < kMaxK; ++k) acc[k] = fmaf(v.v[e], wr[k][e], acc[k]);
+            } else {
+              const int cg = sub + ck * LPP;
+#pragma unroll
+              for (int k = 0; k < kMaxK; ++k)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[k] = fmaf(v.v[e], sw[k * C + cg * 8 + e], acc[k]);
+            }
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < kMaxK; ++k) {
+#pragma unroll
+          for (int o = LPP / 2; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+          // pixel j*PPW + s of the run was summed by the lanes of slot s: hand it to lane j*PPW + s
+          const float t = __shfl_sync(0xffffffffu, acc[k], (lane % PPW) * LPP);
+          if (lane / PPW == j) keep[k] = t;
+        }
+      }
+    }
+    const long long pix = base + lane;
+    if (pix < P) {
+      const long long n = pix / HW, hw = pix - n * HW;
+#pragma unroll
+      for (int k = 0; k < kMaxK; ++k)
+        if (k < K) img[(n * K + k) * HW + hw] = keep[k] + bk[k];
+    }
+  }
+}
+
+// dw(c,k) += scale * sum_pix act[pix,c] * img[k,pix];  dbias(c) += sum_pix act[pix,c] (optional:
+// the bias gradient of a from_rgb layer rides on the same pass over its output gradient)
+template <typename T, int LPP>
+__global__ void __launch_bounds__(256)
+pw_wgrad_kernel(const T *__restrict__ act, const float *__restrict__ img, float *__restrict__ dw,
+                float *__restrict__ dbias, int N, long long HW, int K, int w_sc, int w_sk,
+                float scale) {
+  constexpr int C = 8 * LPP;
+  constexpr int PPW = 32 / LPP;
+  constexpr int RB = LPP <= 8 ? LPP : 8;
+  __shared__ float sm[8][kMaxK + 1][C];          // per-warp partial sums
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int sub = lane % LPP, slot = lane / LPP;
+  float acc[kMaxK + 1][8];
+#pragma unroll
+  for (int k = 0; k <= kMaxK; ++k)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[k][e] = 0.f;
+  const long long P = (long long)N * HW;
+  const long long runs = (P + 31) >> 5;
+  const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + wid;
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long run = warp0; run < runs; run += nwarps) {
+    const long long base = run << 5;
+    const long long pix = base + lane;
+    const bool ok = pix < P;
+    const long long n = ok ? pix / HW : 0;
+    const long long hw = pix - n * HW;
+    float gk[kMaxK];
+#pragma unroll
+    for (int k = 0; k < kMaxK; ++k) gk[k] = (ok && k < K) ? img[(n * K + k) * HW + hw] : 0.f;
+#pragma unroll
+    for (int j0 = 0; j0 < LPP; j0 += RB) {
+      typename RawOf<T>::type raw[RB];
+#pragma unroll
+      for (int jj = 0; jj < RB; ++jj) {
+        const long long pp = base + (j0 + jj) * PPW + slot;
+        if (pp < P) raw[jj] = ldraw8(act + pp * C + sub * 8);
+      }
+#pragma unroll
+      for (int jj = 0; jj < RB; ++jj) {
+        const int pl = (j0 + jj) * PPW + slot;
+        float g[kMaxK];
+#pragma unroll
+        for (int k = 0; k < kMaxK; ++k) g[k] = __shfl_sync(0xffffffffu, gk[k], pl);
+        if (base + pl < P) {
+          const F8 v = unpack8(raw[jj]);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+#pragma unroll
+            for (int k = 0; k < kMaxK; ++k) acc[k][e] = fmaf(v.v[e], g[k], acc[k][e]);
+            acc[kMaxK][e] += v.v[e];
+          }
+        }
+      }
+    }
+  }
+  // lanes with the same `sub` hold partial sums of the same channels
+#pragma unroll
+  for (int k = 0; k <= kMaxK; ++k)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+#pragma unroll
+      for (int o = LPP; o < 32; o <<= 1) acc[k][e] += __shfl_xor_sync(0xffffffffu, acc[k][e], o);
+    }
+  if (slot == 0) {
+#pragma unroll
+    for (int k = 0; k <= kMaxK; ++k)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sm[wid][k][sub * 8 + e] = acc[k][e];
+  }
+  __syncthreads();
+  const int nw = blockDim.x >> 5;
+  for (int i = threadIdx.x; i < (kMaxK + 1) * C; i += blockDim.x) {
+    const int k = i / C, c = i - k * C;
+    if (k < K || (k == kMaxK && dbias)) {
+      float s = 0.f;
+      for (int r = 0; r < nw; ++r) s += sm[r][k][c];
+      if (k < K) atomicAdd(dw + (long long)c * w_sc + (long long)k * w_sk, s * scale);
+      else atomicAdd(dbias + c, s);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 img_chansum_kernel(const float *__restrict__ img, float *__restrict__ out, int N, long long HW,
                    int K) {
@@ -269,21 +537,56 @@ static int check_pw(const char *name, int N, long long HW, int K, int C) {
   return PG_OK;
 }
 
+// (LPP, NCK) of the warp-run kernels for C channels, or false when C is not served by them
+static bool pw_shape(int C, int *lpp, int *nck) {
+  const int nch = C / 8;
+  if (nch <= 32) {
+    if (nch & (nch - 1)) return false;
+    *lpp = nch; *nck = 1;
+    return true;
+  }
+  if (nch == 64 || nch == 128) { *lpp = 32; *nck = nch / 32; return true; }
+  return false;
+}
+
+#define PG_PW_DISPATCH_LPP(lpp, MACRO)                                                     \
+  switch (lpp) {                                                                           \
+    case 1: MACRO(1, 1) break;                                                             \
+    case 2: MACRO(2, 1) break;                                                             \
+    case 4: MACRO(4, 1) break;                                                             \
+    case 8: MACRO(8, 1) break;                                                             \
+    case 16: MACRO(16, 1) break;                                                           \
+    default: MACRO(32, 1) break;                                                           \
+  }
+
 extern "C" int pg_pw_expand(const float *img, const float *w, const float *bias, void *act, int N,
                             long long HW, int K, int C, int w_sc, int w_sk, float scale,
                             int dtype, void *stream) {
   PG_CHECK_ARG(img && w && act, "pg_pw_expand: null pointer");
   if (int rc = check_pw("pg_pw_expand", N, HW, K, C)) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  int lpp = 0, nck = 0;
+  if (pw_shape(C, &lpp, &nck)) {
+    const int grid = bw_grid(((long long)N * HW + 31) / 32, 8 * 2);   // 8 warps x 2 runs per block pass
+#define PG_PWE(L, NC) pw_expand_kernel<T, L, NC><<<grid, 256, 0, s>>>(img, w, bias, (T *)act, N, HW, K, w_sc, w_sk, scale);
+    PG_DISPATCH_DTYPE(dtype, T, {
+      if (nck == 1) { PG_PW_DISPATCH_LPP(lpp, PG_PWE) }
+      else if (nck == 2) { PG_PWE(32, 2) }
+      else { PG_PWE(32, 4) }
+    });
+#undef PG_PWE
+    PG_CHECK_LAUNCH("pg_pw_expand");
+  }
   const long long total = (long long)N * HW * (C / 8);
   const int grid = bw_grid(total, 256);
   const size_t smem = (size_t)(K + 1) * C * sizeof(float);
   const bool small = total + (long long)grid * 256 < (1ll << 31);
   PG_DISPATCH_DTYPE(dtype, T, {
     if (small)
-      pw_expand_kernel<T, unsigned><<<grid, 256, smem, (cudaStream_t)stream>>>(
+      pw_expand_generic_kernel<T, unsigned><<<grid, 256, smem, s>>>(
           img, w, bias, (T *)act, N, (unsigned)HW, K, C, w_sc, w_sk, scale);
     else
-      pw_expand_kernel<T, long long><<<grid, 256, smem, (cudaStream_t)stream>>>(
+      pw_expand_generic_kernel<T, long long><<<grid, 256, smem, s>>>(
           img, w, bias, (T *)act, N, HW, K, C, w_sc, w_sk, scale);
   });
   PG_CHECK_LAUNCH("pg_pw_expand");
@@ -295,17 +598,29 @@ extern "C" int pg_pw_reduce(const void *act, const float *w, const float *bias, 
   PG_CHECK_ARG(img && w && act, "pg_pw_reduce: null pointer");
   if (int rc = check_pw("pg_pw_reduce", N, HW, K, C)) return rc;
   const int nch = C / 8;
-  const size_t smem = (size_t)K * C * sizeof(float);
   const long long P = (long long)N * HW;
   cudaStream_t s = (cudaStream_t)stream;
+  int lpp = 0, nck = 0;
+  if (pw_shape(C, &lpp, &nck)) {
+    const int grid = bw_grid((P + 31) / 32, 8);
+#define PG_PWR(L, NC) pw_reduce_kernel<T, L, NC><<<grid, 256, 0, s>>>((const T *)act, w, bias, img, N, HW, K, w_sc, w_sk, scale);
+    PG_DISPATCH_DTYPE(dtype, T, {
+      if (nck == 1) { PG_PW_DISPATCH_LPP(lpp, PG_PWR) }
+      else if (nck == 2) { PG_PWR(32, 2) }
+      else { PG_PWR(32, 4) }
+    });
+#undef PG_PWR
+    PG_CHECK_LAUNCH("pg_pw_reduce");
+  }
+  const size_t smem = (size_t)K * C * sizeof(float);
 #define PG_LAUNCH_PWR(TPP, CPL)                                                             \
   {                                                                                         \
     const int grid = bw_grid(P, 256 / TPP);                                                 \
     if (P + (long long)grid * 256 < (1ll << 31))                                            \
-      pw_reduce_kernel<T, TPP, unsigned, CPL><<<grid, 256, smem, s>>>(                      \
+      pw_reduce_generic_kernel<T, TPP, unsigned, CPL><<<grid, 256, smem, s>>>(              \
           (const T *)act, w, bias, img, N, (unsigned)HW, K, C, w_sc, w_sk, scale);          \
     else                                                                                    \
-      pw_reduce_kernel<T, TPP, long long, CPL><<<grid, 256, smem, s>>>(                     \
+      pw_reduce_generic_kernel<T, TPP, long long, CPL><<<grid, 256, smem, s>>>(             \
           (const T *)act, w, bias, img, N, HW, K, C, w_sc, w_sk, scale);                    \
   }
   PG_DISPATCH_DTYPE(dtype, T, {
@@ -321,25 +636,45 @@ extern "C" int pg_pw_reduce(const void *act, const float *w, const float *bias, 
   PG_CHECK_LAUNCH("pg_pw_reduce");
 }
 
-extern "C" int pg_pw_wgrad(const void *act, const float *img, float *dw, int N, long long HW,
-                           int K, int C, int w_sc, int w_sk, float scale, int dtype,
+extern "C" int pg_colsum(const void *x, float *out, long long P, int C, int dtype, void *stream);
+
+extern "C" int pg_pw_wgrad(const void *act, const float *img, float *dw, float *dbias, int N,
+                           long long HW, int K, int C, int w_sc, int w_sk, float scale, int dtype,
                            void *stream) {
   PG_CHECK_ARG(img && dw && act, "pg_pw_wgrad: null pointer");
   if (int rc = check_pw("pg_pw_wgrad", N, HW, K, C)) return rc;
   const int nch = C / 8;
+  const long long P = (long long)N * HW;
+  cudaStream_t s = (cudaStream_t)stream;
+  int lpp = 0, nck = 0;
+  if (pw_shape(C, &lpp, &nck) && nck == 1) {
+    // few enough blocks that the final atomics stay cheap, enough warps to cover the HBM latency
+    const int grid = bw_grid((P + 31) / 32, 8 * 4, 4);
+#define PG_PWW(L, NC) pw_wgrad_kernel<T, L><<<grid, 256, 0, s>>>((const T *)act, img, dw, dbias, N, HW, K, w_sc, w_sk, scale);
+    PG_DISPATCH_DTYPE(dtype, T, { PG_PW_DISPATCH_LPP(lpp, PG_PWW) });
+#undef PG_PWW
+    PG_CHECK_LAUNCH("pg_pw_wgrad");
+  }
   const int rows = 256 / nch;
   PG_CHECK_ARG(rows >= 1, "pg_pw_wgrad: C too large");
-  const long long P = (long long)N * HW;
   const int grid = bw_grid(P, rows * 16, 4);
   const size_t smem = (size_t)rows * K * C * sizeof(float);
   PG_DISPATCH_DTYPE(dtype, T, {
     if (P + (long long)grid * 256 < (1ll << 31))
-      pw_wgrad_kernel<T, unsigned><<<grid, 256, smem, (cudaStream_t)stream>>>(
+      pw_wgrad_generic_kernel<T, unsigned><<<grid, 256, smem, s>>>(
           (const T *)act, img, dw, N, (unsigned)HW, K, C, w_sc, w_sk, scale);
     else
-      pw_wgrad_kernel<T, long long><<<grid, 256, smem, (cudaStream_t)stream>>>(
+      pw_wgrad_generic_kernel<T, long long><<<grid, 256, smem, s>>>(
           (const T *)act, img, dw, N, HW, K, C, w_sc, w_sk, scale);
   });
+  if (dbias) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      set_error("pg_pw_wgrad: CUDA launch failed: %s", cudaGetErrorString(e));
+      return PG_ERR_CUDA;
+    }
+    return pg_colsum(act, dbias, P, C, dtype, stream);
+  }
   PG_CHECK_LAUNCH("pg_pw_wgrad");
 }
 

@@ -288,8 +288,8 @@ class ActBwd(Function):
             cot_a = None
         elif DIRECT_GRADS:
             node = ctx.act_node
-            fusable = node is not None and node.link is not None and \
-                getattr(K(), "fuse_actbwd_min_cout", 1 << 30) <= 128     # pass-through Act: no stash
+            fus = getattr(K(), "actbwd_fusable", None)       # pass-through Act: no stash
+            fusable = node is not None and node.link is not None and fus is not None and fus(A)
             if (STASH_SECOND_ORDER and node is not None and not fusable
                     and torch._C._will_engine_execute_node(node)):
                 # the Act node of this layer runs later in this sweep (it receives the chain
@@ -335,14 +335,23 @@ class PwFwd(Function):
         other = "reduce" if kind == "expand" else "expand"
         if ctx.needs_input_grad[0]:
             dx = PwFwd.apply(dy, w, None, other, C, Kc, w_sc, w_sk, scale, act_dtype)
+        bias_done = False
         if _wants_grad(ctx, 1, w):
             act, img = (dy, x) if kind == "expand" else (x, dy)
             tgt = _direct_target(w)
             if tgt is not None:
-                K().pw_wgrad(act, img, tuple(w.shape), w_sc, w_sk, scale, out=tgt)
+                # from_rgb: the bias gradient (column sum of dy) rides on the same pass over dy
+                tgt_b = None
+                if kind == "expand" and b is not None and _wants_grad(ctx, 2, b):
+                    tgt_b = _direct_target(b)
+                if tgt_b is not None:
+                    K().pw_wgrad(act, img, tuple(w.shape), w_sc, w_sk, scale, out=tgt, bias_out=tgt_b)
+                    bias_done = True
+                else:
+                    K().pw_wgrad(act, img, tuple(w.shape), w_sc, w_sk, scale, out=tgt)
             else:
                 dw = PwWgrad.apply(act, img, tuple(w.shape), C, Kc, w_sc, w_sk, scale, act_dtype)
-        if b is not None and _wants_grad(ctx, 2, b):
+        if b is not None and not bias_done and _wants_grad(ctx, 2, b):
             tgt = _direct_target(b)
             if tgt is not None:
                 (K().colsum if kind == "expand" else K().img_chansum)(dy, out=tgt)

@@ -104,10 +104,10 @@ class CudaKernels:
         self.launches = 0              # kernels launched through this shim (bench `gpu_launches`)
         self._packs = {}               # id(param) -> [weakref, version, {variant: (tensor, pack args)}]
         self._pack_tables = {}         # ids of a parameter set -> (signature, device table, n)
-        # measured (profiles/dbg_actbwd.py): in isolation the fused epilogue wins for 128 output
-        # channels (long MMA phase per tile) and loses for <= 64 (the 8 epilogue warps become the
-        # bottleneck)
-        self.fuse_actbwd_min_cout = 1 << 30      # ... and in the whole step neither pays: off
+        # data-gradient convs whose epilogue also applies the PixelNorm/LeakyReLU backward of the
+        # layer in front (one thread per pixel row in the conv4 epilogue): layers of 32 / 64 channels
+        # at >= 16 px; 1 << 30 turns the fusion off
+        self.fuse_actbwd_min_cout = 32
         self.wgrad_side_stream = None  # Trainer: deferred weight gradients run on this stream, next
         self._side_dirty = set()       # to the bandwidth-bound kernels of the data-gradient chain
         self._side_streams = {}        # one side stream per forking stream
@@ -293,12 +293,10 @@ class CudaKernels:
         if x.dtype != torch.bfloat16 or op.xpad or op.ypad:
             return None
         N, H, W, C = x.shape
-        if self.tc_mode(x.dtype, H, W, w.shape, op) != "conv3" or H % 16 or W % 8:
+        if self.tc_mode(x.dtype, H, W, w.shape, op) != "conv3":
             return None
         cin, cout = op.cin_phys(w.shape), op.cout_phys(w.shape)
-        if cout not in (32, 64, 128) or C != cin or tuple(y_prev.shape) != (N, H, W, cout):
-            return None
-        if cout < self.fuse_actbwd_min_cout:
+        if C != cin or tuple(y_prev.shape) != (N, H, W, cout) or not self.actbwd_fusable(y_prev):
             return None
         _chk(x, "x", torch.bfloat16, 4)
         _chk(y_prev, "y_prev", torch.bfloat16, 4)
@@ -317,6 +315,14 @@ class CudaKernels:
                 return None
             raise
         return da
+
+    def actbwd_fusable(self, y):
+        """Is the backward of this stored activation [N,H,W,C] served by the fused data-gradient
+        epilogue (pg_conv_tc_actbwd)?"""
+        if self.conv_impl != "tc" or y.dtype != torch.bfloat16 or y.dim() != 4:
+            return False
+        _, H, W, C = y.shape
+        return C in (32, 64) and C >= self.fuse_actbwd_min_cout and H % 16 == 0 and W % 8 == 0
 
     def conv_wgrad(self, x, dy, wshape, op, scale, out=None):
         """dw[wshape] = scale * sum_pix dy (x) x for the conv `op` (fp32).  out: accumulate into
@@ -524,14 +530,20 @@ class CudaKernels:
                    Kc, C, w_sc, w_sk, float(scale), _dt(act), self._stream())
         return img
 
-    def pw_wgrad(self, act, img, wshape, w_sc, w_sk, scale, out=None):
+    def pw_wgrad(self, act, img, wshape, w_sc, w_sk, scale, out=None, bias_out=None):
+        """dw (+= into `out`); bias_out: fp32 [C] that additionally receives the per-channel sum of
+        `act` (the bias gradient of a from_rgb layer) from the same pass."""
         _chk(act, "act", ndim=4)
         _chk(img, "img", torch.float32, 4)
         N, H, W, C = act.shape
         Kc = img.shape[1]
+        if bias_out is not None:
+            _chk(bias_out, "bias_out", torch.float32, 1)
+            if bias_out.numel() != C:
+                raise RuntimeError("progan_b200: pw_wgrad bias_out must have %d elements" % C)
         dw = out if out is not None else torch.zeros(tuple(wshape), device=act.device, dtype=torch.float32)
-        self._call("pg_pw_wgrad", act.data_ptr(), img.data_ptr(), dw.data_ptr(), N, H * W, Kc, C,
-                   w_sc, w_sk, float(scale), _dt(act), self._stream())
+        self._call("pg_pw_wgrad", act.data_ptr(), img.data_ptr(), dw.data_ptr(), _ptr(bias_out), N, H * W,
+                   Kc, C, w_sc, w_sk, float(scale), _dt(act), self._stream())
         return dw
 
     def img_chansum(self, img, out=None):

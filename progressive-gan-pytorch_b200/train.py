@@ -30,7 +30,7 @@ import torch.distributed as dist
 from . import functions as F_
 from .kernels import get_kernels
 
-_CHUNK = 8192
+_CHUNK = 2048          # elements per block of the multi-tensor Adam kernel (8 per thread)
 
 
 def _d_groups(D):

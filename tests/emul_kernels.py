@@ -179,10 +179,12 @@ class EmulKernels:
             out = out + bias.to(cd).view(1, -1, 1, 1)
         return out.contiguous()
 
-    def pw_wgrad(self, act, img, wshape, w_sc, w_sk, scale, out=None):
+    def pw_wgrad(self, act, img, wshape, w_sc, w_sk, scale, out=None, bias_out=None):
         self.launches += 1
         C, Kc = act.shape[-1], img.shape[1]
         cd = img.dtype
+        if bias_out is not None:
+            bias_out.add_(act.to(cd).reshape(-1, C).sum(0).to(bias_out.dtype))
         dck = torch.einsum('nhwc,nkhw->ck', act.to(cd), img) * scale
         dw = torch.zeros(wshape, dtype=cd, device=img.device)
         idx = (torch.arange(C, device=img.device).view(C, 1) * w_sc
