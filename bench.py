@@ -33,12 +33,34 @@ def step_flops(res):
 
 
 def peaks():
+    """(burst bf16 TF/s, sustained bf16 TF/s, HBM GB/s, provenance)."""
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             p = json.load(f)
-        return p["bf16_tflops_sustained"], p["hbm_gbs"], "measured (MEASURED_PEAKS.json, sustained bf16)"
+        return p["bf16_tflops"], p["bf16_tflops_sustained"], p["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
     except Exception:
-        return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+        return 1590.0, 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def file_sha16(path):
+    import hashlib
+    with open(path, "rb") as f:
+        return hashlib.sha256(f.read()).hexdigest()[:16]
+
+
+def ncu_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full summary
+    (profiles/r2/conv4_ncu_summary.json) — only when that capture was taken from the kernel
+    source this process runs (sha of csrc/conv4_tc.cu), else None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2", "conv4_ncu_summary.json")) as f:
+            rec = json.load(f)
+        src = os.path.join(ROOT, "progressive-gan-pytorch_b200", "csrc", "conv4_tc.cu")
+        if rec.get("conv4_tc_cu_sha16") != file_sha16(src):
+            return None, "profiles/r2/conv4_ncu_summary.json is from another build of conv4_tc.cu"
+        return rec["dram_bytes_per_launch"], rec.get("note", "")
+    except Exception as e:                                     # noqa: BLE001
+        return None, "no ncu summary (%s)" % type(e).__name__
 
 
 class ClockSampler(threading.Thread):
@@ -159,16 +181,27 @@ def run_product(args):
     orig_call = K._call
 
     def timed_conv_call(name, *a):
+        dims = None         # (N, H, W, Cin, Cout) of a launch served by conv4_tc_kernel
         if name == "pg_conv_tc" and a[11] == 9 and a[6] % 16 == 0 and a[7] % 8 == 0 and a[9] == a[10] \
                 and a[10] in (32, 64, 128):
+            dims = a[5:10]
+        elif name == "pg_conv_tc_actbwd":            # data-gradient conv with the fused act-backward
+            dims = a[3:8]
+        if dims is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            orig_call(name, *a)                      # the launch that belongs to the iteration
+            if name == "pg_conv_tc_actbwd":
+                cs_ptr = a[13]                       # the repeats must not add to the bias gradient
+                a = a[:13] + (None,) + a[14:]
+                orig_call(name, *(a[:13] + (cs_ptr,) + a[14:]))
+            else:
+                orig_call(name, *a)                  # the launch that belongs to the iteration
             e0.record()
             for _ in range(3):
                 orig_call(name, *a)
             e1.record()
             K.launches -= 3
-            conv_recs.append((2.0 * a[5] * a[6] * a[7] * a[8] * a[9] * 9, e0, e1))
+            n_, h_, w_, ci_, co_ = dims
+            conv_recs.append((2.0 * n_ * h_ * w_ * ci_ * co_ * 9, e0, e1))
         else:
             orig_call(name, *a)
 
@@ -185,6 +218,15 @@ def run_product(args):
     eager_launches = K.launches - K2
     conv_flops = sum(f for f, _, _ in conv_recs)
     conv_ms = sum(e0.elapsed_time(e1) / 3.0 for _, e0, e1 in conv_recs)
+    # data-parallel correctness on the real NCCL path: after the timed steps every rank must hold
+    # bit-identical parameters (same all-reduced gradients -> same Adam/EMA updates)
+    replicas = None
+    if world > 1:
+        sums = torch.stack([tr.bD.p.double().sum(), tr.bG.p.double().sum(), tr.bR.p.double().sum(),
+                            tr.bD.p.double().abs().sum(), tr.bG.p.double().abs().sum()])
+        allsums = [torch.empty_like(sums) for _ in range(world)]
+        dist.all_gather(allsums, sums)
+        replicas = all(torch.equal(allsums[0], t) for t in allsums)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -192,7 +234,6 @@ def run_product(args):
     imgs = B * world * args.steps
     value = imgs / (ms / 1e3)
     e2e = imgs / (ms_e2e / 1e3)
-    peak_tf, peak_hbm, which = peaks()
     achieved_tf = (value / world) * step_flops(res) / 1e12
     h2d = real_h.numel() * 4 + z_h.numel() * 4 + eps_h.numel() * 4
     line = {
@@ -203,81 +244,115 @@ def run_product(args):
         "config": {"workload": "train.py CelebA-shape G(128,128)/D(128) step %d (%dpx) alpha=%.2f "
                                "batch %d/GPU, full iteration incl. Adam+EMA" % (step, res, alpha, B),
                    "parallelism": "dp%d" % world, "conv": args.conv, "cuda_graph": not args.no_graph,
+                   "allreduce": ("captured in the iteration graph; top of the critic reduced during "
+                                 "the backward sweep" if world > 1 and not tr.segment_graphs
+                                 else ("between segment graphs" if world > 1 else None)),
                    "l2": "working set %.0f MB per pass > 126 MB L2" % (B * res * res * 64 * 2 * 4 / 1e6)},
         "e2e": {"value": round(e2e, 2), "unit": "img/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 12},
         "gpu_launches": eager_launches * args.steps,
-        "roofline": roofline(conv_flops, conv_ms, len(conv_recs), ms / args.steps, achieved_tf, res),
+        "roofline": roofline(conv_flops, conv_ms, len(conv_recs), ms / args.steps, achieved_tf, res,
+                             ms / 1e3),
         "clocks": sampler.summary(),
     }
+    if replicas is not None:
+        line["replicas_identical"] = bool(replicas)
     if not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(res, B, alpha, sample_batch=args.cpu_batch)
+        line["cpu_baseline"] = cpu_baseline(res, B, alpha, sample_batch=args.cpu_batch)[0]
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
-def roofline(conv_flops, conv_ms, n_conv, step_ms, step_tf, res):
+def roofline(conv_flops, conv_ms, n_conv, step_ms, step_tf, res, timed_s):
     """Roofline of the dominant kernel (conv4_tc_kernel, tensor-bound): algorithmic FLOPs of its
-    launches in one iteration over their summed device time, against the measured sustained bf16
-    peak (the kernel runs inside a long step).  `traffic`: DRAM bytes of the largest launch
-    (128->128 @64px, batch 128) from the ncu --set full capture in profiles/ (algorithmic
-    268 MB: no wasted re-reads; part of the output is still in L2 when the kernel ends)."""
-    peak_tf, _, which = peaks()
+    launches in one iteration over their summed device time (CUDA events on the launching
+    stream).  `peak` is the measured BURST bf16 figure when the timed region is shorter than a
+    second (the kernel is effectively timed alone, clocks at maximum), the sustained one for a long
+    region; both fractions are reported.  `traffic`: DRAM bytes of one launch from the committed
+    ncu --set full capture of THIS kernel source (None when the capture is from another build)."""
+    burst, sustained, _, which = peaks()
+    use_burst = timed_s < 1.0
+    peak_tf = burst if use_burst else sustained
     ach = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    traffic, tnote = ncu_traffic() if res == 128 else (None, "captured at 128 px only")
     return {"bound": "tensor", "kernel": "conv4_tc_kernel", "achieved": round(ach, 2), "peak": peak_tf,
             "unit": "TFLOP/s", "frac": round(ach / peak_tf, 4),
-            "traffic": 223.7e6 if res == 128 else None,
+            "peak_kind": "burst" if use_burst else "sustained",
+            "frac_of_burst": round(ach / burst, 4), "frac_of_sustained": round(ach / sustained, 4),
+            "traffic": traffic, "traffic_note": tnote,
             "launches_per_step": n_conv, "kernel_ms_per_step": round(conv_ms, 3),
             "kernel_share_of_step": round(conv_ms / step_ms, 3) if step_ms > 0 else None,
             "whole_step": {"achieved": round(step_tf, 2), "frac": round(step_tf / peak_tf, 4),
+                           "frac_of_burst": round(step_tf / burst, 4),
+                           "frac_of_sustained": round(step_tf / sustained, 4),
                            "note": "14 F_D + 3 F_G = %.2f GFLOP/img over the step time"
                                    % (step_flops(res) / 1e9)},
-            "note": "algorithmic conv FLOPs of the kernel's launches / their device time (CUDA events); "
-                    "peak = %s; ncu tensor-pipe active 65-71%% (profiles/)" % which}
+            "note": "algorithmic conv FLOPs of the kernel's launches / their device time (CUDA events, "
+                    "each launch repeated 3x back to back in one extra eager iteration); peaks %s" % which}
 
 
 def cpu_baseline(res, B, alpha, sample_batch=32, iters=2):
-    """The oracle (fp32 PyTorch restatement of the reference loop, pinned to the reference by
-    the golden vectors) timed on the host cores, on a bounded sample of the workload."""
-    from oracle import progan_oracle as O
-    import progan_b200
+    """The reference's CPU path timed on the host cores, on a bounded sample of the workload: the
+    UNMODIFIED reference modules staged under baseline/_ref/ (oracle/stage_reference.py) driven by
+    the loop body of train.py:97-169 (oracle/ref_loop.py) — kind "reference"; when they are not
+    staged, the oracle restatement (oracle/progan_oracle.py, pinned to the reference's golden
+    vectors) — kind "port"."""
+    from oracle import ref_loop
     threads = len(os.sched_getaffinity(0))
     torch.set_num_threads(threads)
     step = {8: 1, 16: 2, 32: 3, 64: 4, 128: 5, 256: 6}[res]
-    torch.manual_seed(0)
-    with torch.device("cpu"):
-        G = progan_b200.Generator(128, 128, tanh=False)
-        D = progan_b200.Discriminator(128)
-    PG, PD, PR = O.params_of(G), O.params_of(D), O.params_of(G, False)
-    optG, optD = O.AdamState(PG), O.AdamState(PD)
     real, z, eps = make_inputs(sample_batch, res, 128, 1234)
-    O.train_iteration(PG, PD, PR, optG, optD, real, z, eps, step, alpha)      # warm-up
+    R, where = ref_loop.import_reference()
+    torch.manual_seed(0)
+    if R is not None:
+        G, D, Grun, g_opt, d_opt = ref_loop.build(R, 128, 128)
+
+        def it():
+            ref_loop.iteration(G, D, Grun, g_opt, d_opt, real, z, eps, step, alpha)
+        kind, what = "reference", "unmodified progan_modules.py from %s + train.py:97-169 loop body" % (
+            "baseline/_ref" if "baseline" in where else where)
+    else:
+        from oracle import progan_oracle as O
+        import progan_b200
+        with torch.device("cpu"):
+            G = progan_b200.Generator(128, 128, tanh=False)
+            D = progan_b200.Discriminator(128)
+        PG, PD, PR = O.params_of(G), O.params_of(D), O.params_of(G, False)
+        optG, optD = O.AdamState(PG), O.AdamState(PD)
+
+        def it():
+            O.train_iteration(PG, PD, PR, optG, optD, real, z, eps, step, alpha)
+        kind, what = "port", "oracle/progan_oracle.py"
+    it()                                                                     # warm-up
     t0 = time.perf_counter()
     for _ in range(iters):
-        O.train_iteration(PG, PD, PR, optG, optD, real, z, eps, step, alpha)
+        it()
     dt = (time.perf_counter() - t0) / iters
-    return {"value": round(sample_batch / dt, 3), "unit": "img/s", "cores": threads, "kind": "port",
-            "sample": "%d full iterations at batch %d, %dpx (1 warm-up), oracle/progan_oracle.py"
-                      % (iters, sample_batch, res)}
+    return {"value": round(sample_batch / dt, 3), "unit": "img/s", "cores": threads, "kind": kind,
+            "sample": "%d full iterations at batch %d, %dpx (1 warm-up), fp32, %s"
+                      % (iters, sample_batch, res, what)}, dt
 
 
 def run_reference(args):
+    """`--impl reference`: the reference's own CPU implementation of the path on the host cores,
+    at the product arm's config (batch 64 per step by default)."""
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     if rank != 0:
         return
     res, B = args.res, args.batch
     step = {8: 1, 16: 2, 32: 3, 64: 4, 128: 5, 256: 6}[res]
-    cb = cpu_baseline(res, B, args.alpha, sample_batch=args.cpu_batch, iters=max(1, min(args.steps, 3)))
+    iters = max(1, min(args.steps, 2))
+    cb, dt = cpu_baseline(res, B, args.alpha, sample_batch=B, iters=iters)
     line = {"impl": "reference", "metric": "G+D+GP train imgs/sec at %dpx" % res,
-            "value": cb["value"], "unit": "img/s", "n_gpus": world, "steps": max(1, min(args.steps, 3)),
-            "warmup": 1, "ms_per_step": round(1e3 * args.cpu_batch / cb["value"], 2),
+            "value": cb["value"], "unit": "img/s", "n_gpus": world, "steps": iters,
+            "warmup": 1, "ms_per_step": round(1e3 * dt, 2),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32",
             "data": "synthetic",
-            "config": {"workload": "train.py CelebA-shape G(128,128)/D(128) step %d (%dpx) alpha=%.2f, "
-                                   "bounded sample: batch %d per step on the host cores"
-                                   % (step, res, args.alpha, args.cpu_batch)},
+            "config": {"workload": "train.py CelebA-shape G(128,128)/D(128) step %d (%dpx) alpha=%.2f "
+                                   "batch %d, full iteration incl. Adam+EMA, on the host cores"
+                                   % (step, res, args.alpha, B)},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "img/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0}}

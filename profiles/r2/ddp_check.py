@@ -1,0 +1,71 @@
+"""torchrun --nproc-per-node N profiles/r2/ddp_check.py [--res 128]
+Data-parallel check on real NCCL: the ONE-graph iteration with captured collectives and the
+backward-overlapped all-reduce of the top of the critic against the older three-segment form
+(collectives between graph replays), same weights and inputs: parameters after K steps agree,
+replicas stay bit-identical, and the time per iteration of each form."""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+import progan_b200  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--res", type=int, default=128)
+ap.add_argument("--steps", type=int, default=6)
+a = ap.parse_args()
+rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+step = {8: 1, 16: 2, 32: 3, 64: 4, 128: 5}[a.res]
+g = torch.Generator().manual_seed(1234 + rank)
+real = (torch.rand(64, 3, a.res, a.res, generator=g) * 2 - 1).to(dev)
+z = torch.randn(64, 128, generator=g).to(dev)
+eps = torch.rand(64, 1, 1, 1, generator=g).to(dev)
+
+
+def run(segment, early):
+    torch.manual_seed(0)
+    G = progan_b200.Generator(128, 128, tanh=False).to(dev)
+    D = progan_b200.Discriminator(128).to(dev)
+    R = progan_b200.Generator(128, 128, tanh=False).to(dev)
+    R.load_state_dict(G.state_dict())
+    for p in list(G.parameters()) + list(D.parameters()) + list(R.parameters()):
+        dist.broadcast(p.data, 0)
+    os.environ["PG_EARLY_REDUCE"] = "1" if early else "0"
+    tr = progan_b200.Trainer(G, D, R, use_graph=True, segment_graphs=segment)
+    for _ in range(3):
+        tr.step(real, z, eps, step, 0.5)
+    dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        tr.step(real, z, eps, step, 0.5)
+    e1.record()
+    dist.barrier(); torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / a.steps], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    sums = torch.stack([tr.bD.p.double().sum(), tr.bG.p.double().sum(), tr.bR.p.double().sum()])
+    alls = [torch.empty_like(sums) for _ in range(world)]
+    dist.all_gather(alls, sums)
+    same = all(torch.equal(alls[0], t) for t in alls)
+    return float(ms), same, tr.bD.p.clone(), tr.bG.p.clone(), tr.read_metrics()
+
+
+res = {}
+for name, seg, early in (("segments", True, False), ("one_graph", False, False), ("one_graph_early", False, True)):
+    res[name] = run(seg, early)
+    if rank == 0:
+        print("%-16s %.3f ms/iter  replicas identical: %s  metrics %s" % (name, res[name][0], res[name][1], res[name][4]), flush=True)
+if rank == 0:
+    ref = res["segments"]
+    for name in ("one_graph", "one_graph_early"):
+        dD = float((res[name][2] - ref[2]).norm() / ref[2].norm())
+        dG = float((res[name][3] - ref[3]).norm() / ref[3].norm())
+        print("%-16s vs segments: rel diff D params %.2e  G params %.2e" % (name, dD, dG))
+        assert dD < 1e-4 and dG < 1e-4 and res[name][1]
+    print("DDP_CHECK_OK")
+dist.destroy_process_group()

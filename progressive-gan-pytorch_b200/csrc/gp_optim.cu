@@ -99,7 +99,8 @@ gp_bwd_kernel(const float *__restrict__ g, const float *__restrict__ norms,
        i += (long long)gridDim.x * blockDim.x) {
     const long long n = i / D4, j = i - n * D4;
     const float nm = norms[n];
-    const float k = up * 2.f * lambda / (float)N * (nm - 1.f) / nm;
+    // torch's norm backward uses the subgradient 0 at ||g|| = 0 (no NaN into the gradient bucket)
+    const float k = nm > 0.f ? up * 2.f * lambda / (float)N * (nm - 1.f) / nm : 0.f;
     float4 x = reinterpret_cast<const float4 *>(g + n * D)[j];
     x.x *= k; x.y *= k; x.z *= k; x.w *= k;
     reinterpret_cast<float4 *>(v + n * D)[j] = x;

@@ -8,6 +8,7 @@
 // (SURVEY.md F1, Appendix D).  All are HBM-bound: 16-byte vector accesses over the
 // channel dimension, grid sized in multiples of the SM count.
 #include "common.cuh"
+#include <type_traits>
 
 namespace pg {
 
@@ -199,25 +200,36 @@ upsample2_bwd_kernel(const T *__restrict__ dy, T *__restrict__ dx, int N, int H,
     const Tile2D it = tile_item<G>(tile, threadIdx.x, H, W, C, TW, TH);
     if (!it.ok) continue;
     const T *b = dy + (long long)it.n * Ho * Wo * C + it.c;
+    // all sixteen taps are loaded (raw) before the first multiply: the kernel lives on L1/L2 hits
+    // and needs the loads in flight, not the arithmetic
+    typename std::conditional<G == 8, typename RawOf<T>::type, float>::type raw[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int oy = min(max(2 * it.y - 1 + a, 0), Ho - 1);
+#pragma unroll
+      for (int bb = 0; bb < 4; ++bb) {
+        const int ox = min(max(2 * it.x - 1 + bb, 0), Wo - 1);
+        const T *src = b + ((long long)oy * Wo + ox) * C;
+        if constexpr (G == 8) raw[a][bb] = ldraw8(src);
+        else raw[a][bb] = ldf(src);
+      }
+    }
     float acc[G];
 #pragma unroll
     for (int e = 0; e < G; ++e) acc[e] = 0.f;
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      const int oy = min(max(2 * it.y - 1 + a, 0), Ho - 1);
-      Grp<T, G> g[4];
-#pragma unroll
-      for (int bb = 0; bb < 4; ++bb) {
-        const int ox = min(max(2 * it.x - 1 + bb, 0), Wo - 1);
-        g[bb].load(b + ((long long)oy * Wo + ox) * C);
-      }
+    for (int a = 0; a < 4; ++a)
 #pragma unroll
       for (int bb = 0; bb < 4; ++bb) {
         const float wgt = wt[a] * wt[bb];
+        if constexpr (G == 8) {
+          const F8 v = unpack8(raw[a][bb]);
 #pragma unroll
-        for (int e = 0; e < G; ++e) acc[e] = fmaf(wgt, g[bb].v[e], acc[e]);
+          for (int e = 0; e < 8; ++e) acc[e] = fmaf(wgt, v.v[e], acc[e]);
+        } else {
+          acc[0] = fmaf(wgt, raw[a][bb], acc[0]);
+        }
       }
-    }
     Grp<T, G> o;
 #pragma unroll
     for (int e = 0; e < G; ++e) o.v[e] = acc[e];

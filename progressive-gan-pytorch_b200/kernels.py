@@ -177,7 +177,14 @@ class CudaKernels:
         cacheable = isinstance(w, torch.nn.Parameter)
         if cacheable:
             ent = self._packs.get(id(w))
-            if ent is not None and ent[0]() is w and ent[1] == w._version:
+            if ent is not None and ent[0]() is w:
+                if ent[1] != w._version:
+                    # the parameter changed behind the cache (load_state_dict, an in-place edit):
+                    # re-pack every cached copy INTO ITS OWN STORAGE - captured CUDA graphs and
+                    # the device pack tables hold these pointers
+                    for out_, a_ in ent[2].values():
+                        self._call("pg_pack_conv_weight", w.data_ptr(), out_.data_ptr(), *a_, self._stream())
+                    ent[1] = w._version
                 hit = ent[2].get(key)
                 if hit is not None:
                     return hit[0]
@@ -414,23 +421,33 @@ class CudaKernels:
             self._side_streams[cur.cuda_stream] = side
         return side
 
-    def flush_wgrads(self):
-        """Fold every pending weight-gradient workspace into its gradient: one launch per
+    def flush_wgrads(self, ptr_range=None, join=True):
+        """Fold pending weight-gradient workspaces into their gradients: one launch per
         'round', where a round holds at most one workspace per gradient tensor (a conv's own
         weight gradient and its adjoint form from the GP sweep go to different rounds, so the
-        kernel's read-modify-write of dw needs no atomics)."""
+        kernel's read-modify-write of dw needs no atomics).  ptr_range = (lo, hi): only the
+        workspaces whose gradient lives in that address range (the data-parallel Trainer flushes
+        and all-reduces the top of the critic while the backward sweep is still running); join:
+        wait for the weight-gradient side streams first (the caller did it itself otherwise)."""
         if not self._pending:
             return
-        for side in self._side_dirty:    # join the weight-gradient streams
-            torch.cuda.current_stream().wait_stream(side)
-        self._side_dirty = set()
-        sig = tuple(self._pending.keys())
+        if ptr_range is None:
+            sel = dict(self._pending)
+        else:
+            sel = {k: v for k, v in self._pending.items() if ptr_range[0] <= k[0] < ptr_range[1]}
+            if not sel:
+                return
+        if join:
+            for side in self._side_dirty:    # join the weight-gradient streams
+                torch.cuda.current_stream().wait_stream(side)
+            self._side_dirty = set()
+        sig = tuple(sel.keys())
         tabs = self._unpack_tables.get(sig)
         if tabs is None:
             if torch.cuda.is_current_stream_capturing():
                 raise RuntimeError("progan_b200: unpack table changed during CUDA-graph capture")
             rounds = []
-            for wkey, (ws, ent) in self._pending.items():
+            for wkey, (ws, ent) in sel.items():
                 for r in rounds:
                     if wkey[0] not in r[0]:
                         break
@@ -439,12 +456,13 @@ class CudaKernels:
                     rounds.append(r)
                 r[0].add(wkey[0])
                 r[1].append(ent)
-            dev = next(iter(self._pending.values()))[0].device
+            dev = next(iter(sel.values()))[0].device
             tabs = [(self._upload(rows, _lib.UnpackEntry, dev), len(rows)) for _, rows in rounds]
             self._unpack_tables[sig] = tabs
         for tab, n in tabs:
             self._call("pg_wgrad_unpack_multi", tab.data_ptr(), n, self._stream())
-        self._pending.clear()
+        for k in sel:
+            del self._pending[k]
 
     def mbstd_channels(self, C, dtype):
         """Physical channel count of the minibatch-stddev output (C real + 1 statistic):

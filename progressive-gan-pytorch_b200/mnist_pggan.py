@@ -12,7 +12,7 @@ from torch import nn
 from . import functions as F_
 from .progan_modules import (ConvBlock, EqualConv2d, EqualConvTranspose2d, EqualLinear, MnistConvBlock,
                              PixelNorm, _AlphaMixin, _DEFAULT_PRECISION, _LeakyMarker, _act_dtype,
-                             _from_rgb, _fused_layer, _img_dtype, _to_rgb)
+                             _fading, _from_rgb, _fused_layer, _img_dtype, _to_rgb)
 from . import progan_modules as _pm
 
 
@@ -53,7 +53,7 @@ class Generator(nn.Module, _AlphaMixin):
         if step > self.max_step:
             step = self.max_step
         dt = _act_dtype(self.precision)
-        fading = torch.is_tensor(alpha) or (0 <= alpha < 1)
+        fading, alpha = _fading(alpha)
         z = input.reshape(-1, 1, 1, self._latent_dim()).to(dt).contiguous()
         out_4 = _fused_layer(z, self.input_layer[0], 0.1, True)          # slope 0.1 (:21)
         out_4 = self.progression_4(out_4)
@@ -89,7 +89,7 @@ class Discriminator(nn.Module, _AlphaMixin):
 
     def forward(self, input, step=0, alpha=-1, mbstd_group=None):
         dt = _act_dtype(self.precision)
-        fading = torch.is_tensor(alpha) or (0 <= alpha < 1)
+        fading, alpha = _fading(alpha)
         x = input.contiguous()
         if x.dtype != _img_dtype(self.precision):
             x = x.to(_img_dtype(self.precision))

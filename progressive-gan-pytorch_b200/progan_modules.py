@@ -147,6 +147,18 @@ class MnistConvBlock(nn.Module):
         return _fused_layer(x, self.conv[0], 0.2, self.pixel_norm, pool)
 
 
+def _fading(alpha):
+    """(fading, alpha): the reference's gate `0 <= alpha < 1` (progan_modules.py:210,301).  A
+    tensor alpha is evaluated like a number (the reference's comparison also works for 0-dim
+    tensors) unless it is the Trainer's device scalar (marked `_pg_fading`), which stands for
+    "the fade is active, read the value on the device" so that captured graphs follow the schedule."""
+    if torch.is_tensor(alpha):
+        if getattr(alpha, "_pg_fading", False):
+            return True, alpha
+        alpha = float(alpha)
+    return bool(0 <= alpha < 1), alpha
+
+
 class _AlphaMixin:
     @staticmethod
     def _alpha(alpha, device):
@@ -210,9 +222,7 @@ class Generator(nn.Module, _AlphaMixin):
         if step < 1:
             return None                      # reference falls through every `if` (:231-254)
         dt = _act_dtype(self.precision)
-        fading = (not torch.is_tensor(alpha)) and 0 <= alpha < 1
-        if torch.is_tensor(alpha):
-            fading = True
+        fading, alpha = _fading(alpha)
         z = input.reshape(-1, 1, 1, self.input_dim).to(dt).contiguous()
         # input layer always applies PixelNorm (:181-184), independent of `pixel_norm`
         feat = _fused_layer(z, self.input_layer[0], 0.2, True)
@@ -253,13 +263,17 @@ class Discriminator(nn.Module, _AlphaMixin):
                                        EqualConv2d(3, f, 1)])
         self.n_layer = len(self.progression)
         self.linear = EqualLinear(f, 1)
+        # (block index, hook): the data-parallel Trainer learns through this tensor hook when a
+        # backward sweep has passed every layer above that block (their gradients are final and
+        # can be all-reduced while the sweep continues below)
+        self._bwd_tap = None
 
     def forward(self, input, step=0, alpha=-1, mbstd_group=None):
         """mbstd_group (extension, default = reference behaviour): batch slices of this size get
         their own minibatch-stddev statistic, so one call on cat([real, fake]) equals the
         reference's two calls (train.py:126,137)."""
         dt = _act_dtype(self.precision)
-        fading = torch.is_tensor(alpha) or (0 <= alpha < 1)
+        fading, alpha = _fading(alpha)
         x = input.contiguous()
         if x.dtype != _img_dtype(self.precision):
             x = x.to(_img_dtype(self.precision))
@@ -275,6 +289,8 @@ class Discriminator(nn.Module, _AlphaMixin):
                 if i == step and fading:
                     skip = _from_rgb(F_.avgpool2(x, "nchw"), self.from_rgb[index + 1], dt)
                     out = F_.Blend.apply(skip, out, self._alpha(alpha, out.device))
+            if self._bwd_tap is not None and index == self._bwd_tap[0] and out.requires_grad:
+                out.register_hook(self._bwd_tap[1])
         lin = self.linear.linear
         C = out.shape[-1]
         d = F_.PwFwd.apply(out, lin.weight_orig, lin.bias, "reduce", C, 1, 1, C, self.linear.scale, dt)
@@ -323,7 +339,7 @@ class CorrectGenerator(nn.Module, _AlphaMixin):
         if step > self.max_step:
             step = self.max_step
         dt = _act_dtype(self.precision)
-        fading = torch.is_tensor(alpha) or (0 <= alpha < 1)
+        fading, alpha = _fading(alpha)
         z = input.reshape(-1, 1, 1, self._latent_dim()).to(dt).contiguous()
         # the stem applies PixelNorm after both convs whatever `pixel_norm` says (:487-494)
         out_4 = _fused_layer(z, self.progression_4[0], 0.2, True)
@@ -366,7 +382,7 @@ class CorrectDiscriminator(nn.Module, _AlphaMixin):
             raise RuntimeError("CorrectDiscriminator: step must be >= 1 (the reference fails with an "
                                "unbound `out` for step 0, progan_modules.py:578-596)")
         dt = _act_dtype(self.precision)
-        fading = torch.is_tensor(alpha) or (0 <= alpha < 1)
+        fading, alpha = _fading(alpha)
         x = input.contiguous()
         if x.dtype != _img_dtype(self.precision):
             x = x.to(_img_dtype(self.precision))
@@ -447,7 +463,7 @@ class ConditionalCorrectGenerator(CorrectGenerator):
         if step > self.max_step:
             step = self.max_step
         dt = _act_dtype(self.precision)
-        fading = torch.is_tensor(alpha) or (0 <= alpha < 1)
+        fading, alpha = _fading(alpha)
         data_in = torch.cat([input, self.embedding(label).to(input.dtype)], 1)        # (:664-668)
         z = data_in.reshape(-1, 1, 1, self.input_dim + self.embedding_dim).to(dt).contiguous()
         out_4 = _fused_layer(z, self.progression_4[0], 0.2, True)
@@ -501,7 +517,7 @@ class ConditionalCorrectDiscriminatorWgangp(nn.Module, _AlphaMixin):
         if step < 1:
             raise RuntimeError("ConditionalCorrectDiscriminatorWgangp: step must be >= 1")
         dt = _act_dtype(self.precision)
-        fading = torch.is_tensor(alpha) or (0 <= alpha < 1)
+        fading, alpha = _fading(alpha)
         x = input.contiguous()
         if x.dtype != _img_dtype(self.precision):
             x = x.to(_img_dtype(self.precision))
@@ -530,7 +546,7 @@ def _critic_trunk(m, input, step, alpha, mbstd_group, last, plane=None):
     front of the last block.  `plane(img, index)` appends the label plane where the class has
     one.  Returns the [B,1,1,C] feature in front of the linear head."""
     dt = _act_dtype(m.precision)
-    fading = torch.is_tensor(alpha) or (0 <= alpha < 1)
+    fading, alpha = _fading(alpha)
     x = input.contiguous()
     if x.dtype != _img_dtype(m.precision):
         x = x.to(_img_dtype(m.precision))
@@ -611,7 +627,7 @@ class ConditionalGenerator(Generator):
         if step < 1:
             return None
         dt = _act_dtype(self.precision)
-        fading = torch.is_tensor(alpha) or (0 <= alpha < 1)
+        fading, alpha = _fading(alpha)
         z = self._latent(input, label).reshape(-1, 1, 1, self.input_dim + self.embedding_dim).to(dt).contiguous()
         feat = self.progression_4(_fused_layer(z, self.input_layer[0], 0.2, True))
         prev = None

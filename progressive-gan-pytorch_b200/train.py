@@ -22,8 +22,12 @@ What is different from the reference (all host-side, numerics unchanged):
   * losses are accumulated on the device (no .item() sync per iteration, train.py:152-165);
   * the D weight-gradients of the G phase — which the reference computes and then throws
     away (train.py:159-167) — are not computed: backward(inputs=G.parameters()).
-  * optionally the whole iteration is captured in a CUDA graph per (step, fading, batch).
+  * optionally the whole iteration is captured in a CUDA graph per (step, fading, batch) —
+    with world_size > 1 the NCCL all-reduces are captured inside it, and the all-reduce of the top
+    of the critic (everything above the 64 px block: most of D's parameters) is issued from a
+    communication stream while the backward sweep is still working on the 64/128 px blocks.
 """
+import os
 import torch
 import torch.distributed as dist
 
@@ -91,6 +95,21 @@ def _generic_groups(model):
             if ps:
                 groups.append((name, ps))
     return groups
+
+
+def _reduce_ranges(ranges, done=None):
+    """The collectives for a bucket's live ranges: what `done` = (a, b) already covered is cut off,
+    and two ranges with a small gap between them go out as one span."""
+    rs = list(ranges)
+    if done is not None:
+        rs = [(max(a, done[1]), b) for a, b in rs if b > done[1]]
+    if not rs:
+        return []
+    span = rs[-1][1] - rs[0][0]
+    live = sum(b - a for a, b in rs)
+    if len(rs) > 1 and span <= 1.25 * live:
+        rs = [(rs[0][0], rs[-1][1])]
+    return rs
 
 
 class _NullCtx:
@@ -244,14 +263,18 @@ class Trainer:
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
         self.use_graph = use_graph
-        # multi-GPU: three graphs per iteration with the NCCL all-reduces between the replays
-        self.segment_graphs = (self.world > 1) if segment_graphs is None else bool(segment_graphs)
-        if use_graph and self.world > 1 and not self.segment_graphs:
-            # tried on 2 x B200 (NCCL 2.28): with both all-reduces captured inside ONE graph next to
-            # the concurrent side-stream chains the run never completed; the collectives stay
-            # between three segment graphs
-            raise RuntimeError("progan_b200.Trainer: segment_graphs=False is not supported with "
-                               "world_size > 1 (all-reduces captured inside one CUDA graph hang)")
+        # multi-GPU: ONE graph per iteration with the NCCL all-reduces captured inside it
+        # (capture_error_mode="thread_local": ProcessGroupNCCL's watchdog thread queries events
+        # while the capture is open, which the default global mode forbids — the round-1 attempt
+        # with the default mode hung).  segment_graphs=True (or PG_SEGMENT_GRAPHS=1) keeps the
+        # older form: three graphs with the collectives between the replays.
+        if segment_graphs is None:
+            segment_graphs = os.environ.get("PG_SEGMENT_GRAPHS", "0") == "1"
+        self.segment_graphs = bool(segment_graphs) and self.world > 1
+        # all-reduce of the top of the critic overlapped with the rest of its backward sweep
+        self.early_reduce = os.environ.get("PG_EARLY_REDUCE", "1") == "1" and not (
+            use_graph and self.segment_graphs)       # segment graphs: collectives between the replays
+        self._early = None
         from .progan_modules import Discriminator as _BaseD, Generator as _BaseG
         # train.py's own models get the hand-ordered buckets (live set = two contiguous ranges);
         # every other mirrored family a generic layout + a probe pass for the live set
@@ -269,6 +292,8 @@ class Trainer:
                 p.grad = None
         dev = self.bD.p.device
         self.alpha_dev = torch.zeros((), device=dev, dtype=torch.float32)
+        self.alpha_dev._pg_fading = True          # modules: "fade active, value lives on the device"
+        self._comm_stream = torch.cuda.Stream() if (self.world > 1 and dev.type == "cuda") else None
         self.metrics = {k: torch.zeros((), device=dev, dtype=torch.float32)
                         for k in ("disc_loss", "grad_penalty", "gen_loss")}
         self.iterations = 0
@@ -283,19 +308,62 @@ class Trainer:
         self._r_params = list(g_running.parameters()) if g_running is not None else []
 
     # ------------------------------------------------------------------ pieces
-    def _allreduce(self, bucket, plan):
+    def _allreduce(self, bucket, plan, done=None):
         """Sum the live gradient ranges over the ranks.  When the gap between the (at most two)
         ranges is small the whole span goes out as ONE collective — the gap holds zeros (the
         bucket is cleared every phase and inactive layers receive no gradient) and a second NCCL
-        launch costs more than a few KB of payload."""
+        launch costs more than a few KB of payload.  done = (a, b): that prefix of the bucket was
+        already reduced during the backward sweep (_on_top_done)."""
         if self.world > 1:
-            rs = plan["ranges"]
-            span = rs[-1][1] - rs[0][0]
-            live = sum(b - a for a, b in rs)
-            if len(rs) > 1 and span <= 1.25 * live:
-                rs = [(rs[0][0], rs[-1][1])]
-            for a, b in rs:
+            for a, b in _reduce_ranges(plan["ranges"], done):
                 dist.all_reduce(bucket.g[a:b], group=self.pg)
+
+    # the critic block whose OUTPUT gradient marks "every layer above is done": progression[2]
+    # (64 px -> 32 px); above it sit linear + progression[3..6] = the first groups of the bucket
+    _TAP_BLOCK = 2
+
+    def _early_range(self, st):
+        """(a, b) = the prefix of the D bucket that can be reduced during the backward sweep, or
+        None when the feature does not apply (single GPU, generic bucket layout, low resolution
+        steps whose whole critic is above the tap)."""
+        if (self.world <= 1 or not self.early_reduce or self._generic or self._comm_stream is None
+                or st["step"] < 4 or get_kernels().name != "cuda"):
+            return None
+        names = ["linear"] + ["progression.%d" % k for k in range(self.D.n_layer - 1, self._TAP_BLOCK, -1)]
+        a = self.bD.group_range[names[0]][0]
+        b = self.bD.group_range[names[-1]][1]
+        assert a == 0 and all(self.bD.group_range[n][1] <= b for n in names)
+        return (a, b)
+
+    def _on_top_done(self, grad):
+        """Tensor hook on the output of critic block _TAP_BLOCK: fires inside a backward sweep once
+        the gradient of that activation is complete, i.e. after the data- and weight-gradient
+        kernels of every layer above it were launched.  When both D-phase chains (gradient-penalty
+        sweep, real/fake pass) have reached it, the communication stream folds those layers'
+        weight-gradient workspaces into the bucket and all-reduces that prefix — while the sweeps
+        go on through the 64 / 128 px blocks, where most of the time is spent."""
+        e = self._early
+        if e is None or not e["armed"]:
+            return None
+        K = get_kernels()
+        cur = torch.cuda.current_stream()
+        for s_ in (cur, K._side_streams.get(cur.cuda_stream)):
+            if s_ is not None:
+                ev = torch.cuda.Event()
+                ev.record(s_)
+                e["events"].append(ev)
+        e["fires"] += 1
+        if e["fires"] == 2:
+            a, b = e["range"]
+            cs = self._comm_stream
+            for ev in e["events"]:
+                cs.wait_event(ev)
+            with torch.cuda.stream(cs):
+                lo = self.bD.g.data_ptr()
+                K.flush_wgrads(ptr_range=(lo + 4 * a, lo + 4 * b), join=False)
+                dist.all_reduce(self.bD.g[a:b], group=self.pg)
+            e["reduced"] = True
+        return None
 
     def _adam(self, bucket, plan):
         bucket.steps.add_(plan["mask"])
@@ -327,7 +395,7 @@ class Trainer:
         st = self._state(real, z, eps, step, alpha, fading, label, do_g)
         with self._fast_paths(self._side):
             self._seg_d(st)
-            self._allreduce(self.bD, st["planD"])
+            self._allreduce(self.bD, st["planD"], st.get("reduced"))
             if do_g:
                 self._seg_g(st)
                 self._allreduce(self.bG, st["planG"])
@@ -388,6 +456,10 @@ class Trainer:
         # low-resolution layers of one chain hide behind the large kernels of the other.
         s2 = self._gp_stream if (self._gp_stream is not None and K.name == "cuda" and K.conv_impl == "tc") else None
         cur = torch.cuda.current_stream() if s2 is not None else None
+        early = self._early_range(st)
+        if early is not None:
+            self._early = dict(armed=False, fires=0, events=[], range=early, reduced=False)
+            D._bwd_tap = (self._TAP_BLOCK, self._on_top_done)
         if s2 is not None:
             s2.wait_stream(cur)
         with (torch.cuda.stream(s2) if s2 is not None else _NullCtx()):
@@ -400,12 +472,20 @@ class Trainer:
                 ones = self._ones[tuple(hat.shape)] = torch.ones_like(hat)
             (g,) = torch.autograd.grad(outputs=hat, inputs=x_hat, grad_outputs=ones, create_graph=True)
             gp = F_.gradient_penalty(g, self.gp_lambda)
+            if early is not None:
+                self._early["armed"] = True          # the first-order sweep above must not count
             gp.backward()
         both = D(torch.cat([real, fake.detach()]), *la2, step=step, alpha=alpha, mbstd_group=B)
         # loss value (-> metric) and dL/d(outputs) in one launch, then backward from that seed
         both.backward(K.wgan_loss(both.detach(), B, self.drift, self.metrics["disc_loss"]))
         if s2 is not None:
             cur.wait_stream(s2)
+        if early is not None:
+            D._bwd_tap = None
+            if self._early["reduced"]:
+                torch.cuda.current_stream().wait_stream(self._comm_stream)
+                st["reduced"] = early
+            self._early = None
         K.flush_wgrads()
         st["fake"] = fake
         st["gp"] = gp.detach()
@@ -519,7 +599,7 @@ class Trainer:
             torch.cuda.synchronize()
             if not self.segment_graphs:
                 graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
+                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                     self._iteration(sreal, sz, seps, step, a, fading, slabel, do_g)
                 graphs = [graph]
             else:
@@ -554,6 +634,10 @@ class Trainer:
             if do_g:
                 self._allreduce(self.bG, planG)
                 graphs[2].replay()
+        if do_g and self._r_params:
+            # the captured EMA kernel rewrote g_running's weights behind autograd's back: forget
+            # their operand copies so the next g_running(...) call packs the current values
+            K.drop_packs(self._r_params)
 
     def read_metrics(self, reset=True):
         """One host sync for all three running sums (the reference syncs three times per

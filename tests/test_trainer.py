@@ -111,3 +111,25 @@ def test_n_critic_matches_reference_ordered_loop(name, n_critic):
     assert abs(m["gen_loss"] - gen_loss_sum) <= 1e-4 * abs(gen_loss_sum) + 1e-6
     with pytest.raises(ValueError):
         progan_b200.Trainer(G, D, Grun, n_critic=0)
+
+
+def test_reduce_ranges_cut_off_what_the_backward_sweep_already_reduced():
+    from progan_b200.train import _reduce_ranges
+    assert _reduce_ranges([(0, 100), (400, 420)]) == [(0, 100), (400, 420)]
+    assert _reduce_ranges([(0, 100), (110, 120)]) == [(0, 120)]            # small gap: one collective
+    assert _reduce_ranges([(0, 100), (400, 420)], done=(0, 60)) == [(60, 100), (400, 420)]
+    assert _reduce_ranges([(0, 100), (400, 420)], done=(0, 100)) == [(400, 420)]
+    assert _reduce_ranges([(0, 100)], done=(0, 100)) == []
+
+
+def test_tensor_alpha_is_evaluated_like_a_number_unless_marked():
+    """a plain tensor alpha outside [0, 1) must not take the blend path."""
+    from progan_b200.progan_modules import _fading
+    assert _fading(torch.tensor(-1.0)) == (False, -1.0)
+    assert _fading(torch.tensor(1.0)) == (False, 1.0)
+    assert _fading(torch.tensor(0.25))[0] is True
+    t = torch.tensor(0.0)
+    t._pg_fading = True
+    f, a = _fading(t)
+    assert f is True and a is t
+    assert _fading(0.5) == (True, 0.5) and _fading(-1) == (False, -1)
