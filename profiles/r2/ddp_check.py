@@ -1,8 +1,10 @@
-"""torchrun --nproc-per-node N profiles/r2/ddp_check.py [--res 128]
-Data-parallel check on real NCCL: the ONE-graph iteration with captured collectives and the
-backward-overlapped all-reduce of the top of the critic against the older three-segment form
-(collectives between graph replays), same weights and inputs: parameters after K steps agree,
-replicas stay bit-identical, and the time per iteration of each form."""
+"""torchrun --nproc-per-node N profiles/r2/ddp_check.py [--res 128] [--steps 20]
+Data-parallel check on real NCCL: the ONE-graph iteration with captured collectives (with and
+without the backward-overlapped all-reduce of the top of the critic) against the older
+three-segment form (collectives between graph replays).  Same weights and inputs:
+  * the all-reduced gradient buckets after ONE iteration agree (fp32 atomics order only),
+  * replicas stay bit-identical over the timed steps,
+  * time per iteration of each form (max over ranks, CUDA events)."""
 import argparse
 import os
 import sys
@@ -14,7 +16,8 @@ import progan_b200  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--res", type=int, default=128)
-ap.add_argument("--steps", type=int, default=6)
+ap.add_argument("--steps", type=int, default=20)
+ap.add_argument("--variants", default="segments,one_graph,one_graph_early")
 a = ap.parse_args()
 rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(local)
@@ -25,6 +28,7 @@ g = torch.Generator().manual_seed(1234 + rank)
 real = (torch.rand(64, 3, a.res, a.res, generator=g) * 2 - 1).to(dev)
 z = torch.randn(64, 128, generator=g).to(dev)
 eps = torch.rand(64, 1, 1, 1, generator=g).to(dev)
+VAR = {"segments": (True, False), "one_graph": (False, False), "one_graph_early": (False, True)}
 
 
 def run(segment, early):
@@ -37,6 +41,9 @@ def run(segment, early):
         dist.broadcast(p.data, 0)
     os.environ["PG_EARLY_REDUCE"] = "1" if early else "0"
     tr = progan_b200.Trainer(G, D, R, use_graph=True, segment_graphs=segment)
+    tr.step(real, z, eps, step, 0.5)           # capture (warm-up iterations are rolled back) + 1 replay
+    torch.cuda.synchronize()
+    gD, gG = tr.bD.g.clone(), tr.bG.g.clone()
     for _ in range(3):
         tr.step(real, z, eps, step, 0.5)
     dist.barrier(); torch.cuda.synchronize()
@@ -52,20 +59,26 @@ def run(segment, early):
     alls = [torch.empty_like(sums) for _ in range(world)]
     dist.all_gather(alls, sums)
     same = all(torch.equal(alls[0], t) for t in alls)
-    return float(ms), same, tr.bD.p.clone(), tr.bG.p.clone(), tr.read_metrics()
+    return float(ms), same, gD, gG
 
 
 res = {}
-for name, seg, early in (("segments", True, False), ("one_graph", False, False), ("one_graph_early", False, True)):
-    res[name] = run(seg, early)
+for name in a.variants.split(","):
+    res[name] = run(*VAR[name])
     if rank == 0:
-        print("%-16s %.3f ms/iter  replicas identical: %s  metrics %s" % (name, res[name][0], res[name][1], res[name][4]), flush=True)
-if rank == 0:
+        print("%-16s %.3f ms/iter  replicas identical: %s  (NCCL_MAX_NCHANNELS=%s)"
+              % (name, res[name][0], res[name][1], os.environ.get("NCCL_MAX_NCHANNELS", "-")), flush=True)
+ok = True
+if rank == 0 and "segments" in res:
     ref = res["segments"]
-    for name in ("one_graph", "one_graph_early"):
+    for name in res:
+        if name == "segments":
+            continue
         dD = float((res[name][2] - ref[2]).norm() / ref[2].norm())
         dG = float((res[name][3] - ref[3]).norm() / ref[3].norm())
-        print("%-16s vs segments: rel diff D params %.2e  G params %.2e" % (name, dD, dG))
-        assert dD < 1e-4 and dG < 1e-4 and res[name][1]
-    print("DDP_CHECK_OK")
+        print("%-16s vs segments, all-reduced gradients after one iteration: rel diff D %.2e  G %.2e" % (name, dD, dG))
+        # G's gradient follows D's first Adam step (lr * sign(g) at v = 0): sign flips of near-zero D
+        # gradients move a few D weights by 2 lr, which shows up at the 1e-3 level in G's gradient
+        ok = ok and dD < 1e-5 and dG < 1e-2 and res[name][1]
+    print("DDP_CHECK_OK" if ok else "DDP_CHECK_FAILED")
 dist.destroy_process_group()

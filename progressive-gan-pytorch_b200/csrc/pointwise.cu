@@ -242,67 +242,73 @@ pw_wgrad_generic_kernel(const T *__restrict__ act, const float *__restrict__ img
 }
 
 // ------------------------------------------------------------------------------------------
-// Warp-run forms (C = 8 * LPP * NCK channels, LPP = lanes per pixel in {1,2,4,8,16,32}): a warp
-// owns a run of 32 consecutive pixels.  On the image side lane l touches pixel l of the run
-// (one coalesced 128-byte access per image plane); on the activation side the warp moves
-// 512 contiguous bytes per instruction (32 / LPP pixels x LPP 16-byte chunks) and the
-// per-pixel image values travel between the two mappings by warp shuffles.  No integer
-// division per element (one per lane per run), weights in registers, every load of a batch
-// issued before the arithmetic.  (The generic kernels above gave each thread one 16-byte chunk
-// with its own strided image loads and ran at 0.3 of the HBM roofline.)
-template <typename T, int LPP, int NCK>
+// Warp-run forms (C = 8 * LPP * NCK channels, LPP = lanes per pixel in {1,2,4,8,16,32}; KT = number
+// of image channels, compile time): a warp owns a run of 32 consecutive pixels.  On the image
+// side lane l touches pixel l of the run (one coalesced 128-byte access per image plane); on the
+// activation side the warp moves 512 contiguous bytes per instruction (32 / LPP pixels x LPP
+// 16-byte chunks) and the per-pixel image values travel between the two mappings by warp
+// shuffles.  These kernels are INSTRUCTION-bound, not latency-bound (ncu: issue slots 60-70 %
+// busy at 0.3-0.4 of the HBM roofline in their first form), so everything per element that is not
+// an FMA is removed: 32-bit index arithmetic, one division per lane per run, weights in
+// registers, the image-channel count a template parameter, and loop trip counts that depend on
+// kernel parameters only (a warp-uniform loop lets ptxas emit plain SHFL instead of
+// WARPSYNC/ENDCOLLECTIVE sequences around every shuffle).
+template <typename T, int LPP, int NCK, int KT>
 __global__ void __launch_bounds__(256)
 pw_expand_kernel(const float *__restrict__ img, const float *__restrict__ w,
-                 const float *__restrict__ bias, T *__restrict__ act, int N, long long HW,
+                 const float *__restrict__ bias, T *__restrict__ act, int P, int HW,
                  int K, int w_sc, int w_sk, float scale) {
   constexpr int C = 8 * LPP * NCK;
   constexpr int PPW = 32 / LPP;                 // pixels per store instruction
-  __shared__ float sw[NCK > 1 ? (kMaxK + 1) * C : 1];
+  __shared__ float sw[NCK > 1 ? (KT + 1) * C : 1];
   const int lane = threadIdx.x & 31;
   const int sub = lane % LPP, slot = lane / LPP;
-  float wr[kMaxK][8], br[8];
+  float wr[KT][8], br[8];
   if (NCK == 1) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       br[e] = bias ? bias[sub * 8 + e] : 0.f;
 #pragma unroll
-      for (int k = 0; k < kMaxK; ++k)
-        wr[k][e] = (k < K) ? w[(long long)(sub * 8 + e) * w_sc + (long long)k * w_sk] * scale : 0.f;
+      for (int k = 0; k < KT; ++k)
+        wr[k][e] = (k < K) ? w[(sub * 8 + e) * w_sc + k * w_sk] * scale : 0.f;
     }
   } else {
-    for (int i = threadIdx.x; i < kMaxK * C; i += blockDim.x) {
+    for (int i = threadIdx.x; i < KT * C; i += blockDim.x) {
       const int k = i / C, c = i - k * C;
-      sw[i] = (k < K) ? w[(long long)c * w_sc + (long long)k * w_sk] * scale : 0.f;
+      sw[i] = (k < K) ? w[c * w_sc + k * w_sk] * scale : 0.f;
     }
-    for (int c = threadIdx.x; c < C; c += blockDim.x) sw[kMaxK * C + c] = bias ? bias[c] : 0.f;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) sw[KT * C + c] = bias ? bias[c] : 0.f;
     __syncthreads();
   }
-  const long long P = (long long)N * HW;
-  const long long runs = (P + 31) >> 5;
-  const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  const int runs = (P + 31) >> 5;
+  const int wpb = blockDim.x >> 5;
+  const int warp0 = blockIdx.x * wpb + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * wpb;
   constexpr int UN = 2;                          // runs in flight per warp
-  for (long long run0 = warp0; run0 < runs; run0 += nwarps * UN) {
-    float xk[UN][kMaxK];
+  const int n_iter = (runs + nwarps * UN - 1) / (nwarps * UN);     // warp-uniform trip count
+  for (int it = 0; it < n_iter; ++it) {
+    const int run0 = warp0 + it * nwarps * UN;
+    float xk[UN][KT];
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
-      const long long pix = ((run0 + (long long)u * nwarps) << 5) + lane;
+      const int pix = ((run0 + u * nwarps) << 5) + lane;
       const bool ok = pix < P;
-      const long long n = ok ? pix / HW : 0;
-      const long long hw = pix - n * HW;
+      const int n = ok ? pix / HW : 0;
+      const int hw = pix - n * HW;
+      const float *src = img + (size_t)n * K * HW + hw;
 #pragma unroll
-      for (int k = 0; k < kMaxK; ++k) xk[u][k] = (ok && k < K) ? img[(n * K + k) * HW + hw] : 0.f;
+      for (int k = 0; k < KT; ++k) xk[u][k] = (ok && k < K) ? src[(size_t)k * HW] : 0.f;
     }
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
-      const long long base = (run0 + (long long)u * nwarps) << 5;
+      const int base = (run0 + u * nwarps) << 5;
 #pragma unroll
       for (int j = 0; j < LPP; ++j) {
         const int pl = j * PPW + slot;
-        float xs[kMaxK];
+        float xs[KT];
 #pragma unroll
-        for (int k = 0; k < kMaxK; ++k) xs[k] = __shfl_sync(0xffffffffu, xk[u][k], pl);
-        const long long pp = base + pl;
+        for (int k = 0; k < KT; ++k) xs[k] = __shfl_sync(0xffffffffu, xk[u][k], pl);
+        const int pp = base + pl;
         if (pp < P) {
 #pragma unroll
           for (int ck = 0; ck < NCK; ++ck) {
@@ -313,19 +319,19 @@ pw_expand_kernel(const float *__restrict__ img, const float *__restrict__ w,
               for (int e = 0; e < 8; ++e) {
                 float v = br[e];
 #pragma unroll
-                for (int k = 0; k < kMaxK; ++k) v = fmaf(xs[k], wr[k][e], v);
+                for (int k = 0; k < KT; ++k) v = fmaf(xs[k], wr[k][e], v);
                 o.v[e] = v;
               }
             } else {
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
-                float v = sw[kMaxK * C + cg * 8 + e];
+                float v = sw[KT * C + cg * 8 + e];
 #pragma unroll
-                for (int k = 0; k < kMaxK; ++k) v = fmaf(xs[k], sw[k * C + cg * 8 + e], v);
+                for (int k = 0; k < KT; ++k) v = fmaf(xs[k], sw[k * C + cg * 8 + e], v);
                 o.v[e] = v;
               }
             }
-            st8(act + pp * C + cg * 8, o);
+            st8(act + (size_t)pp * C + cg * 8, o);
           }
         }
       }
@@ -333,60 +339,61 @@ pw_expand_kernel(const float *__restrict__ img, const float *__restrict__ w,
   }
 }
 
-template <typename T, int LPP, int NCK>
+template <typename T, int LPP, int NCK, int KT>
 __global__ void __launch_bounds__(256)
 pw_reduce_kernel(const T *__restrict__ act, const float *__restrict__ w,
-                 const float *__restrict__ bias, float *__restrict__ img, int N, long long HW,
+                 const float *__restrict__ bias, float *__restrict__ img, int P, int HW,
                  int K, int w_sc, int w_sk, float scale) {
   constexpr int C = 8 * LPP * NCK;
   constexpr int PPW = 32 / LPP;
   constexpr int RB = (LPP * NCK <= 8) ? LPP : (8 / NCK > 0 ? 8 / NCK : 1);   // rounds per load batch
-  __shared__ float sw[NCK > 1 ? kMaxK * C : 1];
+  __shared__ float sw[NCK > 1 ? KT * C : 1];
   const int lane = threadIdx.x & 31;
   const int sub = lane % LPP, slot = lane / LPP;
-  float wr[kMaxK][8];
+  float wr[KT][8];
   if (NCK == 1) {
 #pragma unroll
     for (int e = 0; e < 8; ++e)
 #pragma unroll
-      for (int k = 0; k < kMaxK; ++k)
-        wr[k][e] = (k < K) ? w[(long long)(sub * 8 + e) * w_sc + (long long)k * w_sk] * scale : 0.f;
+      for (int k = 0; k < KT; ++k)
+        wr[k][e] = (k < K) ? w[(sub * 8 + e) * w_sc + k * w_sk] * scale : 0.f;
   } else {
-    for (int i = threadIdx.x; i < kMaxK * C; i += blockDim.x) {
+    for (int i = threadIdx.x; i < KT * C; i += blockDim.x) {
       const int k = i / C, c = i - k * C;
-      sw[i] = (k < K) ? w[(long long)c * w_sc + (long long)k * w_sk] * scale : 0.f;
+      sw[i] = (k < K) ? w[c * w_sc + k * w_sk] * scale : 0.f;
     }
     __syncthreads();
   }
-  float bk[kMaxK];
+  float bk[KT];
 #pragma unroll
-  for (int k = 0; k < kMaxK; ++k) bk[k] = (bias && k < K) ? bias[k] : 0.f;
-  const long long P = (long long)N * HW;
-  const long long runs = (P + 31) >> 5;
-  const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
-  for (long long run = warp0; run < runs; run += nwarps) {
-    const long long base = run << 5;
-    float keep[kMaxK];
+  for (int k = 0; k < KT; ++k) bk[k] = (bias && k < K) ? bias[k] : 0.f;
+  const int runs = (P + 31) >> 5;
+  const int wpb = blockDim.x >> 5;
+  const int warp0 = blockIdx.x * wpb + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * wpb;
+  const int n_iter = (runs + nwarps - 1) / nwarps;                 // warp-uniform trip count
+  for (int it = 0; it < n_iter; ++it) {
+    const int base = (warp0 + it * nwarps) << 5;
+    float keep[KT];
 #pragma unroll
-    for (int k = 0; k < kMaxK; ++k) keep[k] = 0.f;
+    for (int k = 0; k < KT; ++k) keep[k] = 0.f;
 #pragma unroll
     for (int j0 = 0; j0 < LPP; j0 += RB) {
       typename RawOf<T>::type raw[RB][NCK];
 #pragma unroll
       for (int jj = 0; jj < RB; ++jj) {
-        const long long pp = base + (j0 + jj) * PPW + slot;
+        const int pp = base + (j0 + jj) * PPW + slot;
 #pragma unroll
         for (int ck = 0; ck < NCK; ++ck)
-          if (pp < P) raw[jj][ck] = ldraw8(act + pp * C + (sub + ck * LPP) * 8);
+          if (pp < P) raw[jj][ck] = ldraw8(act + (size_t)pp * C + (sub + ck * LPP) * 8);
       }
 #pragma unroll
       for (int jj = 0; jj < RB; ++jj) {
         const int j = j0 + jj;
-        const long long pp = base + j * PPW + slot;
-        float acc[kMaxK];
+        const int pp = base + j * PPW + slot;
+        float acc[KT];
 #pragma unroll
-        for (int k = 0; k < kMaxK; ++k) acc[k] = 0.f;
+        for (int k = 0; k < KT; ++k) acc[k] = 0.f;
         if (pp < P) {
 #pragma unroll
           for (int ck = 0; ck < NCK; ++ck) {
@@ -395,18 +402,18 @@ pw_reduce_kernel(const T *__restrict__ act, const float *__restrict__ w,
 #pragma unroll
               for (int e = 0; e < 8; ++e)
 #pragma unroll
-                for (int k = 0; k < kMaxK; ++k) acc[k] = fmaf(v.v[e], wr[k][e], acc[k]);
+                for (int k = 0; k < KT; ++k) acc[k] = fmaf(v.v[e], wr[k][e], acc[k]);
             } else {
               const int cg = sub + ck * LPP;
 #pragma unroll
-              for (int k = 0; k < kMaxK; ++k)
+              for (int k = 0; k < KT; ++k)
 #pragma unroll
                 for (int e = 0; e < 8; ++e) acc[k] = fmaf(v.v[e], sw[k * C + cg * 8 + e], acc[k]);
             }
           }
         }
 #pragma unroll
-        for (int k = 0; k < kMaxK; ++k) {
+        for (int k = 0; k < KT; ++k) {
 #pragma unroll
           for (int o = LPP / 2; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
           // pixel j*PPW + s of the run was summed by the lanes of slot s: hand it to lane j*PPW + s
@@ -415,68 +422,70 @@ pw_reduce_kernel(const T *__restrict__ act, const float *__restrict__ w,
         }
       }
     }
-    const long long pix = base + lane;
+    const int pix = base + lane;
     if (pix < P) {
-      const long long n = pix / HW, hw = pix - n * HW;
+      const int n = pix / HW, hw = pix - n * HW;
+      float *dst = img + (size_t)n * K * HW + hw;
 #pragma unroll
-      for (int k = 0; k < kMaxK; ++k)
-        if (k < K) img[(n * K + k) * HW + hw] = keep[k] + bk[k];
+      for (int k = 0; k < KT; ++k)
+        if (k < K) dst[(size_t)k * HW] = keep[k] + bk[k];
     }
   }
 }
 
 // dw(c,k) += scale * sum_pix act[pix,c] * img[k,pix];  dbias(c) += sum_pix act[pix,c] (optional:
 // the bias gradient of a from_rgb layer rides on the same pass over its output gradient)
-template <typename T, int LPP>
+template <typename T, int LPP, int KT>
 __global__ void __launch_bounds__(256)
 pw_wgrad_kernel(const T *__restrict__ act, const float *__restrict__ img, float *__restrict__ dw,
-                float *__restrict__ dbias, int N, long long HW, int K, int w_sc, int w_sk,
-                float scale) {
+                float *__restrict__ dbias, int P, int HW, int K, int w_sc, int w_sk, float scale) {
   constexpr int C = 8 * LPP;
   constexpr int PPW = 32 / LPP;
   constexpr int RB = LPP <= 8 ? LPP : 8;
-  __shared__ float sm[8][kMaxK + 1][C];          // per-warp partial sums
+  __shared__ float sm[8][KT + 1][C];             // per-warp partial sums
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int sub = lane % LPP, slot = lane / LPP;
-  float acc[kMaxK + 1][8];
+  float acc[KT + 1][8];
 #pragma unroll
-  for (int k = 0; k <= kMaxK; ++k)
+  for (int k = 0; k <= KT; ++k)
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[k][e] = 0.f;
-  const long long P = (long long)N * HW;
-  const long long runs = (P + 31) >> 5;
-  const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + wid;
-  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
-  for (long long run = warp0; run < runs; run += nwarps) {
-    const long long base = run << 5;
-    const long long pix = base + lane;
+  const int runs = (P + 31) >> 5;
+  const int wpb = blockDim.x >> 5;
+  const int warp0 = blockIdx.x * wpb + wid;
+  const int nwarps = gridDim.x * wpb;
+  const int n_iter = (runs + nwarps - 1) / nwarps;                 // warp-uniform trip count
+  for (int it = 0; it < n_iter; ++it) {
+    const int base = (warp0 + it * nwarps) << 5;
+    const int pix = base + lane;
     const bool ok = pix < P;
-    const long long n = ok ? pix / HW : 0;
-    const long long hw = pix - n * HW;
-    float gk[kMaxK];
+    const int n = ok ? pix / HW : 0;
+    const int hw = pix - n * HW;
+    const float *src = img + (size_t)n * K * HW + hw;
+    float gk[KT];
 #pragma unroll
-    for (int k = 0; k < kMaxK; ++k) gk[k] = (ok && k < K) ? img[(n * K + k) * HW + hw] : 0.f;
+    for (int k = 0; k < KT; ++k) gk[k] = (ok && k < K) ? src[(size_t)k * HW] : 0.f;
 #pragma unroll
     for (int j0 = 0; j0 < LPP; j0 += RB) {
       typename RawOf<T>::type raw[RB];
 #pragma unroll
       for (int jj = 0; jj < RB; ++jj) {
-        const long long pp = base + (j0 + jj) * PPW + slot;
-        if (pp < P) raw[jj] = ldraw8(act + pp * C + sub * 8);
+        const int pp = base + (j0 + jj) * PPW + slot;
+        if (pp < P) raw[jj] = ldraw8(act + (size_t)pp * C + sub * 8);
       }
 #pragma unroll
       for (int jj = 0; jj < RB; ++jj) {
         const int pl = (j0 + jj) * PPW + slot;
-        float g[kMaxK];
+        float g[KT];
 #pragma unroll
-        for (int k = 0; k < kMaxK; ++k) g[k] = __shfl_sync(0xffffffffu, gk[k], pl);
+        for (int k = 0; k < KT; ++k) g[k] = __shfl_sync(0xffffffffu, gk[k], pl);
         if (base + pl < P) {
           const F8 v = unpack8(raw[jj]);
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
 #pragma unroll
-            for (int k = 0; k < kMaxK; ++k) acc[k][e] = fmaf(v.v[e], g[k], acc[k][e]);
-            acc[kMaxK][e] += v.v[e];
+            for (int k = 0; k < KT; ++k) acc[k][e] = fmaf(v.v[e], g[k], acc[k][e]);
+            acc[KT][e] += v.v[e];
           }
         }
       }
@@ -484,7 +493,7 @@ pw_wgrad_kernel(const T *__restrict__ act, const float *__restrict__ img, float 
   }
   // lanes with the same `sub` hold partial sums of the same channels
 #pragma unroll
-  for (int k = 0; k <= kMaxK; ++k)
+  for (int k = 0; k <= KT; ++k)
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
 #pragma unroll
@@ -492,19 +501,18 @@ pw_wgrad_kernel(const T *__restrict__ act, const float *__restrict__ img, float 
     }
   if (slot == 0) {
 #pragma unroll
-    for (int k = 0; k <= kMaxK; ++k)
+    for (int k = 0; k <= KT; ++k)
 #pragma unroll
       for (int e = 0; e < 8; ++e) sm[wid][k][sub * 8 + e] = acc[k][e];
   }
   __syncthreads();
-  const int nw = blockDim.x >> 5;
-  for (int i = threadIdx.x; i < (kMaxK + 1) * C; i += blockDim.x) {
+  for (int i = threadIdx.x; i < (KT + 1) * C; i += blockDim.x) {
     const int k = i / C, c = i - k * C;
-    if (k < K || (k == kMaxK && dbias)) {
+    if (k < K || (k == KT && dbias)) {
       float s = 0.f;
-      for (int r = 0; r < nw; ++r) s += sm[r][k][c];
-      if (k < K) atomicAdd(dw + (long long)c * w_sc + (long long)k * w_sk, s * scale);
-      else atomicAdd(dbias + c, s);
+      for (int r = 0; r < wpb; ++r) s += sm[r][k][c];
+      if (k < K) atomicAdd(dw + c * w_sc + k * w_sk, s * scale);
+      else if (k == KT) atomicAdd(dbias + c, s);
     }
   }
 }
@@ -558,6 +566,16 @@ static bool pw_shape(int C, int *lpp, int *nck) {
     case 16: MACRO(16, 1) break;                                                           \
     default: MACRO(32, 1) break;                                                           \
   }
+// image-channel count as a template parameter: 1 (linear, mnist), 3 (rgb), 4 (rgb + label plane, 2)
+#define PG_PW_DISPATCH_K(K, BODY)                                                          \
+  if ((K) == 1) { constexpr int KT = 1; BODY }                                             \
+  else if ((K) == 3) { constexpr int KT = 3; BODY }                                        \
+  else { constexpr int KT = 4; BODY }
+// the warp-run kernels index with 32 bits
+static bool pw_fits32(long long P, int C, int K, long long HW, int w_sc, int w_sk) {
+  return P * C < (1ll << 31) && P + 32 < (1ll << 31) && (long long)C * w_sc + (long long)K * w_sk < (1ll << 31)
+         && HW < (1ll << 31);
+}
 
 extern "C" int pg_pw_expand(const float *img, const float *w, const float *bias, void *act, int N,
                             long long HW, int K, int C, int w_sc, int w_sk, float scale,
@@ -566,13 +584,16 @@ extern "C" int pg_pw_expand(const float *img, const float *w, const float *bias,
   if (int rc = check_pw("pg_pw_expand", N, HW, K, C)) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   int lpp = 0, nck = 0;
-  if (pw_shape(C, &lpp, &nck)) {
-    const int grid = bw_grid(((long long)N * HW + 31) / 32, 8 * 2);   // 8 warps x 2 runs per block pass
-#define PG_PWE(L, NC) pw_expand_kernel<T, L, NC><<<grid, 256, 0, s>>>(img, w, bias, (T *)act, N, HW, K, w_sc, w_sk, scale);
+  if (pw_shape(C, &lpp, &nck) && pw_fits32((long long)N * HW, C, K, HW, w_sc, w_sk)) {
+    const int P = (int)((long long)N * HW);
+    const int grid = bw_grid((P + 31) / 32, 8 * 2);   // 8 warps x 2 runs per block pass
+#define PG_PWE(L, NC) pw_expand_kernel<T, L, NC, KT><<<grid, 256, 0, s>>>(img, w, bias, (T *)act, P, (int)HW, K, w_sc, w_sk, scale);
     PG_DISPATCH_DTYPE(dtype, T, {
-      if (nck == 1) { PG_PW_DISPATCH_LPP(lpp, PG_PWE) }
-      else if (nck == 2) { PG_PWE(32, 2) }
-      else { PG_PWE(32, 4) }
+      PG_PW_DISPATCH_K(K, {
+        if (nck == 1) { PG_PW_DISPATCH_LPP(lpp, PG_PWE) }
+        else if (nck == 2) { PG_PWE(32, 2) }
+        else { PG_PWE(32, 4) }
+      })
     });
 #undef PG_PWE
     PG_CHECK_LAUNCH("pg_pw_expand");
@@ -601,13 +622,15 @@ extern "C" int pg_pw_reduce(const void *act, const float *w, const float *bias, 
   const long long P = (long long)N * HW;
   cudaStream_t s = (cudaStream_t)stream;
   int lpp = 0, nck = 0;
-  if (pw_shape(C, &lpp, &nck)) {
+  if (pw_shape(C, &lpp, &nck) && pw_fits32(P, C, K, HW, w_sc, w_sk)) {
     const int grid = bw_grid((P + 31) / 32, 8);
-#define PG_PWR(L, NC) pw_reduce_kernel<T, L, NC><<<grid, 256, 0, s>>>((const T *)act, w, bias, img, N, HW, K, w_sc, w_sk, scale);
+#define PG_PWR(L, NC) pw_reduce_kernel<T, L, NC, KT><<<grid, 256, 0, s>>>((const T *)act, w, bias, img, (int)P, (int)HW, K, w_sc, w_sk, scale);
     PG_DISPATCH_DTYPE(dtype, T, {
-      if (nck == 1) { PG_PW_DISPATCH_LPP(lpp, PG_PWR) }
-      else if (nck == 2) { PG_PWR(32, 2) }
-      else { PG_PWR(32, 4) }
+      PG_PW_DISPATCH_K(K, {
+        if (nck == 1) { PG_PW_DISPATCH_LPP(lpp, PG_PWR) }
+        else if (nck == 2) { PG_PWR(32, 2) }
+        else { PG_PWR(32, 4) }
+      })
     });
 #undef PG_PWR
     PG_CHECK_LAUNCH("pg_pw_reduce");
@@ -647,11 +670,11 @@ extern "C" int pg_pw_wgrad(const void *act, const float *img, float *dw, float *
   const long long P = (long long)N * HW;
   cudaStream_t s = (cudaStream_t)stream;
   int lpp = 0, nck = 0;
-  if (pw_shape(C, &lpp, &nck) && nck == 1) {
+  if (pw_shape(C, &lpp, &nck) && nck == 1 && pw_fits32(P, C, K, HW, w_sc, w_sk)) {
     // few enough blocks that the final atomics stay cheap, enough warps to cover the HBM latency
     const int grid = bw_grid((P + 31) / 32, 8 * 4, 4);
-#define PG_PWW(L, NC) pw_wgrad_kernel<T, L><<<grid, 256, 0, s>>>((const T *)act, img, dw, dbias, N, HW, K, w_sc, w_sk, scale);
-    PG_DISPATCH_DTYPE(dtype, T, { PG_PW_DISPATCH_LPP(lpp, PG_PWW) });
+#define PG_PWW(L, NC) pw_wgrad_kernel<T, L, KT><<<grid, 256, 0, s>>>((const T *)act, img, dw, dbias, (int)P, (int)HW, K, w_sc, w_sk, scale);
+    PG_DISPATCH_DTYPE(dtype, T, { PG_PW_DISPATCH_K(K, { PG_PW_DISPATCH_LPP(lpp, PG_PWW) }) });
 #undef PG_PWW
     PG_CHECK_LAUNCH("pg_pw_wgrad");
   }
