@@ -173,42 +173,30 @@ def run_product(args):
     ms_e2e = timed(e2e_step, args.steps)
     sampler.stop_flag = True
     # One more EAGER iteration on every rank (it contains the gradient all-reduces): counts the
-    # launches of an iteration and times the dominant kernel live.  Every 3x3 tensor-core conv
-    # launch (conv4_tc_kernel: forward, data-gradient and GP tangent convs) is issued three
-    # times back to back between two CUDA events on its stream — the call is idempotent, and the
-    # repeats hide the host launch latency of eager mode — and a third of the time is charged.
-    conv_recs = []
+    # launches of an iteration and records every launch served by the dominant kernel
+    # (conv4_tc_kernel: 3x3 forward, data-gradient and GP tangent convs, with and without the fused
+    # activation-backward epilogue).  Afterwards, with nothing else in flight, each recorded launch
+    # is re-issued three times back to back between two CUDA events on its stream (same operands,
+    # same kernel variant; the call is idempotent) and a third of the time is charged: the kernel
+    # timed ALONE, which is what the measured burst peak is the denominator for.
+    conv_calls = []
     orig_call = K._call
 
-    def timed_conv_call(name, *a):
+    def recording_call(name, *a):
         dims = None         # (N, H, W, Cin, Cout) of a launch served by conv4_tc_kernel
         if name == "pg_conv_tc" and a[11] == 9 and a[6] % 16 == 0 and a[7] % 8 == 0 and a[9] == a[10] \
                 and a[10] in (32, 64, 128):
             dims = a[5:10]
+            conv_calls.append((name, a, dims))
         elif name == "pg_conv_tc_actbwd":            # data-gradient conv with the fused act-backward
             dims = a[3:8]
-        if dims is not None:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            if name == "pg_conv_tc_actbwd":
-                cs_ptr = a[13]                       # the repeats must not add to the bias gradient
-                a = a[:13] + (None,) + a[14:]
-                orig_call(name, *(a[:13] + (cs_ptr,) + a[14:]))
-            else:
-                orig_call(name, *a)                  # the launch that belongs to the iteration
-            e0.record()
-            for _ in range(3):
-                orig_call(name, *a)
-            e1.record()
-            K.launches -= 3
-            n_, h_, w_, ci_, co_ = dims
-            conv_recs.append((2.0 * n_ * h_ * w_ * ci_ * co_ * 9, e0, e1))
-        else:
-            orig_call(name, *a)
+            conv_calls.append((name, a[:13] + (None,) + a[14:], dims))   # repeats: no bias-gradient add
+        orig_call(name, *a)
 
     K2 = K.launches
     was_graph = tr.use_graph
     tr.use_graph = False
-    K._call = timed_conv_call
+    K._call = recording_call
     try:
         tr.step(real, z, eps, step, alpha)
         torch.cuda.synchronize()
@@ -216,6 +204,20 @@ def run_product(args):
         K._call = orig_call
         tr.use_graph = was_graph
     eager_launches = K.launches - K2
+    conv_recs = []
+    st_now = torch.cuda.current_stream().cuda_stream
+    for name, a, dims in conv_calls:
+        a = a[:-1] + (st_now,)                       # everything on the current stream
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        orig_call(name, *a)                          # warm (descriptor cache, L2 state of a chain)
+        e0.record()
+        for _ in range(3):
+            orig_call(name, *a)
+        e1.record()
+        n_, h_, w_, ci_, co_ = dims
+        conv_recs.append((2.0 * n_ * h_ * w_ * ci_ * co_ * 9, e0, e1))
+    torch.cuda.synchronize()
+    K.launches = K2 + eager_launches
     conv_flops = sum(f for f, _, _ in conv_recs)
     conv_ms = sum(e0.elapsed_time(e1) / 3.0 for _, e0, e1 in conv_recs)
     # data-parallel correctness on the real NCCL path: after the timed steps every rank must hold
@@ -288,8 +290,9 @@ def roofline(conv_flops, conv_ms, n_conv, step_ms, step_tf, res, timed_s):
                            "frac_of_sustained": round(step_tf / sustained, 4),
                            "note": "14 F_D + 3 F_G = %.2f GFLOP/img over the step time"
                                    % (step_flops(res) / 1e9)},
-            "note": "algorithmic conv FLOPs of the kernel's launches / their device time (CUDA events, "
-                    "each launch repeated 3x back to back in one extra eager iteration); peaks %s" % which}
+            "note": "algorithmic conv FLOPs of the kernel's launches of one iteration / their device time "
+                    "(CUDA events; every launch of the iteration re-issued alone, 3x back to back); "
+                    "peaks %s" % which}
 
 
 def cpu_baseline(res, B, alpha, sample_batch=32, iters=2):

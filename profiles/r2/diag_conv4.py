@@ -7,6 +7,7 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+os.environ["PG_DBG_LIVE"] = "1"     # the library re-reads PG_DBG on every launch
 import torch  # noqa: E402
 import progan_b200  # noqa: E402
 from progan_b200.kernels import ConvOp, EPI_PN_LRELU, EPI_LINEAR  # noqa: E402

@@ -1,5 +1,6 @@
 // Error channel + device query of the C-ABI (include/progan_b200.h).
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace pg {
 static thread_local char g_err[512] = "";
@@ -13,6 +14,18 @@ void set_error(const char *fmt, ...) {
 
 extern "C" const char *pg_last_error(void) { return pg::g_err; }
 extern "C" int pg_abi_version(void) { return 1; }
+
+namespace pg {
+// PG_PDL: 0 = no programmatic-serialization attribute, 1 = small launches (default), 2 = all
+// (read once per process)
+int pdl_mode() {
+  static const int mode = [] {
+    const char *e = getenv("PG_PDL");
+    return e ? atoi(e) : 1;
+  }();
+  return mode;
+}
+}  // namespace pg
 
 extern "C" int pg_device_info(int *sm_count, int *cc_major, int *cc_minor) {
   int dev = 0;

@@ -29,6 +29,7 @@ pn_lrelu_grad_kernel(const T *__restrict__ t_in, const T *__restrict__ dy,
                      T *__restrict__ out0, T *__restrict__ out1, long long P, int C,
                      float slope, int use_pn, int pool_h, int pool_w,
                      float *__restrict__ colsum) {
+  pg::grid_dep_sync();
   // first order : out0 = da (+ t_in when ADD: a second gradient contribution to the same
   //               pre-activation, summed here instead of by a separate add kernel)
   // second order: out0 = cot_dy, out1 = cot_a
@@ -179,6 +180,7 @@ pn_lrelu_bwd_pooled_kernel(const T *__restrict__ addend, const T *__restrict__ d
                            const T *__restrict__ y, const float *__restrict__ rr,
                            T *__restrict__ da, unsigned NQ, unsigned H2, unsigned W2, int C,
                            float slope, int use_pn, float *__restrict__ colsum) {
+  pg::grid_dep_sync();
   using Raw = typename RawOf<T>::type;
   const int sub = threadIdx.x % TPP;
   const unsigned qpb = blockDim.x / TPP;
@@ -271,10 +273,10 @@ static int launch_pn_grad(const T *t, const T *dy, const T *y, const float *r, T
     const int grid = bw_grid(NQ, qpb, 3);                                                  \
     const size_t sm = colsum ? (size_t)qpb * C * sizeof(float) : 0;                        \
     if (t != nullptr)                                                                      \
-      pn_lrelu_bwd_pooled_kernel<T, TPP, true><<<grid, 256, sm, s>>>(                      \
+      pg::launcher(pn_lrelu_bwd_pooled_kernel<T, TPP, true>, grid, 256, sm, s)(                      \
           t, dy, y, r, o0, NQ, H_ / 2, W_ / 2, C, slope, use_pn, colsum);                  \
     else                                                                                   \
-      pn_lrelu_bwd_pooled_kernel<T, TPP, false><<<grid, 256, sm, s>>>(                     \
+      pg::launcher(pn_lrelu_bwd_pooled_kernel<T, TPP, false>, grid, 256, sm, s)(                     \
           t, dy, y, r, o0, NQ, H_ / 2, W_ / 2, C, slope, use_pn, colsum);                  \
   }
     if (nch <= 4) PG_LAUNCH_PQ(4)
@@ -291,10 +293,10 @@ static int launch_pn_grad(const T *t, const T *dy, const T *y, const float *r, T
     const int grid = bw_grid(P, (int)ppb * U_);                                           \
     const size_t sm = (!SECOND && colsum) ? (size_t)ppb * C * sizeof(float) : 0;          \
     if (!SECOND && t != nullptr)                                                          \
-      pn_lrelu_grad_kernel<T, TPP, MAXI, false, U_, true><<<grid, 256, sm, s>>>(          \
+      pg::launcher(pn_lrelu_grad_kernel<T, TPP, MAXI, false, U_, true>, grid, 256, sm, s)(          \
           t, dy, y, r, o0, o1, P, C, slope, use_pn, pool_h, pool_w, colsum);              \
     else                                                                                  \
-      pn_lrelu_grad_kernel<T, TPP, MAXI, SECOND, U_, false><<<grid, 256, sm, s>>>(        \
+      pg::launcher(pn_lrelu_grad_kernel<T, TPP, MAXI, SECOND, U_, false>, grid, 256, sm, s)(        \
           t, dy, y, r, o0, o1, P, C, slope, use_pn, pool_h, pool_w, colsum);              \
   }
   if (nch <= 4) PG_LAUNCH_PN(4, 1)
@@ -315,6 +317,7 @@ static int launch_pn_grad(const T *t, const T *dy, const T *y, const float *r, T
 template <typename T>
 __global__ void __launch_bounds__(256)
 colsum_kernel(const T *__restrict__ x, float *__restrict__ out, long long P, int C) {
+  pg::grid_dep_sync();
   extern __shared__ float sm[];  // [rows][C]
   const int nch = C >> 3;
   const int rows = blockDim.x / nch;
@@ -373,6 +376,7 @@ template <typename T, int MAXV>
 __global__ void __launch_bounds__(256)
 pn_lrelu_fwd_kernel(const T *__restrict__ a, T *__restrict__ y, float *__restrict__ r, long long P,
                     int C, float slope, int use_pn) {
+  pg::grid_dep_sync();
   using Raw = typename RawOf<T>::type;
   const int lane = threadIdx.x & 31;
   const int nch = C >> 3;
@@ -422,11 +426,11 @@ extern "C" int pg_pn_lrelu_fwd(const void *a, void *y, float *r, long long P, in
   const int grid = (int)(want < 148 * 8 ? want : 148 * 8);
   PG_DISPATCH_DTYPE(dtype, T, {
     if (C <= 256)
-      pn_lrelu_fwd_kernel<T, 1><<<grid, 256, 0, (cudaStream_t)stream>>>((const T *)a, (T *)y, r, P, C, slope, use_pn);
+      pg::launcher(pn_lrelu_fwd_kernel<T, 1>, grid, 256, 0, (cudaStream_t)stream)((const T *)a, (T *)y, r, P, C, slope, use_pn);
     else if (C <= 512)
-      pn_lrelu_fwd_kernel<T, 2><<<grid, 256, 0, (cudaStream_t)stream>>>((const T *)a, (T *)y, r, P, C, slope, use_pn);
+      pg::launcher(pn_lrelu_fwd_kernel<T, 2>, grid, 256, 0, (cudaStream_t)stream)((const T *)a, (T *)y, r, P, C, slope, use_pn);
     else
-      pn_lrelu_fwd_kernel<T, 4><<<grid, 256, 0, (cudaStream_t)stream>>>((const T *)a, (T *)y, r, P, C, slope, use_pn);
+      pg::launcher(pn_lrelu_fwd_kernel<T, 4>, grid, 256, 0, (cudaStream_t)stream)((const T *)a, (T *)y, r, P, C, slope, use_pn);
   });
   PG_CHECK_LAUNCH("pg_pn_lrelu_fwd");
 }
@@ -479,7 +483,7 @@ extern "C" int pg_colsum(const void *x, float *out, long long P, int C, int dtyp
   const int rows = 256 / nch;
   const int grid = bw_grid(P, rows * 16, 4);
   const size_t smem = (size_t)rows * C * sizeof(float);
-  PG_DISPATCH_DTYPE(dtype, T, colsum_kernel<T><<<grid, 256, smem, (cudaStream_t)stream>>>(
+  PG_DISPATCH_DTYPE(dtype, T, pg::launcher(colsum_kernel<T>, grid, 256, smem, (cudaStream_t)stream)(
                                   (const T *)x, out, P, C));
   PG_CHECK_LAUNCH("pg_colsum");
 }

@@ -1,9 +1,9 @@
 // 3x3 pad-1 implicit-GEMM convolution, third generation ("single halo box") kernel.
 //
-// conv3_tc.cu is bound by L2->SM bandwidth (~30-40 B/cycle/SM measured): per 128-pixel tile
-// and 64-channel block it fetches three 8x18 activation boxes (one per horizontal tap) and,
-// when the weights do not fit in smem, the full weight matrix per two tiles.  This kernel
-// fetches per tile and channel block
+// A kernel that fetches one activation box per horizontal tap (three 8x18 boxes per 128-pixel
+// tile and 64-channel block) and the whole weight matrix per two tiles is bound by L2->SM
+// bandwidth (~30-40 B/cycle/SM measured in round 1).  This kernel fetches per tile and channel
+// block
 //   * ONE 10(w) x 18(h) pixel box: all nine taps are start-address offsets
 //     (dh*10 + dw) * row_bytes into it; a tile row is 8 consecutive pixels = one 8-row swizzle
 //     atom that starts on a 128-byte (not 1024-byte) boundary, atoms SBO = 10 rows apart.
@@ -60,16 +60,32 @@ conv4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   constexpr uint32_t row_bytes = BK * 2u;                          // 128 or 64
   constexpr uint32_t box_real = 18u * 10u * row_bytes;
   constexpr uint32_t kBoxPad = (box_real + 1023u) / 1024u * 1024u;
+  // PAIR: the two CTAs of a cluster execute ONE M = 256 MMA (tcgen05.mma.cta_group::2): each
+  // CTA feeds its own 128-pixel tile (A) and HALF of the weight rows (B).  Per MMA a CTA then
+  // reads 4 KB of A + N*16 B of B instead of 4 KB + N*32 B (smem operand bandwidth, 128 B/clk, is
+  // what bounds every N <= 128 layer), and half of the packed weights per CTA is small enough to
+  // stay RESIDENT for every layer of the network (128 -> 128: 144 KB), which removes the weight
+  // stream — the other large consumer of smem bandwidth — altogether.  Rank 0 (leader) issues
+  // all MMAs; both CTAs run an activation producer and the epilogue for their own tile.
+  //   afull[s]  (leader)  count 2: each CTA's producer arms it with its box bytes; both TMA
+  //                       loads (.cta_group::2) complete_tx on the leader's barrier
+  //   aempty[s], tfull[a] (each CTA) count 1: tcgen05.commit.cta_group::2, multicast to the pair
+  //   tempty[a] (leader)  count 8: one arrive per epilogue warp of group a in both CTAs
+  constexpr bool PAIR = RES && CL == 2;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t w_bytes = RES ? (uint32_t)(9 * p.ncb * p.wtile_bytes)
+  const uint32_t w_bytes = RES ? (uint32_t)(9 * p.ncb * p.wtile_bytes) / (PAIR ? 2u : 1u)
                                : (uint32_t)(p.w_stages * p.wtile_bytes);
   const uint32_t smem_w = base;
   const uint32_t smem_a = base + w_bytes;
   const uint32_t smem_out = smem_a + (uint32_t)(p.a_stages * MT) * kBoxPad;
   // one staging tile (128 pixels x min(COUT, 64) channels) per epilogue group, and one pooled
   // staging tile (32 pooled pixels) per group when the launch asks for the fused average pool
+  // (two of each per group for COUT <= 64: a TMA store needs ~1000 cycles to read its tile, longer
+  // than the whole epilogue of a 128 x 32 tile, so with ONE tile per group the next tile's staging
+  // writes waited for it every time - measured 920 cycles per 128 x 32 tile for the epilogue alone)
   constexpr uint32_t kHC = COUT > 64 ? 64u : (uint32_t)COUT;
-  constexpr uint32_t out_bytes = 2u * 128u * kHC * 2u;
+  constexpr uint32_t kNSB = COUT > 64 ? 1u : 2u;
+  constexpr uint32_t out_bytes = 2u * kNSB * 128u * kHC * 2u;
   const uint32_t smem_pool = smem_out + out_bytes;
   const uint32_t bar_base = smem_pool + (p.pool ? out_bytes / 4u : 0u);
   auto afull = [&](int s) { return bar_base + 8u * (uint32_t)s; };
@@ -101,7 +117,7 @@ conv4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.a_stages; ++s) {
-      mbar_init(afull(s), 1);
+      mbar_init(afull(s), PAIR ? 2 : 1);
       mbar_init(aempty(s), 1);
     }
     for (int s = 0; s < p.w_stages; ++s) {
@@ -110,18 +126,27 @@ conv4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull(a), 1);
-      mbar_init(tempty(a), kC4EpiThreads / 2);     // the epilogue group that owns stage a
+      mbar_init(tempty(a), PAIR ? 8 : 4);          // one arrive per warp of the group that owns stage a
     }
-    mbar_init(wres_bar, 1);
+    mbar_init(wres_bar, PAIR ? 2 : 1);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  if (!PAIR && warp == 2) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  // everything above touches only this CTA's shared memory / TMEM: it overlaps the tail of the
+  // previous kernel; from here on the predecessors' results are read
+  pg::grid_dep_sync();
   for (int c = threadIdx.x; c < COUT; c += kC4Threads) bias_ptr[c] = p.bias ? p.bias[c] : 0.f;
   tc_fence_before();
   __syncthreads();
   if (CL > 1) cluster_sync_all();          // peers' barriers exist before any multicast lands
+  if (PAIR) {                              // pair allocation: both CTAs, after the cluster is up
+    if (warp == 2) tmem_alloc2(tmem_slot, (uint32_t)p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+  }
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  const bool leader = rank == 0;
   constexpr int acc_stride = MT * COUT;       // TMEM columns per accumulator stage
 
   if (warp == 0) {
@@ -134,18 +159,21 @@ conv4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         for (int cb = 0; cb < NCB; ++cb) {
           mbar_wait(aempty(as), aph ^ 1u);
           if (p.dbg & 8) {            // experiment: no activation loads
-            mbar_arrive(afull(as));
+            if (!PAIR || leader) mbar_arrive(afull(as));
+            else mbar_arrive_remote(mapa_shared(afull(as), 0));
             if (++as == p.a_stages) { as = 0; aph ^= 1u; }
             continue;
           }
-          mbar_expect_tx(afull(as), (uint32_t)MT * box_real);
+          if (!PAIR || leader) mbar_expect_tx(afull(as), (uint32_t)MT * box_real);
+          else mbar_expect_tx_remote(mapa_shared(afull(as), 0), (uint32_t)MT * box_real);
           for (int mt = 0; mt < MT; ++mt) {
             const int tile = st * MT + mt;
             const int tw = tile % p.tiles_w;
             const int th = (tile / p.tiles_w) % p.tiles_h;
             const int n = tile / (p.tiles_w * p.tiles_h);
-            tma_load_4d(smem_a + (uint32_t)(as * MT + mt) * kBoxPad, &tmap_x, afull(as), cb * BK,
-                        tw * 8 - 1, th * 16 - 1, n);
+            const uint32_t dst = smem_a + (uint32_t)(as * MT + mt) * kBoxPad;
+            if (PAIR) tma_load_4d_pair(dst, &tmap_x, afull(as), cb * BK, tw * 8 - 1, th * 16 - 1, n);
+            else tma_load_4d(dst, &tmap_x, afull(as), cb * BK, tw * 8 - 1, th * 16 - 1, n);
           }
           if (++as == p.a_stages) { as = 0; aph ^= 1u; }
         }
@@ -154,7 +182,15 @@ conv4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   } else if (warp == 3) {
     // ===================== weight producer =====================
     if (lane == 0) {
-      if (RES) {
+      if (PAIR) {                 // this CTA's half of the rows of every tap tile, once
+        const uint32_t whalf = (uint32_t)p.wtile_bytes / 2u;
+        if (leader) mbar_expect_tx(wres_bar, w_bytes);
+        else mbar_expect_tx_remote(mapa_shared(wres_bar, 0), w_bytes);
+        for (int tap = 0; tap < 9; ++tap)
+          for (int cb = 0; cb < p.ncb; ++cb)
+            tma_load_2d_pair(smem_w + (uint32_t)(tap * p.ncb + cb) * whalf, &tmap_w, wres_bar,
+                             tap * p.Cin + cb * BK, (int)rank * (COUT / 2));
+      } else if (RES) {
         mbar_expect_tx(wres_bar, w_bytes);
         for (int tap = 0; tap < 9; ++tap)
           for (int cb = 0; cb < p.ncb; ++cb)
@@ -196,10 +232,10 @@ conv4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     constexpr uint32_t hi_a = ((sbo_a >> 4) & 0x3FFFu) | (1u << 14) | (layout << 29);
     constexpr uint32_t hi_b = ((sbo_b >> 4) & 0x3FFFu) | (1u << 14) | (layout << 29);
     constexpr uint32_t lbo_lo = 1u << 16;
-    constexpr uint32_t wtile16 = (uint32_t)(COUT * BK * 2) >> 4;
+    constexpr uint32_t wtile16 = (uint32_t)((PAIR ? COUT / 2 : COUT) * BK * 2) >> 4;
     constexpr uint32_t box16 = kBoxPad >> 4;
-    const uint32_t idesc = make_idesc_bf16(128, COUT, 0, 0);
-    if (RES) {
+    const uint32_t idesc = make_idesc_bf16(PAIR ? 256 : 128, COUT, 0, 0);
+    if (RES && (!PAIR || leader)) {
       mbar_wait(wres_bar, 0);
       tc_fence_after();
     }
@@ -208,7 +244,7 @@ conv4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     // ONE thread is elected for the whole kernel, and the barrier waits that the NEXT tap /
     // channel block / tile needs are performed just before the LAST TWO MMAs of the current tap,
     // i.e. while two instructions are still in flight.
-    if (elect_one_sync()) {
+    if ((!PAIR || leader) && elect_one_sync()) {
       int as = 0, ws = 0, acc = 0;
       uint32_t aph = 0, wph = 0, acc_phase = 0;
       const int stride = ncl * CL;
@@ -261,7 +297,8 @@ conv4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
                 const uint64_t ad = ((uint64_t)hi_a << 32) |
                                     (uint64_t)(a16 + (uint32_t)mt * box16 + a_off16 + (uint32_t)(k * 2));
                 const uint64_t bd = ((uint64_t)hi_b << 32) | (uint64_t)(b16 + (uint32_t)(k * 2));
-                umma_bf16(d_base + (uint32_t)(mt * COUT), ad, bd, idesc, (cb | tap | k) ? 1u : 0u);
+                if (PAIR) umma_bf16_2cta(d_base + (uint32_t)(mt * COUT), ad, bd, idesc, (cb | tap | k) ? 1u : 0u);
+                else umma_bf16(d_base + (uint32_t)(mt * COUT), ad, bd, idesc, (cb | tap | k) ? 1u : 0u);
               }
             }
             if (!RES) {
@@ -271,8 +308,13 @@ conv4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
               wph = wph_next;
             }
             if (tap == 8) {
-              umma_commit(aempty(as));
-              if (cb == NCB - 1) umma_commit(tfull(acc));
+              if (PAIR) {
+                umma_commit2(aempty(as));
+                if (cb == NCB - 1) umma_commit2(tfull(acc));
+              } else {
+                umma_commit(aempty(as));
+                if (cb == NCB - 1) umma_commit(tfull(acc));
+              }
             }
             if (!(ok_w && ok_a && ok_t)) {
               if (!ok_w) mbar_wait(wfull(ws), wph);            // ws / wph already advanced
@@ -311,16 +353,24 @@ conv4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     const int row = q * 32 + lane;                  // tile row: pixel (hl = row/8, wl = row%8)
     const int gt = (int)threadIdx.x - 128 - g * 128;   // 0..127 inside the group
     const int bar_id = 1 + g;
-    uint8_t *stage_ptr = out_ptr + (size_t)g * 128 * row_b;
-    const uint32_t stage_s = smem_out + (uint32_t)g * 128u * (uint32_t)row_b;
-    uint8_t *pool_g = pool_ptr + (size_t)g * 32 * row_b;
-    const uint32_t pool_s = smem_pool + (uint32_t)g * 32u * (uint32_t)row_b;
+    constexpr int NSB = (int)kNSB;                  // staging tiles per group (alternating)
+    int sbuf = 0;
     const float invC = 1.f / (float)COUT;
     const float scale = p.scale, slope = p.slope;
     const float inv_slope = 1.f / slope;
     const bool pn = ABW ? (p.use_pn != 0) : (p.epi == PG_EPI_PN_LRELU);
     const bool act = !ABW && p.epi != PG_EPI_LINEAR;
     auto group_bar = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory"); };
+    // this warp has read its quadrant of accumulator stage g: one arrive per warp on the MMA
+    // issuer's barrier (the pair's leader owns it)
+    auto release_stage = [&]() {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (!PAIR || leader) mbar_arrive(tempty(g));
+        else mbar_arrive_remote(mapa_shared(tempty(g), 0));
+      }
+    };
     float csum[2] = {0.f, 0.f};                     // ABW: this lane's share of the bias gradient
     uint32_t ph = 0;
     int it = 0;
@@ -340,6 +390,11 @@ conv4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         const long long pix = ((long long)n * p.H + (h0 + (row >> 3))) * p.W + w0 + (row & 7);
         const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) +
                                 (uint32_t)(g * acc_stride + mt * COUT);
+        uint8_t *stage_ptr = out_ptr + (size_t)(g * NSB + sbuf) * 128 * row_b;
+        const uint32_t stage_s = smem_out + (uint32_t)(g * NSB + sbuf) * 128u * (uint32_t)row_b;
+        uint8_t *pool_g = pool_ptr + (size_t)(g * NSB + sbuf) * 32 * row_b;
+        const uint32_t pool_s = smem_pool + (uint32_t)(g * NSB + sbuf) * 32u * (uint32_t)row_b;
+        if (NSB > 1) sbuf ^= 1;
         float v[HC];                         // accumulators are loaded in place (one register set)
         uint32_t *vr = reinterpret_cast<uint32_t *>(v);
         // ---- pass 1: the first HC columns stay in registers
@@ -353,14 +408,16 @@ conv4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           for (int i = 0; i < HC / 8; ++i) yraw[i] = __ldg(yp + i);
           if (pn) rp = __ldg(p.r_prev + pix);
         }
-        // the group's staging tile is free once its previous TMA store has read it
-        if (gt == 0) tma_store_wait_read0();
+        // this staging tile is free once the TMA store(s) that last used it have read it: with
+        // two tiles per group the previous tile's stores may still be in flight
+        if (gt == 0) {
+          if (NSB == 1) tma_store_wait_read0();
+          else if (p.pool) tma_store_wait_read<2>();
+          else tma_store_wait_read<1>();
+        }
         group_bar();
         tmem_ld_wait();
-        if (NH == 1 && mt == MT - 1) {       // stage fully read: hand it back to the MMA warp
-          tc_fence_before();
-          mbar_arrive(tempty(g));
-        }
+        if (NH == 1 && mt == MT - 1) release_stage();   // stage fully read: back to the MMA warp
         float red = 0.f;                     // sum of squares (forward) or <p,u> (fused backward)
         if constexpr (!ABW) {
 #pragma unroll
@@ -409,10 +466,7 @@ conv4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           }
         }
         if (p.dbg & 2) {                     // experiment: accumulator drain only
-          if (NH == 2 && mt == MT - 1) {
-            tc_fence_before();
-            mbar_arrive(tempty(g));
-          }
+          if (NH == 2 && mt == MT - 1) release_stage();
           continue;
         }
         float r = 1.f;
@@ -427,10 +481,7 @@ conv4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
             if (gt == 0) tma_store_wait_read0();     // first half's store has read the staging tile
             group_bar();
             tmem_ld_wait();
-            if (mt == MT - 1) {
-              tc_fence_before();
-              mbar_arrive(tempty(g));
-            }
+            if (mt == MT - 1) release_stage();
 #pragma unroll
             for (int j = 0; j < HC; ++j)
               v[j] = fmaf(__uint_as_float(vr[j]), scale, bias_ptr[HC + j]);
@@ -566,7 +617,8 @@ conv4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   if (CL > 1) cluster_sync_all();          // no CTA exits while a peer may still signal it
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    if (PAIR) tmem_dealloc2(tmem_base, (uint32_t)p.tmem_cols);
+    else tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
 }
 
@@ -587,19 +639,26 @@ static cudaError_t launch_c4(const CUtensorMap &tx, const CUtensorMap &tw, const
   cfg.blockDim = dim3(kC4Threads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = CL;
-  at[0].val.clusterDim.y = 1;
-  at[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_for(p.num_super) ? 1 : 0;
+  at[1].id = cudaLaunchAttributeClusterDimension;
+  at[1].val.clusterDim.x = CL;
+  at[1].val.clusterDim.y = 1;
+  at[1].val.clusterDim.z = 1;
   cfg.attrs = at;
-  cfg.numAttrs = CL > 1 ? 1 : 0;
+  cfg.numAttrs = CL > 1 ? 2 : 1;
   if (max_ctas == 0) {
     max_ctas = sm_count();
     if (CL > 1) {
       int ncl = 0;
       cfg.gridDim = dim3((unsigned)(sm_count() / CL * CL));
-      if (cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg) == cudaSuccess && ncl > 0)
+      cfg.attrs = at + 1;          // the occupancy query takes the cluster attribute only
+      cfg.numAttrs = 1;
+      const bool occ_ok = cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg) == cudaSuccess && ncl > 0;
+      cfg.attrs = at;
+      cfg.numAttrs = 2;
+      if (occ_ok)
         max_ctas = ncl * CL;
       else
         (void)cudaGetLastError();
@@ -622,11 +681,22 @@ int conv4_tc_launch(const void *x, const void *wp, const float *bias, void *y, f
                     int use_pn, void *y_pool) {
   const bool abw = y_prev != nullptr;
   if (abw && (y_pool || Cout > 64)) return PG_ERR_UNSUPPORTED;
-  if (const char *e = getenv("PG_CONV_V4"))
-    if (atoi(e) == 0) return PG_ERR_UNSUPPORTED;
-  int min_h = 16;
-  if (const char *e = getenv("PG_C4_MINH")) min_h = atoi(e);
-  if (H % 16 || H < min_h || W % 8 || !(Cout == 32 || Cout == 64 || Cout == 128) || Cin % 32)
+  // experiment knobs, read ONCE per process (PG_DBG: epilogue / load / MMA switches for
+  // profiles/r2/diag_conv4.py; PG_C4_RES / PG_C4_MT / PG_C4_CL: force a kernel variant)
+  struct Knobs {
+    int dbg = 0, res = -1, mt = -1, cl = -1, pair = 1;
+    bool live = false;          // PG_DBG_LIVE=1: re-read PG_DBG on every launch (diag script)
+    Knobs() {
+      if (const char *e = getenv("PG_DBG")) dbg = atoi(e);
+      if (const char *e = getenv("PG_C4_RES")) res = atoi(e);
+      if (const char *e = getenv("PG_C4_MT")) mt = atoi(e);
+      if (const char *e = getenv("PG_C4_CL")) cl = atoi(e);
+      if (const char *e = getenv("PG_C4_PAIR")) pair = atoi(e);     // 0: no CTA-pair (cta_group::2) variants
+      if (const char *e = getenv("PG_DBG_LIVE")) live = atoi(e) != 0;
+    }
+  };
+  static const Knobs knobs;
+  if (H % 16 || H < 16 || W % 8 || !(Cout == 32 || Cout == 64 || Cout == 128) || Cin % 32)
     return PG_ERR_UNSUPPORTED;
   tc::Conv4Params p;
   p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
@@ -641,23 +711,37 @@ int conv4_tc_launch(const void *x, const void *wp, const float *bias, void *y, f
   p.epi = epi; p.scale = scale; p.slope = slope; p.bias = bias; p.r_out = r_out;
   p.y_prev = (const __nv_bfloat16 *)y_prev; p.r_prev = r_prev; p.colsum = colsum; p.use_pn = use_pn;
   p.pool = y_pool != nullptr;
-  p.dbg = 0;
-  if (const char *e = getenv("PG_DBG")) p.dbg = atoi(e);
+  p.dbg = knobs.dbg;
+  if (knobs.live)
+    if (const char *e = getenv("PG_DBG")) p.dbg = atoi(e);
   const int hc = Cout > 64 ? 64 : Cout;      // channels per staging tile; one tile per epilogue group
-  const int out_bytes = 2 * 128 * hc * 2 + (y_pool ? 2 * 32 * hc * 2 : 0);   // staging (+ pooled tiles)
+  const int nsb = Cout > 64 ? 1 : 2;         // staging tiles per group
+  const int out_bytes = 2 * nsb * 128 * hc * 2 + (y_pool ? 2 * nsb * 32 * hc * 2 : 0);   // staging (+ pooled tiles)
   const int misc = 1024 + 8 * (2 * tc::kC4MaxA + 2 * tc::kC4MaxW + 5) + 16 + 16 + 128 * 4 + 2 * 128 * 4 + 64;
   const int budget = 227 * 1024 - out_bytes - misc;
   const int wres = 9 * p.ncb * p.wtile_bytes;
-  int force_res = -1, force_mt = -1, force_cl = -1;
-  if (const char *e = getenv("PG_C4_RES")) force_res = atoi(e);
-  if (const char *e = getenv("PG_C4_MT")) force_mt = atoi(e);
-  if (const char *e = getenv("PG_C4_CL")) force_cl = atoi(e);
+  const int force_res = knobs.res, force_mt = knobs.mt, force_cl = knobs.cl;
   int res = (wres + 2 * p.box_pad <= budget) ? 1 : 0;
   if (force_res >= 0 && (force_res == 0 || wres + 2 * p.box_pad <= budget)) res = force_res;
   if (BK == 32 && !res) return PG_ERR_UNSUPPORTED;
   if (!res && Cout < 64) return PG_ERR_UNSUPPORTED;
   int MT, CL;
-  if (res) {
+  // CTA pair (M = 256 MMAs, half of the weights resident in each CTA) wherever it fits
+  // ... and where the MMA phase of a tile is long enough to hide the cross-CTA handshakes of a
+  // pair (tfull multicast -> peer epilogue -> remote tempty arrive: ~2x the latency of the local
+  // protocol with the same two accumulator stages).  Measured (profiles/r2/diag_pair*.txt): K = 9 x 128
+  // layers gain 7-9 %, the Cin <= 64 layers at 128 px LOSE 3-30 %; PG_C4_PAIR=2 forces pairs everywhere.
+  const bool pair = knobs.pair != 0 && force_res != 0 && p.num_tiles % 2 == 0 &&
+                    wres / 2 + 2 * p.box_pad <= budget && (Cin >= 128 || knobs.pair == 2);
+  if (pair) {
+    res = 1;
+    CL = 2;
+    MT = (p.num_tiles % 4 == 0 && 4 * Cout <= 512 && wres / 2 + 4 * p.box_pad <= budget) ? 2 : 1;
+    if (force_mt == 1) MT = 1;
+    p.a_stages = (budget - wres / 2) / (MT * p.box_pad);
+    if (p.a_stages > tc::kC4MaxA) p.a_stages = tc::kC4MaxA;
+    p.w_stages = 0;
+  } else if (res) {
     CL = 1;
     // two pixel tiles per accumulator stage when they fit: per-tile handshakes amortise
     MT = (p.num_tiles % 2 == 0 && 4 * Cout <= 512 && wres + 4 * p.box_pad <= budget) ? 2 : 1;
@@ -681,7 +765,7 @@ int conv4_tc_launch(const void *x, const void *wp, const float *bias, void *y, f
   int cols = 2 * MT * Cout;
   p.tmem_cols = 32;
   while (p.tmem_cols < cols) p.tmem_cols <<= 1;
-  const size_t smem = (size_t)(res ? wres : p.w_stages * p.wtile_bytes) +
+  const size_t smem = (size_t)(pair ? wres / 2 : (res ? wres : p.w_stages * p.wtile_bytes)) +
                       (size_t)p.a_stages * MT * p.box_pad + out_bytes + misc;
 
   CUtensorMap tx, tw_, ty;
@@ -721,13 +805,15 @@ int conv4_tc_launch(const void *x, const void *wp, const float *bias, void *y, f
             : tc::launch_c4<BK_, NCB_, MT_, RES_, CO_, CL_, false>(tx, tw_, ty, typ, p, smem, stream); \
   }
 #define PG_C4_RESIDENT(BK_, NCB_, CO_)                                                           \
-  PG_C4_TRY(BK_, NCB_, 1, true, CO_, 1) PG_C4_TRY(BK_, NCB_, 2, true, CO_, 1)
+  PG_C4_TRY(BK_, NCB_, 1, true, CO_, 1) PG_C4_TRY(BK_, NCB_, 2, true, CO_, 1)                    \
+  PG_C4_TRY(BK_, NCB_, 1, true, CO_, 2) PG_C4_TRY(BK_, NCB_, 2, true, CO_, 2)
 #define PG_C4_STREAM(NCB_, CO_)                                                                  \
   PG_C4_TRY(64, NCB_, 1, false, CO_, 1) PG_C4_TRY(64, NCB_, 1, false, CO_, 2)                    \
   PG_C4_TRY(64, NCB_, 1, false, CO_, 4) PG_C4_TRY(64, NCB_, 2, false, CO_, 1)                    \
   PG_C4_TRY(64, NCB_, 2, false, CO_, 2) PG_C4_TRY(64, NCB_, 2, false, CO_, 4)
   PG_C4_RESIDENT(64, 1, 32) PG_C4_RESIDENT(64, 1, 64) PG_C4_RESIDENT(64, 1, 128)
   PG_C4_RESIDENT(64, 2, 32) PG_C4_RESIDENT(64, 2, 64)
+  PG_C4_TRY(64, 2, 1, true, 128, 2) PG_C4_TRY(64, 2, 2, true, 128, 2)     /* 128 -> 128: pair only */
   PG_C4_RESIDENT(32, 1, 32) PG_C4_RESIDENT(32, 1, 64) PG_C4_RESIDENT(32, 1, 128)
   PG_C4_STREAM(2, 64) PG_C4_STREAM(2, 128) PG_C4_STREAM(1, 128)
 #undef PG_C4_STREAM

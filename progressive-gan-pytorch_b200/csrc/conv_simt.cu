@@ -12,6 +12,7 @@ template <typename T>
 __global__ void pack_weight_kernel(const float *__restrict__ w, T *__restrict__ out,
                                    int d0, int d1, int taps, int swap_io, int flip,
                                    int layout, int ci_pad, int co_pad) {
+  pg::grid_dep_sync();
   const int Cout = swap_io ? d1 : d0;
   const int Cin = swap_io ? d0 : d1;
   const long long total = (long long)co_pad * taps * ci_pad;
@@ -45,6 +46,7 @@ __global__ void pack_weight_kernel(const float *__restrict__ w, T *__restrict__ 
 // every (weight, operand layout) pair of a network in one launch: blockIdx.y = table entry
 __global__ void __launch_bounds__(256)
 pack_weight_multi_kernel(const PgPackEntry *__restrict__ table) {
+  pg::grid_dep_sync();
   const PgPackEntry e = table[blockIdx.y];
   const int Cout = e.swap_io ? e.d1 : e.d0;
   const int Cin = e.swap_io ? e.d0 : e.d1;
@@ -111,6 +113,7 @@ __global__ void conv_fwd_simt_kernel(const T *__restrict__ x, const T *__restric
                                      float *__restrict__ r_out, int N, int H, int W,
                                      int Cin, int Ho, int Wo, int Cout, int k, int pad,
                                      float scale, int epi, float slope) {
+  pg::grid_dep_sync();
   extern __shared__ float xs[];  // [k*k][Cin]
   __shared__ float red[32];
   const long long pix = blockIdx.x;
@@ -160,6 +163,7 @@ __global__ void conv_wgrad_simt_kernel(const T *__restrict__ x, const T *__restr
                                        float *__restrict__ dw, int N, int H, int W, int Cin,
                                        int Ho, int Wo, int Cout, int k, int pad, float scale,
                                        int swap_io, int flip, int splits, int d1) {
+  pg::grid_dep_sync();
   const int ci = blockIdx.x * 32 + threadIdx.x;
   const int co = blockIdx.y * 8 + threadIdx.y;
   const int taps = k * k;
@@ -209,7 +213,7 @@ extern "C" int pg_pack_conv_weight(const float *w, void *out, int d0, int d1, in
   const long long total = (long long)co_pad * kh * kw * ci_pad;
   const int grid = bw_grid(total, 256);
   PG_DISPATCH_DTYPE(out_dtype, T,
-                    pack_weight_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
+                    pg::launcher(pack_weight_kernel<T>, grid, 256, 0, (cudaStream_t)stream)(
                         w, (T *)out, d0, d1, kh * kw, swap_io, flip, out_layout, ci_pad, co_pad));
   PG_CHECK_LAUNCH("pg_pack_conv_weight");
 }
@@ -217,7 +221,7 @@ extern "C" int pg_pack_conv_weight(const float *w, void *out, int d0, int d1, in
 extern "C" int pg_pack_conv_weight_multi(const PgPackEntry *table, int n, void *stream) {
   PG_CHECK_ARG(table && n > 0 && n <= 65535, "pg_pack_conv_weight_multi: bad table");
   dim3 grid(64, (unsigned)n);
-  pack_weight_multi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(table);
+  pg::launcher(pack_weight_multi_kernel, grid, 256, 0, (cudaStream_t)stream)(table);
   PG_CHECK_LAUNCH("pg_pack_conv_weight_multi");
 }
 
@@ -240,7 +244,7 @@ extern "C" int pg_conv_fwd_simt(const void *x, const void *wp, const float *bias
     if (smem > 48 * 1024)
       cudaFuncSetAttribute(conv_fwd_simt_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)smem);
-    conv_fwd_simt_kernel<T><<<(unsigned)P, threads, smem, (cudaStream_t)stream>>>(
+    pg::launcher(conv_fwd_simt_kernel<T>, (unsigned)P, threads, smem, (cudaStream_t)stream)(
         (const T *)x, (const T *)wp, bias, (T *)y, r_out, N, H, W, Cin, Ho, Wo, Cout, k, pad,
         scale, epi, slope);
   });
@@ -262,7 +266,7 @@ extern "C" int pg_conv_wgrad_simt(const void *x, const void *dy, float *dw, int 
   dim3 grid((Cin + 31) / 32, (Cout + 7) / 8, taps * splits), block(32, 8);
   const int d1 = swap_io ? Cout : Cin;
   PG_DISPATCH_DTYPE(dtype, T,
-                    conv_wgrad_simt_kernel<T><<<grid, block, 0, (cudaStream_t)stream>>>(
+                    pg::launcher(conv_wgrad_simt_kernel<T>, grid, block, 0, (cudaStream_t)stream)(
                         (const T *)x, (const T *)dy, dw, N, H, W, Cin, Ho, Wo, Cout, k, pad,
                         scale, swap_io, flip, splits, d1));
   PG_CHECK_LAUNCH("pg_conv_wgrad_simt");

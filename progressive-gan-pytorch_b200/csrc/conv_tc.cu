@@ -18,6 +18,9 @@
 //           warps 4-7 = epilogue (tcgen05.ld -> scale/bias/PN/LReLU -> bf16 -> swizzled
 //           smem -> TMA store).  Persistent: grid = min(#tiles, #SMs).
 #include "tc_common.cuh"
+#include <string.h>
+#include <mutex>
+#include <unordered_map>
 #include <mutex>
 #include <stdlib.h>
 
@@ -37,9 +40,46 @@ PFN_encodeTiled get_encode_tiled() {
   return fn;
 }
 
+// Descriptor cache ("caches (TMA descriptors keyed by ptr/shape) are per-process,
+// mutex-guarded"): a tensor map is a pure function of (base, dims, strides, box, swizzle), and
+// the caching allocator hands the same buffers back every iteration, so the eager path encodes
+// each descriptor once instead of three or four driver calls per launch.
+namespace {
+struct TmapKey {
+  const void *base;
+  int rank, swizzle;
+  uint64_t dims[5], strides[4];
+  uint32_t box[5];
+  bool operator==(const TmapKey &o) const { return memcmp(this, &o, sizeof(TmapKey)) == 0; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey &k) const {
+    const uint64_t *w = reinterpret_cast<const uint64_t *>(&k);
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < sizeof(TmapKey) / 8; ++i) h = (h ^ w[i]) * 1099511628211ull;
+    return (size_t)h;
+  }
+};
+std::mutex g_tmap_mu;
+std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+}  // namespace
+
 int make_tmap_bf16(CUtensorMap *out, const void *base, int rank, const uint64_t *dims,
                    const uint64_t *strides_bytes, const uint32_t *box, int swizzle_bytes,
                    const char *what) {
+  TmapKey key;
+  memset(&key, 0, sizeof(key));
+  key.base = base; key.rank = rank; key.swizzle = swizzle_bytes;
+  for (int i = 0; i < rank; ++i) { key.dims[i] = dims[i]; key.box[i] = box[i]; }
+  for (int i = 0; i + 1 < rank; ++i) key.strides[i] = strides_bytes[i];
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    auto it = g_tmap_cache.find(key);
+    if (it != g_tmap_cache.end()) {
+      *out = it->second;
+      return PG_OK;
+    }
+  }
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) {
     set_error("%s: cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)", what);
@@ -63,6 +103,11 @@ int make_tmap_bf16(CUtensorMap *out, const void *base, int rank, const uint64_t 
   if (r != CUDA_SUCCESS) {
     set_error("%s: cuTensorMapEncodeTiled failed with CUresult %d", what, (int)r);
     return PG_ERR_CUDA;
+  }
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    if (g_tmap_cache.size() > 8192) g_tmap_cache.clear();      // bound the table (shape sweeps)
+    g_tmap_cache.emplace(key, *out);
   }
   return PG_OK;
 }
@@ -133,6 +178,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  // everything above touches only this CTA's shared memory / TMEM: it overlaps the tail of the
+  // previous kernel; from here on the predecessors' results are read
+  pg::grid_dep_sync();
   for (int c = threadIdx.x; c < p.Cout; c += kThreads)
     bias_ptr[c] = p.bias ? p.bias[c % p.bias_mod] : 0.f;
   tc_fence_before();
@@ -364,16 +412,10 @@ extern "C" int pg_conv_tc(const void *x, const void *wp, const float *bias, void
                "PG_EPI_LINEAR + pg_pn_lrelu_fwd (Cout_total %d, tile %d)", Cout_total, Cout);
   PG_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)wp & 15) == 0 && ((uintptr_t)y & 15) == 0,
                "pg_conv_tc: pointers must be 16-byte aligned");
-  if (taps == 9 && n_tiles == 1) {   // newer kernel generations where the shape allows
-    const int rc5 = conv5_tc_launch(x, wp, bias, y, r_out, N, H, W, Cin, Cout, scale, epi, slope,
-                                    (cudaStream_t)stream, y_pool);
-    if (rc5 != PG_ERR_UNSUPPORTED) return rc5;
+  if (taps == 9 && n_tiles == 1) {   // the single-halo-box kernel where the shape allows
     const int rc4 = conv4_tc_launch(x, wp, bias, y, r_out, N, H, W, Cin, Cout, scale, epi, slope,
                                     (cudaStream_t)stream, nullptr, nullptr, nullptr, 0, y_pool);
     if (rc4 != PG_ERR_UNSUPPORTED) return rc4;
-    const int rc = conv3_tc_launch(x, wp, bias, y, r_out, N, H, W, Cin, Cout, scale, epi, slope,
-                                   (cudaStream_t)stream);
-    if (rc != PG_ERR_UNSUPPORTED) return rc;
   }
   PG_CHECK_ARG(!y_pool, "pg_conv_tc: the fused 2x2 pool needs a 3x3 conv with H %% 16 == 0, W %% 8 == 0, "
                         "Cout in {32,64,128} (H=%d W=%d Cout=%d taps=%d)", H, W, Cout, taps);
@@ -406,10 +448,6 @@ extern "C" int pg_conv_tc(const void *x, const void *wp, const float *bias, void
   const int budget = 227 * 1024;
   int stages = (budget - out_bytes - misc) / (p.a_bytes + p.b_bytes);
   if (stages > 8) stages = 8;
-  if (const char *e = getenv("PG_TC_STAGES")) {   // tuning/experiment knob
-    int v = atoi(e);
-    if (v >= 2 && v < stages) stages = v;
-  }
   PG_CHECK_ARG(stages >= 2, "pg_conv_tc: not enough shared memory for the pipeline");
   p.stages = stages;
   const size_t smem = (size_t)stages * (p.a_bytes + p.b_bytes) + out_bytes + misc;
@@ -446,7 +484,7 @@ extern "C" int pg_conv_tc(const void *x, const void *wp, const float *bias, void
     attr_set = true;
   }
   int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-  tc::conv_tc_kernel<<<grid, tc::kThreads, smem, (cudaStream_t)stream>>>(tx, tw_, ty, p);
+  pg::launcher(tc::conv_tc_kernel, grid, tc::kThreads, smem, (cudaStream_t)stream, p.num_tiles)(tx, tw_, ty, p);
   PG_CHECK_LAUNCH("pg_conv_tc");
 }
 

@@ -9,6 +9,7 @@ namespace pg {
 __global__ void __launch_bounds__(256)
 interp_xhat_kernel(const float *__restrict__ real, const float *__restrict__ fake,
                    const float *__restrict__ eps, float *__restrict__ out, int N, long long D) {
+  pg::grid_dep_sync();
   const long long D4 = D >> 2;
   const long long total = (long long)N * D4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -33,6 +34,7 @@ interp_xhat_kernel(const float *__restrict__ real, const float *__restrict__ fak
 // one CTA per sample: norms[n] = ||g[n,:]||_2
 __global__ void __launch_bounds__(1024)
 gp_norm_kernel(const float *__restrict__ g, float *__restrict__ norms, long long D) {
+  pg::grid_dep_sync();
   __shared__ float red[32];
   const float *p = g + (long long)blockIdx.x * D;
   const long long D4 = D >> 2;
@@ -53,6 +55,7 @@ gp_norm_kernel(const float *__restrict__ g, float *__restrict__ norms, long long
 __global__ void __launch_bounds__(256)
 wgan_loss_kernel(const float *__restrict__ d, float *__restrict__ seed, float *__restrict__ metric,
                  int n_real, int n_fake, float drift) {
+  pg::grid_dep_sync();
   __shared__ float red[32];
   float sr = 0.f, sr2 = 0.f, sf = 0.f;
   const float ir = n_real > 0 ? 1.f / (float)n_real : 0.f, ifk = 1.f / (float)n_fake;
@@ -78,6 +81,7 @@ wgan_loss_kernel(const float *__restrict__ d, float *__restrict__ seed, float *_
 
 __global__ void gp_loss_kernel(const float *__restrict__ norms, float *__restrict__ gp, int N,
                                float lambda) {
+  pg::grid_dep_sync();
   __shared__ float red[32];
   float s = 0.f;
   for (int n = threadIdx.x; n < N; n += blockDim.x) {
@@ -92,6 +96,7 @@ __global__ void __launch_bounds__(256)
 gp_bwd_kernel(const float *__restrict__ g, const float *__restrict__ norms,
               const float *__restrict__ upstream, float *__restrict__ v, int N, long long D,
               float lambda) {
+  pg::grid_dep_sync();
   const long long D4 = D >> 2;
   const long long total = (long long)N * D4;
   const float up = upstream ? *upstream : 1.f;
@@ -114,6 +119,7 @@ __global__ void __launch_bounds__(256)
 adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
             float *__restrict__ v, long long n, float lr, float b1, float b2, float eps,
             const float *__restrict__ step_dev, float grad_scale) {
+  pg::grid_dep_sync();
   const float t = *step_dev;
   const float bc1 = 1.f - powf(b1, t);
   const float bc2_sqrt = sqrtf(1.f - powf(b2, t));
@@ -135,6 +141,7 @@ adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restric
 
 __global__ void __launch_bounds__(256)
 ema_kernel(float *__restrict__ ema, const float *__restrict__ p, long long n, float decay) {
+  pg::grid_dep_sync();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x)
     ema[i] = ema[i] * decay + (1.f - decay) * p[i];
@@ -149,7 +156,7 @@ extern "C" int pg_interp_xhat(const float *real, const float *fake, const float 
   PG_CHECK_ARG(real && fake && eps && out, "pg_interp_xhat: null pointer");
   PG_CHECK_ARG(N > 0 && D > 0 && D % 4 == 0, "pg_interp_xhat: need D %% 4 == 0");
   const int grid = bw_grid((long long)N * (D / 4), 256);
-  interp_xhat_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(real, fake, eps, out, N, D);
+  pg::launcher(interp_xhat_kernel, grid, 256, 0, (cudaStream_t)stream)(real, fake, eps, out, N, D);
   PG_CHECK_LAUNCH("pg_interp_xhat");
 }
 
@@ -159,8 +166,8 @@ extern "C" int pg_gp_fwd(const float *g, float *norms, float *gp, int N, long lo
   PG_CHECK_ARG(N > 0 && D > 0 && D % 4 == 0, "pg_gp_fwd: need D %% 4 == 0");
   int threads = 1024;
   while (threads > 32 && (long long)threads * 4 > D) threads >>= 1;
-  gp_norm_kernel<<<N, threads, 0, (cudaStream_t)stream>>>(g, norms, D);
-  gp_loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(norms, gp, N, lambda);
+  pg::launcher(gp_norm_kernel, N, threads, 0, (cudaStream_t)stream)(g, norms, D);
+  pg::launcher(gp_loss_kernel, 1, 256, 0, (cudaStream_t)stream)(norms, gp, N, lambda);
   PG_CHECK_LAUNCH("pg_gp_fwd");
 }
 
@@ -169,7 +176,7 @@ extern "C" int pg_gp_bwd(const float *g, const float *norms, const float *upstre
   PG_CHECK_ARG(g && norms && v, "pg_gp_bwd: null pointer");
   PG_CHECK_ARG(N > 0 && D > 0 && D % 4 == 0, "pg_gp_bwd: need D %% 4 == 0");
   const int grid = bw_grid((long long)N * (D / 4), 256);
-  gp_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g, norms, upstream, v, N, D, lambda);
+  pg::launcher(gp_bwd_kernel, grid, 256, 0, (cudaStream_t)stream)(g, norms, upstream, v, N, D, lambda);
   PG_CHECK_LAUNCH("pg_gp_bwd");
 }
 
@@ -179,14 +186,14 @@ extern "C" int pg_adam_step(float *p, const float *g, float *m, float *v, long l
   PG_CHECK_ARG(p && g && v && step_dev, "pg_adam_step: null pointer");
   PG_CHECK_ARG(m || beta1 == 0.f, "pg_adam_step: beta1 != 0 needs a first-moment buffer");
   PG_CHECK_ARG(n > 0, "pg_adam_step: n must be > 0");
-  adam_kernel<<<bw_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2,
+  pg::launcher(adam_kernel, bw_grid(n, 256), 256, 0, (cudaStream_t)stream)(p, g, m, v, n, lr, beta1, beta2,
                                                                  eps, step_dev, grad_scale);
   PG_CHECK_LAUNCH("pg_adam_step");
 }
 
 extern "C" int pg_ema(float *ema, const float *p, long long n, float decay, void *stream) {
   PG_CHECK_ARG(ema && p && n > 0, "pg_ema: bad args");
-  ema_kernel<<<bw_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(ema, p, n, decay);
+  pg::launcher(ema_kernel, bw_grid(n, 256), 256, 0, (cudaStream_t)stream)(ema, p, n, decay);
   PG_CHECK_LAUNCH("pg_ema");
 }
 
@@ -201,6 +208,7 @@ adam_multi_kernel(float *__restrict__ p, const float *__restrict__ g, float *__r
                   float *__restrict__ v, const int4 *__restrict__ chunks,
                   const float *__restrict__ steps_dev, float lr, float b1, float b2, float eps,
                   float grad_scale) {
+  pg::grid_dep_sync();
   const int4 c = chunks[blockIdx.x];   // x = start, y = length, z = segment
   const float t = steps_dev[c.z];
   const float bc1 = 1.f - powf(b1, t);
@@ -248,7 +256,7 @@ extern "C" int pg_adam_multi(float *p, const float *g, float *m, float *v, const
   PG_CHECK_ARG(p && g && v && chunks && steps_dev, "pg_adam_multi: null pointer");
   PG_CHECK_ARG(m || beta1 == 0.f, "pg_adam_multi: beta1 != 0 needs a first-moment buffer");
   PG_CHECK_ARG(nchunks > 0, "pg_adam_multi: nchunks must be > 0");
-  pg::adam_multi_kernel<<<nchunks, 256, 0, (cudaStream_t)stream>>>(
+  pg::launcher(pg::adam_multi_kernel, nchunks, 256, 0, (cudaStream_t)stream)(
       p, g, m, v, (const int4 *)chunks, steps_dev, lr, beta1, beta2, eps, grad_scale);
   PG_CHECK_LAUNCH("pg_adam_multi");
 }
@@ -256,6 +264,6 @@ extern "C" int pg_adam_multi(float *p, const float *g, float *m, float *v, const
 extern "C" int pg_wgan_loss(const float *d, float *seed, float *metric, int n_real, int n_fake,
                             float drift, void *stream) {
   PG_CHECK_ARG(d && seed && n_real >= 0 && n_fake > 0, "pg_wgan_loss: bad arguments");
-  pg::wgan_loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(d, seed, metric, n_real, n_fake, drift);
+  pg::launcher(pg::wgan_loss_kernel, 1, 256, 0, (cudaStream_t)stream)(d, seed, metric, n_real, n_fake, drift);
   PG_CHECK_LAUNCH("pg_wgan_loss");
 }

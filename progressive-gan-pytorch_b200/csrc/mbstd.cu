@@ -21,6 +21,7 @@ template <typename T>
 __global__ void __launch_bounds__(kMbT)
 mbstd_stats_kernel(const T *__restrict__ x, const T *__restrict__ t, float *__restrict__ stats, int N,
                    int F) {
+  pg::grid_dep_sync();
   __shared__ float red[32];
   const int f = blockIdx.x * kMbT + threadIdx.x;
   float part = 0.f;
@@ -64,6 +65,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 mbstd_fwd_write_kernel(const T *__restrict__ x, const float *__restrict__ stats, T *__restrict__ out,
                        int N, int C, int Cp, int nparts) {
+  pg::grid_dep_sync();
   const int F = 16 * C;
   const float m = mb_sum_parts(stats, F, nparts) / (float)F;
   const long long total = (long long)N * 16 * Cp;
@@ -90,6 +92,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 mbstd_bwd_kernel(const T *__restrict__ dout, const T *__restrict__ x, const float *__restrict__ stats,
                  T *__restrict__ dx, int N, int C, int Cp) {
+  pg::grid_dep_sync();
   __shared__ float red[32];
   const int F = 16 * C;
   const float dm = mb_delta_m(dout, N, C, Cp, red);
@@ -110,6 +113,7 @@ __global__ void __launch_bounds__(256)
 mbstd_bwd_bwd_kernel(const T *__restrict__ t, const T *__restrict__ dout, const T *__restrict__ x,
                      const float *__restrict__ stats, T *__restrict__ cot_dout,
                      T *__restrict__ cot_x, int N, int C, int Cp, int nparts) {
+  pg::grid_dep_sync();
   __shared__ float red[32];
   const int F = 16 * C;
   const float dm = mb_delta_m(dout, N, C, Cp, red);
@@ -154,8 +158,8 @@ extern "C" int pg_mbstd_fwd(const void *x, void *out, float *stats, int N, int C
   const int F = 16 * C, nparts = (F + kMbT - 1) / kMbT;
   cudaStream_t s = (cudaStream_t)stream;
   PG_DISPATCH_DTYPE(dtype, T, {
-    mbstd_stats_kernel<T><<<nparts, kMbT, 0, s>>>((const T *)x, (const T *)nullptr, stats, N, F);
-    mbstd_fwd_write_kernel<T><<<bw_grid((long long)N * 16 * Cp, 256, 2), 256, 0, s>>>(
+    pg::launcher(mbstd_stats_kernel<T>, nparts, kMbT, 0, s)((const T *)x, (const T *)nullptr, stats, N, F);
+    pg::launcher(mbstd_fwd_write_kernel<T>, bw_grid((long long)N * 16 * Cp, 256, 2), 256, 0, s)(
         (const T *)x, stats, (T *)out, N, C, Cp, nparts);
   });
   PG_CHECK_LAUNCH("pg_mbstd_fwd");
@@ -166,8 +170,8 @@ extern "C" int pg_mbstd_bwd(const void *dout, const void *x, const float *stats,
   PG_CHECK_ARG(dout && x && dx && stats, "pg_mbstd_bwd: null pointer");
   if (int rc = check_mb("pg_mbstd_bwd", N, C, Cp)) return rc;
   PG_DISPATCH_DTYPE(dtype, T,
-                    mbstd_bwd_kernel<T><<<bw_grid((long long)N * 16 * C, 256, 2), 256, 0,
-                                          (cudaStream_t)stream>>>((const T *)dout, (const T *)x, stats,
+                    pg::launcher(mbstd_bwd_kernel<T>, bw_grid((long long)N * 16 * C, 256, 2), 256, 0,
+                                          (cudaStream_t)stream)((const T *)dout, (const T *)x, stats,
                                                                   (T *)dx, N, C, Cp));
   PG_CHECK_LAUNCH("pg_mbstd_bwd");
 }
@@ -180,8 +184,8 @@ extern "C" int pg_mbstd_bwd_bwd(const void *t, const void *dout, const void *x, 
   const int F = 16 * C, nparts = (F + kMbT - 1) / kMbT;
   cudaStream_t s = (cudaStream_t)stream;
   PG_DISPATCH_DTYPE(dtype, T, {
-    mbstd_stats_kernel<T><<<nparts, kMbT, 0, s>>>((const T *)x, (const T *)t, stats, N, F);
-    mbstd_bwd_bwd_kernel<T><<<bw_grid((long long)N * 16 * Cp, 256, 2), 256, 0, s>>>(
+    pg::launcher(mbstd_stats_kernel<T>, nparts, kMbT, 0, s)((const T *)x, (const T *)t, stats, N, F);
+    pg::launcher(mbstd_bwd_bwd_kernel<T>, bw_grid((long long)N * 16 * Cp, 256, 2), 256, 0, s)(
         (const T *)t, (const T *)dout, (const T *)x, stats, (T *)cot_dout, (T *)cot_x, N, C, Cp, nparts);
   });
   PG_CHECK_LAUNCH("pg_mbstd_bwd_bwd");

@@ -19,6 +19,7 @@ __global__ void __launch_bounds__(256)
 pw_expand_generic_kernel(const float *__restrict__ img, const float *__restrict__ w,
                  const float *__restrict__ bias, T *__restrict__ act, int N, I HW,
                  int K, int C, int w_sc, int w_sk, float scale) {
+  pg::grid_dep_sync();
   extern __shared__ float sw[];  // [K][C] then bias[C]
   float *sb = sw + K * C;
   for (int i = threadIdx.x; i < K * C; i += blockDim.x) {
@@ -94,6 +95,7 @@ __global__ void __launch_bounds__(256)
 pw_reduce_generic_kernel(const T *__restrict__ act, const float *__restrict__ w,
                  const float *__restrict__ bias, float *__restrict__ img, int N, I HW,
                  int K, int C, int w_sc, int w_sk, float scale) {
+  pg::grid_dep_sync();
   extern __shared__ float sw[];  // [K][C]
   for (int i = threadIdx.x; i < K * C; i += blockDim.x) {
     const int k = i / C, c = i - k * C;
@@ -183,6 +185,7 @@ __global__ void __launch_bounds__(256)
 pw_wgrad_generic_kernel(const T *__restrict__ act, const float *__restrict__ img,
                 float *__restrict__ dw, int N, I HW, int K, int C, int w_sc, int w_sk,
                 float scale) {
+  pg::grid_dep_sync();
   extern __shared__ float sm[];  // [rows][K][C]
   const int nch = C >> 3;
   const int rows = blockDim.x / nch;
@@ -258,6 +261,7 @@ __global__ void __launch_bounds__(256)
 pw_expand_kernel(const float *__restrict__ img, const float *__restrict__ w,
                  const float *__restrict__ bias, T *__restrict__ act, int P, int HW,
                  int K, int w_sc, int w_sk, float scale) {
+  pg::grid_dep_sync();
   constexpr int C = 8 * LPP * NCK;
   constexpr int PPW = 32 / LPP;                 // pixels per store instruction
   __shared__ float sw[NCK > 1 ? (KT + 1) * C : 1];
@@ -344,6 +348,7 @@ __global__ void __launch_bounds__(256)
 pw_reduce_kernel(const T *__restrict__ act, const float *__restrict__ w,
                  const float *__restrict__ bias, float *__restrict__ img, int P, int HW,
                  int K, int w_sc, int w_sk, float scale) {
+  pg::grid_dep_sync();
   constexpr int C = 8 * LPP * NCK;
   constexpr int PPW = 32 / LPP;
   constexpr int RB = (LPP * NCK <= 8) ? LPP : (8 / NCK > 0 ? 8 / NCK : 1);   // rounds per load batch
@@ -439,6 +444,7 @@ template <typename T, int LPP, int KT>
 __global__ void __launch_bounds__(256)
 pw_wgrad_kernel(const T *__restrict__ act, const float *__restrict__ img, float *__restrict__ dw,
                 float *__restrict__ dbias, int P, int HW, int K, int w_sc, int w_sk, float scale) {
+  pg::grid_dep_sync();
   constexpr int C = 8 * LPP;
   constexpr int PPW = 32 / LPP;
   constexpr int RB = LPP <= 8 ? LPP : 8;
@@ -520,6 +526,7 @@ pw_wgrad_kernel(const T *__restrict__ act, const float *__restrict__ img, float 
 __global__ void __launch_bounds__(256)
 img_chansum_kernel(const float *__restrict__ img, float *__restrict__ out, int N, long long HW,
                    int K) {
+  pg::grid_dep_sync();
   __shared__ float red[32];
   // grid.y = plane (n*K + k); grid.x strides over HW
   const int plane = blockIdx.y;
@@ -587,7 +594,7 @@ extern "C" int pg_pw_expand(const float *img, const float *w, const float *bias,
   if (pw_shape(C, &lpp, &nck) && pw_fits32((long long)N * HW, C, K, HW, w_sc, w_sk)) {
     const int P = (int)((long long)N * HW);
     const int grid = bw_grid((P + 31) / 32, 8 * 2);   // 8 warps x 2 runs per block pass
-#define PG_PWE(L, NC) pw_expand_kernel<T, L, NC, KT><<<grid, 256, 0, s>>>(img, w, bias, (T *)act, P, (int)HW, K, w_sc, w_sk, scale);
+#define PG_PWE(L, NC) pg::launcher(pw_expand_kernel<T, L, NC, KT>, grid, 256, 0, s)(img, w, bias, (T *)act, P, (int)HW, K, w_sc, w_sk, scale);
     PG_DISPATCH_DTYPE(dtype, T, {
       PG_PW_DISPATCH_K(K, {
         if (nck == 1) { PG_PW_DISPATCH_LPP(lpp, PG_PWE) }
@@ -604,10 +611,10 @@ extern "C" int pg_pw_expand(const float *img, const float *w, const float *bias,
   const bool small = total + (long long)grid * 256 < (1ll << 31);
   PG_DISPATCH_DTYPE(dtype, T, {
     if (small)
-      pw_expand_generic_kernel<T, unsigned><<<grid, 256, smem, s>>>(
+      pg::launcher(pw_expand_generic_kernel<T, unsigned>, grid, 256, smem, s)(
           img, w, bias, (T *)act, N, (unsigned)HW, K, C, w_sc, w_sk, scale);
     else
-      pw_expand_generic_kernel<T, long long><<<grid, 256, smem, s>>>(
+      pg::launcher(pw_expand_generic_kernel<T, long long>, grid, 256, smem, s)(
           img, w, bias, (T *)act, N, HW, K, C, w_sc, w_sk, scale);
   });
   PG_CHECK_LAUNCH("pg_pw_expand");
@@ -624,7 +631,7 @@ extern "C" int pg_pw_reduce(const void *act, const float *w, const float *bias, 
   int lpp = 0, nck = 0;
   if (pw_shape(C, &lpp, &nck) && pw_fits32(P, C, K, HW, w_sc, w_sk)) {
     const int grid = bw_grid((P + 31) / 32, 8);
-#define PG_PWR(L, NC) pw_reduce_kernel<T, L, NC, KT><<<grid, 256, 0, s>>>((const T *)act, w, bias, img, (int)P, (int)HW, K, w_sc, w_sk, scale);
+#define PG_PWR(L, NC) pg::launcher(pw_reduce_kernel<T, L, NC, KT>, grid, 256, 0, s)((const T *)act, w, bias, img, (int)P, (int)HW, K, w_sc, w_sk, scale);
     PG_DISPATCH_DTYPE(dtype, T, {
       PG_PW_DISPATCH_K(K, {
         if (nck == 1) { PG_PW_DISPATCH_LPP(lpp, PG_PWR) }
@@ -640,10 +647,10 @@ extern "C" int pg_pw_reduce(const void *act, const float *w, const float *bias, 
   {                                                                                         \
     const int grid = bw_grid(P, 256 / TPP);                                                 \
     if (P + (long long)grid * 256 < (1ll << 31))                                            \
-      pw_reduce_generic_kernel<T, TPP, unsigned, CPL><<<grid, 256, smem, s>>>(              \
+      pg::launcher(pw_reduce_generic_kernel<T, TPP, unsigned, CPL>, grid, 256, smem, s)(              \
           (const T *)act, w, bias, img, N, (unsigned)HW, K, C, w_sc, w_sk, scale);          \
     else                                                                                    \
-      pw_reduce_generic_kernel<T, TPP, long long, CPL><<<grid, 256, smem, s>>>(             \
+      pg::launcher(pw_reduce_generic_kernel<T, TPP, long long, CPL>, grid, 256, smem, s)(             \
           (const T *)act, w, bias, img, N, HW, K, C, w_sc, w_sk, scale);                    \
   }
   PG_DISPATCH_DTYPE(dtype, T, {
@@ -673,7 +680,7 @@ extern "C" int pg_pw_wgrad(const void *act, const float *img, float *dw, float *
   if (pw_shape(C, &lpp, &nck) && nck == 1 && pw_fits32(P, C, K, HW, w_sc, w_sk)) {
     // few enough blocks that the final atomics stay cheap, enough warps to cover the HBM latency
     const int grid = bw_grid((P + 31) / 32, 8 * 4, 4);
-#define PG_PWW(L, NC) pw_wgrad_kernel<T, L, KT><<<grid, 256, 0, s>>>((const T *)act, img, dw, dbias, (int)P, (int)HW, K, w_sc, w_sk, scale);
+#define PG_PWW(L, NC) pg::launcher(pw_wgrad_kernel<T, L, KT>, grid, 256, 0, s)((const T *)act, img, dw, dbias, (int)P, (int)HW, K, w_sc, w_sk, scale);
     PG_DISPATCH_DTYPE(dtype, T, { PG_PW_DISPATCH_K(K, { PG_PW_DISPATCH_LPP(lpp, PG_PWW) }) });
 #undef PG_PWW
     PG_CHECK_LAUNCH("pg_pw_wgrad");
@@ -684,10 +691,10 @@ extern "C" int pg_pw_wgrad(const void *act, const float *img, float *dw, float *
   const size_t smem = (size_t)rows * K * C * sizeof(float);
   PG_DISPATCH_DTYPE(dtype, T, {
     if (P + (long long)grid * 256 < (1ll << 31))
-      pw_wgrad_generic_kernel<T, unsigned><<<grid, 256, smem, s>>>(
+      pg::launcher(pw_wgrad_generic_kernel<T, unsigned>, grid, 256, smem, s)(
           (const T *)act, img, dw, N, (unsigned)HW, K, C, w_sc, w_sk, scale);
     else
-      pw_wgrad_generic_kernel<T, long long><<<grid, 256, smem, s>>>(
+      pg::launcher(pw_wgrad_generic_kernel<T, long long>, grid, 256, smem, s)(
           (const T *)act, img, dw, N, HW, K, C, w_sc, w_sk, scale);
   });
   if (dbias) {
@@ -709,6 +716,6 @@ extern "C" int pg_img_chansum(const float *img, float *out, int N, long long HW,
   if (gx < 1) gx = 1;
   if (gx > 64) gx = 64;
   dim3 grid(gx, N * K);
-  img_chansum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img, out, N, HW, K);
+  pg::launcher(img_chansum_kernel, grid, 256, 0, (cudaStream_t)stream)(img, out, N, HW, K);
   PG_CHECK_LAUNCH("pg_img_chansum");
 }

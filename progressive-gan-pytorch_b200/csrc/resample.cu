@@ -40,6 +40,7 @@ struct Grp {
 template <typename T, int G, typename I>
 __global__ void __launch_bounds__(256)
 avgpool2_kernel(const T *__restrict__ x, T *__restrict__ y, int N, int H, int W, int C) {
+  pg::grid_dep_sync();
   const int Ho = H / 2, Wo = W / 2, cg = C / G;
   const I total = (I)N * (I)Ho * (I)Wo * (I)cg;
   for (I i = (I)blockIdx.x * (I)blockDim.x + (I)threadIdx.x; i < total;
@@ -65,6 +66,7 @@ avgpool2_kernel(const T *__restrict__ x, T *__restrict__ y, int N, int H, int W,
 template <typename T, int G, typename I>
 __global__ void __launch_bounds__(256)
 avgpool2_bwd_kernel(const T *__restrict__ dy, T *__restrict__ dx, int N, int H, int W, int C) {
+  pg::grid_dep_sync();
   const int Ho = H / 2, Wo = W / 2, cg = C / G;
   const I total = (I)N * (I)H * (I)W * (I)cg;
   for (I i = (I)blockIdx.x * (I)blockDim.x + (I)threadIdx.x; i < total;
@@ -88,6 +90,7 @@ avgpool2_bwd_kernel(const T *__restrict__ dy, T *__restrict__ dx, int N, int H, 
 __global__ void __launch_bounds__(256)
 avgpool2_kernel_plane(const float *__restrict__ x, float *__restrict__ y, long long planes, int H,
                       int W) {
+  pg::grid_dep_sync();
   const int Ho = H / 2, Wq = W / 4;
   const long long total = planes * Ho * Wq;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -109,6 +112,7 @@ avgpool2_kernel_plane(const float *__restrict__ x, float *__restrict__ y, long l
 __global__ void __launch_bounds__(256)
 avgpool2_bwd_kernel_plane(const float *__restrict__ dy, float *__restrict__ dx, long long planes,
                           int H, int W) {
+  pg::grid_dep_sync();
   const int Wq = W / 4;
   const long long total = planes * H * Wq;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -155,6 +159,7 @@ template <typename T, int G>
 __global__ void __launch_bounds__(256)
 upsample2_kernel(const T *__restrict__ x, T *__restrict__ y, int N, int H, int W, int C, int TW,
                  int TH, long long tiles) {
+  pg::grid_dep_sync();
   const int Ho = 2 * H, Wo = 2 * W;
   for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const Tile2D it = tile_item<G>(tile, threadIdx.x, H + 1, W + 1, C, TW, TH);
@@ -194,6 +199,7 @@ template <typename T, int G>
 __global__ void __launch_bounds__(256)
 upsample2_bwd_kernel(const T *__restrict__ dy, T *__restrict__ dx, int N, int H, int W, int C,
                      int TW, int TH, long long tiles) {
+  pg::grid_dep_sync();
   const int Ho = 2 * H, Wo = 2 * W;
   const float wt[4] = {0.25f, 0.75f, 0.75f, 0.25f};
   for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -242,6 +248,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 axpby_kernel(const T *__restrict__ a, const T *__restrict__ b, T *__restrict__ out, long long n,
              float a0, float a1, float b0, float b1, const float *__restrict__ alpha_dev) {
+  pg::grid_dep_sync();
   const float alpha = alpha_dev ? *alpha_dev : 0.f;
   const float ca = a0 + a1 * alpha, cb = b0 + b1 * alpha;
   const long long nv = n >> 3;
@@ -270,6 +277,7 @@ axpby_kernel(const T *__restrict__ a, const T *__restrict__ b, T *__restrict__ o
 __global__ void __launch_bounds__(256)
 tanh_kernel(const float *__restrict__ x, const float *__restrict__ y_saved,
             float *__restrict__ out, long long n, int bwd) {
+  pg::grid_dep_sync();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     if (!bwd) out[i] = tanhf(x[i]);
@@ -290,7 +298,7 @@ using namespace pg;
     const long long work = (work_expr);                                                        \
     if (C == 1 && dtype == PG_F32 && W % 4 == 0 && (((uintptr_t)x | (uintptr_t)y) & 15) == 0) { \
       const long long items = (long long)N * H * W / 4 / ((even_check) == 1 ? 2 : 1);          \
-      kernel##_plane<<<bw_grid(items, 256), 256, 0, (cudaStream_t)stream>>>(                    \
+      pg::launcher(kernel##_plane, bw_grid(items, 256), 256, 0, (cudaStream_t)stream)(                    \
           (const float *)x, (float *)y, (long long)N, H, W);                                   \
       PG_CHECK_LAUNCH(#fn);                                                                    \
     }                                                                                          \
@@ -300,17 +308,17 @@ using namespace pg;
     if (C % 8 == 0) {                                                                          \
       const int grid = bw_grid(work / 8, 256);                                                 \
       PG_DISPATCH_DTYPE(dtype, T, {                                                            \
-        if (small) kernel<T, 8, unsigned><<<grid, 256, 0, (cudaStream_t)stream>>>(             \
+        if (small) pg::launcher(kernel<T, 8, unsigned>, grid, 256, 0, (cudaStream_t)stream)(             \
                        (const T *)x, (T *)y, N, H, W, C);                                      \
-        else kernel<T, 8, long long><<<grid, 256, 0, (cudaStream_t)stream>>>(                  \
+        else pg::launcher(kernel<T, 8, long long>, grid, 256, 0, (cudaStream_t)stream)(                  \
                  (const T *)x, (T *)y, N, H, W, C);                                            \
       });                                                                                      \
     } else {                                                                                   \
       const int grid = bw_grid(work, 256);                                                     \
       PG_DISPATCH_DTYPE(dtype, T, {                                                            \
-        if (small) kernel<T, 1, unsigned><<<grid, 256, 0, (cudaStream_t)stream>>>(             \
+        if (small) pg::launcher(kernel<T, 1, unsigned>, grid, 256, 0, (cudaStream_t)stream)(             \
                        (const T *)x, (T *)y, N, H, W, C);                                      \
-        else kernel<T, 1, long long><<<grid, 256, 0, (cudaStream_t)stream>>>(                  \
+        else pg::launcher(kernel<T, 1, long long>, grid, 256, 0, (cudaStream_t)stream)(                  \
                  (const T *)x, (T *)y, N, H, W, C);                                            \
       });                                                                                      \
     }                                                                                          \
@@ -342,14 +350,14 @@ static void tile_shape(int Hd, int Wd, int C, int *TW, int *TH) {
       tile_shape<8>(HD, WD, C, &TW, &TH);                                                      \
       const long long tiles = (long long)N * (((HD) + TH - 1) / TH) * (((WD) + TW - 1) / TW);  \
       const int grid = bw_grid(tiles, 1);                                                      \
-      PG_DISPATCH_DTYPE(dtype, T, (kernel<T, 8><<<grid, 256, 0, (cudaStream_t)stream>>>(       \
+      PG_DISPATCH_DTYPE(dtype, T, (pg::launcher(kernel<T, 8>, grid, 256, 0, (cudaStream_t)stream)(       \
                                       (const T *)x, (T *)y, N, H, W, C, TW, TH, tiles)));      \
     } else {                                                                                   \
       PG_CHECK_ARG(C <= 256, #fn ": C must be a multiple of 8 or <= 256");                     \
       tile_shape<1>(HD, WD, C, &TW, &TH);                                                      \
       const long long tiles = (long long)N * (((HD) + TH - 1) / TH) * (((WD) + TW - 1) / TW);  \
       const int grid = bw_grid(tiles, 1);                                                      \
-      PG_DISPATCH_DTYPE(dtype, T, (kernel<T, 1><<<grid, 256, 0, (cudaStream_t)stream>>>(       \
+      PG_DISPATCH_DTYPE(dtype, T, (pg::launcher(kernel<T, 1>, grid, 256, 0, (cudaStream_t)stream)(       \
                                       (const T *)x, (T *)y, N, H, W, C, TW, TH, tiles)));      \
     }                                                                                          \
     PG_CHECK_LAUNCH(#fn);                                                                      \
@@ -363,7 +371,7 @@ extern "C" int pg_blend(const void *a, const void *b, void *out, long long n,
   PG_CHECK_ARG(a && b && out && alpha_dev, "pg_blend: null pointer");
   PG_CHECK_ARG(n > 0, "pg_blend: n must be > 0");
   const int grid = bw_grid((n + 7) / 8, 256);
-  PG_DISPATCH_DTYPE(dtype, T, axpby_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
+  PG_DISPATCH_DTYPE(dtype, T, pg::launcher(axpby_kernel<T>, grid, 256, 0, (cudaStream_t)stream)(
                                   (const T *)a, (const T *)b, (T *)out, n, 1.f, -1.f, 0.f, 1.f,
                                   alpha_dev));
   PG_CHECK_LAUNCH("pg_blend");
@@ -375,7 +383,7 @@ extern "C" int pg_scale(const void *x, void *out, long long n, float c0, float c
   PG_CHECK_ARG(n > 0, "pg_scale: n must be > 0");
   PG_CHECK_ARG(alpha_dev || c1 == 0.f, "pg_scale: c1 != 0 needs alpha_dev");
   const int grid = bw_grid((n + 7) / 8, 256);
-  PG_DISPATCH_DTYPE(dtype, T, axpby_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
+  PG_DISPATCH_DTYPE(dtype, T, pg::launcher(axpby_kernel<T>, grid, 256, 0, (cudaStream_t)stream)(
                                   (const T *)x, (const T *)nullptr, (T *)out, n, c0, c1, 0.f,
                                   0.f, alpha_dev));
   PG_CHECK_LAUNCH("pg_scale");
@@ -383,13 +391,13 @@ extern "C" int pg_scale(const void *x, void *out, long long n, float c0, float c
 
 extern "C" int pg_tanh_fwd(const float *x, float *y, long long n, void *stream) {
   PG_CHECK_ARG(x && y && n > 0, "pg_tanh_fwd: bad args");
-  tanh_kernel<<<bw_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(x, nullptr, y, n, 0);
+  pg::launcher(tanh_kernel, bw_grid(n, 256), 256, 0, (cudaStream_t)stream)(x, nullptr, y, n, 0);
   PG_CHECK_LAUNCH("pg_tanh_fwd");
 }
 
 extern "C" int pg_tanh_bwd(const float *dy, const float *y, float *dx, long long n,
                            void *stream) {
   PG_CHECK_ARG(dy && y && dx && n > 0, "pg_tanh_bwd: bad args");
-  tanh_kernel<<<bw_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(dy, y, dx, n, 1);
+  pg::launcher(tanh_kernel, bw_grid(n, 256), 256, 0, (cudaStream_t)stream)(dy, y, dx, n, 1);
   PG_CHECK_LAUNCH("pg_tanh_bwd");
 }

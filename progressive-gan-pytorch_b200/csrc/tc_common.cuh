@@ -93,6 +93,10 @@ __device__ __forceinline__ void tma_store_commit() {
 __device__ __forceinline__ void tma_store_wait_read0() {
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {      // at most N store groups still reading
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
 __device__ __forceinline__ void tma_store_wait_all() {
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
@@ -341,29 +345,15 @@ int make_tmap_bf16(CUtensorMap *out, const void *base, int rank, const uint64_t 
                    const uint64_t *strides_bytes, const uint32_t *box, int swizzle_bytes,
                    const char *what);
 
-// second-generation 3x3 kernel (conv3_tc.cu); PG_ERR_UNSUPPORTED when the shape is not eligible
-int conv3_tc_launch(const void *x, const void *wp, const float *bias, void *y, float *r_out, int N,
-                    int H, int W, int Cin, int Cout, float scale, int epi, float slope,
-                    cudaStream_t stream);
-
-// third-generation 3x3 kernel (conv4_tc.cu): one 10x18 halo box per channel block, weight ring,
+// 3x3 kernel (conv4_tc.cu): one 10x18 halo box per channel block, weight ring,
 // cluster multicast of streamed weights; PG_ERR_UNSUPPORTED when the shape is not eligible
 int conv4_tc_launch(const void *x, const void *wp, const float *bias, void *y, float *r_out, int N,
                     int H, int W, int Cin, int Cout, float scale, int epi, float slope,
                     cudaStream_t stream, const void *y_prev = nullptr, const float *r_prev = nullptr,
                     float *colsum = nullptr, int use_pn = 0, void *y_pool = nullptr);
 
-// second-generation weight-gradient kernel (wgrad3_tc.cu); workspace pre-zeroed by the caller
-int wgrad3_tc_launch(const void *x, const void *dy, float *workspace, int N, int H, int W, int Cin,
-                     int Cout, cudaStream_t stream);
 
-
-// CTA-pair (cta_group::2) variant of the 3x3 kernel for resident half-weights (conv5_tc.cu)
-int conv5_tc_launch(const void *x, const void *wp, const float *bias, void *y, float *r_out, int N,
-                    int H, int W, int Cin, int Cout, float scale, int epi, float slope,
-                    cudaStream_t stream, void *y_pool);
-
-// third-generation weight-gradient kernel (wgrad4_tc.cu): single halo box, paired taps
+// weight-gradient kernel (wgrad4_tc.cu): single halo box, paired taps
 int wgrad4_tc_launch(const void *x, const void *dy, float *workspace, int N, int H, int W, int Cin,
                      int Cout, cudaStream_t stream);
 

@@ -1,6 +1,6 @@
 // 3x3 pad-1 weight-gradient, third generation ("single halo box") kernel.
 //
-// Same math as wgrad3_tc.cu: dW[tap][co][ci] = sum_pix dy[pix,co] x[pix+tap,ci], K = pixels,
+// dW[tap][co][ci] = sum_pix dy[pix,co] x[pix+tap,ci], K = pixels,
 // both operands MN-major straight from NHWC, accumulators resident in TMEM for the CTA's whole
 // pixel range.  Like conv4_tc.cu the activation is fetched as ONE 10(w) x 18(h) pixel box per
 // channel block and tile; every tap (dh,dw) is the start-address offset (dh*10 + dw) rows into
@@ -83,6 +83,9 @@ wgrad4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  // everything above touches only this CTA's shared memory / TMEM: it overlaps the tail of the
+  // previous kernel; from here on the predecessors' results are read
+  pg::grid_dep_sync();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -265,7 +268,7 @@ static int launch_w4(const void *x, const void *dy, float *workspace, int N, int
   if (gx > p.num_tiles) gx = p.num_tiles;
   if (gx < 1) gx = 1;
   dim3 grid(gx, passes);
-  wgrad4_tc_kernel<CIN, COUT><<<grid, kW4Threads, smem, stream>>>(tx, tdy, p);
+  pg::launcher(wgrad4_tc_kernel<CIN, COUT>, grid, kW4Threads, smem, stream, p.num_tiles)(tx, tdy, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("pg_conv_wgrad_tc/v4: CUDA launch failed: %s", cudaGetErrorString(e));
@@ -280,8 +283,6 @@ static int launch_w4(const void *x, const void *dy, float *workspace, int N, int
 // The workspace is accumulated into; the caller runs the unpack kernel afterwards.
 int wgrad4_tc_launch(const void *x, const void *dy, float *workspace, int N, int H, int W, int Cin,
                      int Cout, cudaStream_t stream) {
-  if (const char *e = getenv("PG_WGRAD_V4"))
-    if (atoi(e) == 0) return PG_ERR_UNSUPPORTED;
   if (H % 16 || H < 16 || W % 8) return PG_ERR_UNSUPPORTED;
 #define PG_W4(CI, CO) \
   if (Cin == CI && Cout == CO) return tc::launch_w4<CI, CO>(x, dy, workspace, N, H, W, stream);

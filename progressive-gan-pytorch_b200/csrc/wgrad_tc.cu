@@ -83,6 +83,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  // everything above touches only this CTA's shared memory / TMEM: it overlaps the tail of the
+  // previous kernel; from here on the predecessors' results are read
+  pg::grid_dep_sync();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -138,7 +141,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     // warp-uniform loop, tcgen05 ops issued by the elected lane, descriptors = constant high
-    // word + (start>>4) low word advanced by adds (see conv3_tc.cu).
+    // word + (start>>4) low word advanced by adds.
     const uint32_t idesc = make_idesc_bf16(128, p.Cout, 1, 1);   // both operands MN-major
     const uint32_t rowA = (uint32_t)p.atomM * 2u, rowB = (uint32_t)p.atomN * 2u;
     const uint32_t layA = rowA == 128 ? 2u : 4u, layB = rowB == 128 ? 2u : 4u;
@@ -222,6 +225,7 @@ __global__ void __launch_bounds__(256)
 wgrad_unpack_kernel(const float *__restrict__ dwp, float *__restrict__ dw, int Cin, int Cout,
                     int Cin_p, int Cout_p, int taps, float scale, int swap_io, int flip,
                     int accumulate) {
+  pg::grid_dep_sync();
   const int total = Cin * Cout * taps;
   const int d1 = swap_io ? Cout : Cin;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -243,6 +247,7 @@ wgrad_unpack_kernel(const float *__restrict__ dwp, float *__restrict__ dw, int C
 // read-modify-write: the caller never puts two entries with the same dw into one launch.
 __global__ void __launch_bounds__(256)
 wgrad_unpack_multi_kernel(const PgUnpackEntry *__restrict__ table) {
+  pg::grid_dep_sync();
   // One thread per (co, ci) pair and ALL its taps: the workspace [tap][co][ci] is read with
   // coalesced 128-byte rows (consecutive ci), the parameter gradient [d0][d1][taps] receives the
   // taps of one pair as one contiguous 36- or 64-byte run.  (One thread per workspace element
@@ -289,7 +294,7 @@ extern "C" int pg_wgrad_unpack_multi(const PgUnpackEntry *table, int n, void *st
   if (gx < 16) gx = 16;
   if (gx > 1024) gx = 1024;
   dim3 grid((unsigned)gx, (unsigned)n);
-  tc::wgrad_unpack_multi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(table);
+  pg::launcher(tc::wgrad_unpack_multi_kernel, grid, 256, 0, (cudaStream_t)stream)(table);
   PG_CHECK_LAUNCH("pg_wgrad_unpack_multi");
 }
 
@@ -394,7 +399,6 @@ extern "C" int pg_conv_wgrad_tc(const void *x, const void *dy, float *dw, float 
   int rc2 = PG_ERR_UNSUPPORTED;
   if (!flat && taps == 9 && co_tiles == 1) {  // newer kernel generations where the shape allows
     rc2 = wgrad4_tc_launch(x, dy, workspace, N, H, W, Cin, Cout, s);
-    if (rc2 == PG_ERR_UNSUPPORTED) rc2 = wgrad3_tc_launch(x, dy, workspace, N, H, W, Cin, Cout, s);
   }
   if (rc2 != PG_OK && rc2 != PG_ERR_UNSUPPORTED) return rc2;
   if (rc2 == PG_ERR_UNSUPPORTED) {
@@ -402,11 +406,11 @@ extern "C" int pg_conv_wgrad_tc(const void *x, const void *dy, float *dw, float 
     if (gx > p.num_tiles) gx = p.num_tiles;
     if (gx < 1) gx = 1;
     dim3 grid(gx, passes, co_tiles);
-    tc::wgrad_tc_kernel<<<grid, tc::kWgThreads, smem, s>>>(tx, tdy, p);
+    pg::launcher(tc::wgrad_tc_kernel, grid, tc::kWgThreads, smem, s, p.num_tiles)(tx, tdy, p);
   }
   const int total = taps * Cin_log * Cout_log;
   if (!deferred)
-  tc::wgrad_unpack_kernel<<<(total + 255) / 256, 256, 0, s>>>(workspace, dw, Cin_log, Cout_log, Cin,
+  pg::launcher(tc::wgrad_unpack_kernel, (total + 255) / 256, 256, 0, s)(workspace, dw, Cin_log, Cout_log, Cin,
                                                              Cout_total, taps, scale, swap_io, flip, accumulate);
   PG_CHECK_LAUNCH("pg_conv_wgrad_tc");
 }
