@@ -371,7 +371,9 @@ conv4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         else mbar_arrive_remote(mapa_shared(tempty(g), 0));
       }
     };
-    float csum[2] = {0.f, 0.f};                     // ABW: this lane's share of the bias gradient
+    float csum[2 * NH];                             // ABW: this lane's share of the bias gradient
+#pragma unroll
+    for (int i = 0; i < 2 * NH; ++i) csum[i] = 0.f;
     uint32_t ph = 0;
     int it = 0;
     for (int sb = cid * CL; sb < p.num_super; sb += ncl * CL, ++it) {
@@ -395,6 +397,40 @@ conv4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         uint8_t *pool_g = pool_ptr + (size_t)(g * NSB + sbuf) * 32 * row_b;
         const uint32_t pool_s = smem_pool + (uint32_t)(g * NSB + sbuf) * 32u * (uint32_t)row_b;
         if (NSB > 1) sbuf ^= 1;
+        float red = 0.f;                     // sum of squares (forward) or <p,u> (fused backward)
+        if constexpr (ABW && NH == 2) {
+          // fused backward, 128 channels: columns HC..COUT-1 contribute to <p,u> only in this pass
+          // (16 columns and the matching 32 bytes of the stored activation at a time; done first so
+          // that these temporaries are dead when the first half is held in registers)
+          const uint4 *yp2 = reinterpret_cast<const uint4 *>(p.y_prev + pix * COUT + HC);
+          uint32_t tb[2][16];
+          uint4 yb[2][2];
+          tmem_ld<16>(t_addr + (uint32_t)HC, tb[0]);
+          yb[0][0] = __ldg(yp2);
+          yb[0][1] = __ldg(yp2 + 1);
+#pragma unroll
+          for (int c = 0; c < HC / 16; ++c) {
+            tmem_ld_wait();
+            if (c + 1 < HC / 16) {
+              tmem_ld<16>(t_addr + (uint32_t)(HC + (c + 1) * 16), tb[(c + 1) & 1]);
+              yb[(c + 1) & 1][0] = __ldg(yp2 + 2 * (c + 1));
+              yb[(c + 1) & 1][1] = __ldg(yp2 + 2 * (c + 1) + 1);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const __nv_bfloat162 *h2 = reinterpret_cast<const __nv_bfloat162 *>(&yb[c & 1][i]);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 yy = __bfloat1622float2(h2[e]);
+                const int j = i * 8 + 2 * e;
+                const float u0 = __uint_as_float(tb[c & 1][j]) * scale * (yy.x > 0.f ? 1.f : slope);
+                const float u1 = __uint_as_float(tb[c & 1][j + 1]) * scale * (yy.y > 0.f ? 1.f : slope);
+                red = fmaf(yy.x > 0.f ? yy.x : yy.x * inv_slope, u0, red);
+                red = fmaf(yy.y > 0.f ? yy.y : yy.y * inv_slope, u1, red);
+              }
+            }
+          }
+        }
         float v[HC];                         // accumulators are loaded in place (one register set)
         uint32_t *vr = reinterpret_cast<uint32_t *>(v);
         // ---- pass 1: the first HC columns stay in registers
@@ -418,7 +454,6 @@ conv4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         group_bar();
         tmem_ld_wait();
         if (NH == 1 && mt == MT - 1) release_stage();   // stage fully read: back to the MMA warp
-        float red = 0.f;                     // sum of squares (forward) or <p,u> (fused backward)
         if constexpr (!ABW) {
 #pragma unroll
           for (int j = 0; j < HC; j += 4) {
@@ -478,13 +513,32 @@ conv4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
             // ---- pass 2 (COUT = 128): re-read columns HC.. and normalise them
 #pragma unroll
             for (int c = 0; c < HC; c += 32) tmem_ld<32>(t_addr + (uint32_t)(HC + c), vr + c);
+            if constexpr (ABW) {
+              const uint4 *yp = reinterpret_cast<const uint4 *>(p.y_prev + pix * COUT + HC);
+#pragma unroll
+              for (int i = 0; i < HC / 8; ++i) yraw[i] = __ldg(yp + i);
+            }
             if (gt == 0) tma_store_wait_read0();     // first half's store has read the staging tile
             group_bar();
             tmem_ld_wait();
             if (mt == MT - 1) release_stage();
+            if constexpr (!ABW) {
 #pragma unroll
-            for (int j = 0; j < HC; ++j)
-              v[j] = fmaf(__uint_as_float(vr[j]), scale, bias_ptr[HC + j]);
+              for (int j = 0; j < HC; ++j)
+                v[j] = fmaf(__uint_as_float(vr[j]), scale, bias_ptr[HC + j]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < HC / 8; ++i) {
+                const __nv_bfloat162 *h2 = reinterpret_cast<const __nv_bfloat162 *>(&yraw[i]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 yy = __bfloat1622float2(h2[e]);
+                  const int j = i * 8 + 2 * e;
+                  v[j] = __uint_as_float(vr[j]) * scale * (yy.x > 0.f ? 1.f : slope);
+                  v[j + 1] = __uint_as_float(vr[j + 1]) * scale * (yy.y > 0.f ? 1.f : slope);
+                }
+              }
+            }
           }
 #pragma unroll
           for (int i = 0; i < HC / 8; ++i) {                       // 8 channels = 16 bytes per store
@@ -562,31 +616,32 @@ conv4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
               tma_store_commit();
             }
           }
-        }
-        if (ABW && p.colsum != nullptr) {
-          // per-channel sum over the warp's 32 pixels by a halving butterfly: each step trades
-          // half of the remaining channels with the partner lane (HC - 1 shuffles in total)
-          int nrem = HC;
+          if (ABW && p.colsum != nullptr) {
+            // bias gradient: per-channel sum of this half's da over the warp's 32 pixels by a
+            // halving butterfly - each step trades half of the remaining channels with the partner
+            // lane (HC - 1 shuffles in total)
+            int nrem = HC;
 #pragma unroll
-          for (int off = 16; off >= 1; off >>= 1) {
-            if (nrem >= 2) {
-              const int hn = nrem / 2;
-              const bool up = (lane & off) != 0;
+            for (int off = 16; off >= 1; off >>= 1) {
+              if (nrem >= 2) {
+                const int hn = nrem / 2;
+                const bool up = (lane & off) != 0;
 #pragma unroll
-              for (int j = 0; j < HC / 2; ++j) {
-                if (j < hn) {
-                  const float send = up ? v[j] : v[j + hn];
-                  const float keep = up ? v[j + hn] : v[j];
-                  v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                for (int j = 0; j < HC / 2; ++j) {
+                  if (j < hn) {
+                    const float send = up ? v[j] : v[j + hn];
+                    const float keep = up ? v[j + hn] : v[j];
+                    v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                  }
                 }
+                nrem = hn;
+              } else {
+                v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
               }
-              nrem = hn;
-            } else {
-              v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
             }
+            csum[2 * h] += v[0];
+            if (HC >= 64) csum[2 * h + 1] += v[1];
           }
-          csum[0] += v[0];
-          if (HC >= 64) csum[1] += v[1];
         }
       }
     }
@@ -602,11 +657,10 @@ conv4_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           hn >>= 1;
         }
       }
-      if (HC >= 64) {
-        atomicAdd(p.colsum + ch, csum[0]);
-        atomicAdd(p.colsum + ch + 1, csum[1]);
-      } else {
-        atomicAdd(p.colsum + ch, csum[0]);
+#pragma unroll
+      for (int h = 0; h < NH; ++h) {
+        atomicAdd(p.colsum + h * HC + ch, csum[2 * h]);
+        if (HC >= 64) atomicAdd(p.colsum + h * HC + ch + 1, csum[2 * h + 1]);
       }
     }
     if (gt == 0) tma_store_wait_all();
@@ -680,7 +734,7 @@ int conv4_tc_launch(const void *x, const void *wp, const float *bias, void *y, f
                     cudaStream_t stream, const void *y_prev, const float *r_prev, float *colsum,
                     int use_pn, void *y_pool) {
   const bool abw = y_prev != nullptr;
-  if (abw && (y_pool || Cout > 64)) return PG_ERR_UNSUPPORTED;
+  if (abw && y_pool) return PG_ERR_UNSUPPORTED;
   // experiment knobs, read ONCE per process (PG_DBG: epilogue / load / MMA switches for
   // profiles/r2/diag_conv4.py; PG_C4_RES / PG_C4_MT / PG_C4_CL: force a kernel variant)
   struct Knobs {

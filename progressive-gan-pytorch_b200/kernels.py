@@ -10,6 +10,7 @@ Tensor conventions
   params, param grads, per-pixel statistics: float32
 """
 import ctypes
+import os
 import weakref
 from dataclasses import dataclass
 
@@ -105,9 +106,14 @@ class CudaKernels:
         self._packs = {}               # id(param) -> [weakref, version, {variant: (tensor, pack args)}]
         self._pack_tables = {}         # ids of a parameter set -> (signature, device table, n)
         # data-gradient convs whose epilogue also applies the PixelNorm/LeakyReLU backward of the
-        # layer in front (one thread per pixel row in the conv4 epilogue): layers of 32 / 64 channels
-        # at >= 16 px; 1 << 30 turns the fusion off
-        self.fuse_actbwd_min_cout = 32
+        # layer in front (pg_conv_tc_actbwd: one thread per pixel row in the conv4 epilogue, 32 / 64
+        # / 128 channels at >= 16 px).  Correct and tested, but OFF by default: measured on the
+        # same box (profiles/r2/README.md) the step time is the same with and without it - the
+        # stand-alone activation-backward kernels overlap the side-stream weight gradients, the
+        # longer conv epilogue does not - while the conv kernel's FLOP rate drops from 947 to 840
+        # TFLOP/s.  PG_FUSE_ACTBWD_MAX=128 (or setting fuse_actbwd_max_cout) turns it on.
+        self.fuse_actbwd_min_cout = int(os.environ.get("PG_FUSE_ACTBWD_MIN", "32"))
+        self.fuse_actbwd_max_cout = int(os.environ.get("PG_FUSE_ACTBWD_MAX", "0"))
         self.wgrad_side_stream = None  # Trainer: deferred weight gradients run on this stream, next
         self._side_dirty = set()       # to the bandwidth-bound kernels of the data-gradient chain
         self._side_streams = {}        # one side stream per forking stream
@@ -329,7 +335,8 @@ class CudaKernels:
         if self.conv_impl != "tc" or y.dtype != torch.bfloat16 or y.dim() != 4:
             return False
         _, H, W, C = y.shape
-        return C in (32, 64) and C >= self.fuse_actbwd_min_cout and H % 16 == 0 and W % 8 == 0
+        return (C in (32, 64, 128) and self.fuse_actbwd_min_cout <= C <= self.fuse_actbwd_max_cout
+                and H % 16 == 0 and W % 8 == 0)
 
     def conv_wgrad(self, x, dy, wshape, op, scale, out=None):
         """dw[wshape] = scale * sum_pix dy (x) x for the conv `op` (fp32).  out: accumulate into

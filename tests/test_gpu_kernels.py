@@ -365,6 +365,7 @@ def test_gp_and_optim(KE):
     # N, H, W, Cin, Cout  (Cout = channels of the activation whose backward is fused)
     (2, 32, 32, 64, 64), (1, 64, 64, 64, 32), (3, 16, 16, 128, 32), (2, 32, 32, 128, 64),
     (5, 128, 128, 64, 64), (2, 64, 64, 32, 64), (10, 64, 64, 64, 32),
+    (3, 16, 16, 128, 128), (10, 64, 64, 128, 128), (4, 32, 32, 64, 128),      # two-pass epilogue
 ])
 @pytest.mark.parametrize("use_pn", [True, False])
 def test_conv_dgrad_actbwd_fused_matches_two_kernels(KE, cfg, use_pn):
@@ -382,7 +383,11 @@ def test_conv_dgrad_actbwd_fused_matches_two_kernels(KE, cfg, use_pn):
     pnorm = a_prev * r_prev.unsqueeze(-1) if use_pn else a_prev
     y_prev = torch.where(pnorm > 0, pnorm, 0.2 * pnorm).to(torch.bfloat16)
     cs = torch.zeros(Cout, device=DEV)
-    da = K.conv_dgrad_actbwd(x, w, op, scale, y_prev, r_prev, 0.2, use_pn, cs)
+    prev_max, K.fuse_actbwd_max_cout = K.fuse_actbwd_max_cout, 128      # the fusion is off by default
+    try:
+        da = K.conv_dgrad_actbwd(x, w, op, scale, y_prev, r_prev, 0.2, use_pn, cs)
+    finally:
+        K.fuse_actbwd_max_cout = prev_max
     assert da is not None
     dh, _ = K.conv_fwd(x, w, None, op, scale, EPI_LINEAR)
     cs_ref = torch.zeros(Cout, device=DEV)
