@@ -42,7 +42,8 @@ def test_trainer_bf16_tc_runs_and_graph_equals_eager(name):
     # one iteration: only the fp32 atomics order differs between runs
     _, e1, _, _, _ = _run(name, "bf16", "tc", use_graph=False, iters=1)
     _, g1, _, _, _ = _run(name, "bf16", "tc", use_graph=True, iters=1)
-    assert helpers.rel(g1.bD.p, e1.bD.p) < 1e-5 and helpers.rel(g1.bG.p, e1.bG.p) < 1e-5
+    # (a handful of near-zero gradients may change sign with the atomics order: 2 lr each after Adam)
+    assert helpers.rel(g1.bD.p, e1.bD.p) < 1e-4 and helpers.rel(g1.bG.p, e1.bG.p) < 1e-4
     m_e1, m_g1 = e1.read_metrics(), g1.read_metrics()
     for k in m_e1:
         assert abs(m_e1[k] - m_g1[k]) <= 1e-4 * abs(m_e1[k]) + 1e-4, (k, m_e1[k], m_g1[k])
@@ -136,3 +137,30 @@ def test_n_critic_graph_replay_equals_eager():
         me, mo = runs[0].read_metrics(reset=False), other.read_metrics(reset=False)
         for k in me:
             assert abs(me[k] - mo[k]) <= 1e-2 * abs(me[k]) + 5e-2, (k, me[k], mo[k])
+
+
+@pytest.mark.parametrize("name", ["s3_a0.25", "s5_a0.5"])
+def test_fused_activation_backward_epilogue_in_the_full_iteration(name):
+    """The data-gradient convs with the fused PixelNorm/LeakyReLU-backward epilogue (off by
+    default) through a whole iteration: the gradient buckets agree with the unfused path (the
+    fused path skips one bf16 rounding of dh, hence 2e-2) and the fused entry point was used."""
+    K = progan_b200.get_kernels()
+    _, off, _, _, _ = _run(name, "bf16", "tc")
+    calls = []
+    orig = K._call
+
+    def counting(fn, *a):
+        calls.append(fn)
+        return orig(fn, *a)
+    prev = K.fuse_actbwd_max_cout
+    K.fuse_actbwd_max_cout, K._call = 128, counting
+    try:
+        _, on, _, _, _ = _run(name, "bf16", "tc")
+    finally:
+        K.fuse_actbwd_max_cout, K._call = prev, orig
+    assert calls.count("pg_conv_tc_actbwd") >= 2, "the fused kernel did not run"
+    assert helpers.rel(on.bD.g, off.bD.g) < 2e-2 and helpers.rel(on.bG.g, off.bG.g) < 2e-2
+    mo, mf = off.read_metrics(), on.read_metrics()
+    for k in mo:     # gen_loss follows D's Adam step (lr * sign(g) at v = 0), which amplifies the difference
+        tol = 1e-2 if k == "gen_loss" else 1e-3
+        assert abs(mo[k] - mf[k]) <= tol * abs(mo[k]) + tol, (k, mo[k], mf[k])
