@@ -97,19 +97,23 @@ def _generic_groups(model):
     return groups
 
 
-def _reduce_ranges(ranges, done=None):
-    """The collectives for a bucket's live ranges: what `done` = (a, b) already covered is cut off,
-    and two ranges with a small gap between them go out as one span."""
+def _reduce_ranges(ranges, done=None, total=None):
+    """The collective for a bucket's live ranges: ONE all-reduce over the span from the first live
+    element to the last (the gaps hold zeros: the bucket is cleared every phase and inactive layers
+    receive no gradient, so reducing them is harmless and a second NCCL launch costs more than the
+    extra megabytes over NVLink), cut off below by what `done` = (a, b) already covered, with both
+    ends moved outwards to 16-byte boundaries (bounded by `total` elements)."""
     rs = list(ranges)
     if done is not None:
         rs = [(max(a, done[1]), b) for a, b in rs if b > done[1]]
     if not rs:
         return []
-    span = rs[-1][1] - rs[0][0]
-    live = sum(b - a for a, b in rs)
-    if len(rs) > 1 and span <= 1.25 * live:
-        rs = [(rs[0][0], rs[-1][1])]
-    return rs
+    a, b = rs[0][0] & ~3, (rs[-1][1] + 3) & ~3
+    if done is not None:
+        a = max(a, done[1])
+    if total is not None:
+        b = min(b, total)
+    return [(a, b)]
 
 
 class _NullCtx:
@@ -309,13 +313,11 @@ class Trainer:
 
     # ------------------------------------------------------------------ pieces
     def _allreduce(self, bucket, plan, done=None):
-        """Sum the live gradient ranges over the ranks.  When the gap between the (at most two)
-        ranges is small the whole span goes out as ONE collective — the gap holds zeros (the
-        bucket is cleared every phase and inactive layers receive no gradient) and a second NCCL
-        launch costs more than a few KB of payload.  done = (a, b): that prefix of the bucket was
-        already reduced during the backward sweep (_on_top_done)."""
+        """Sum the live gradient span over the ranks (one collective, see _reduce_ranges).
+        done = (a, b): that prefix of the bucket was already reduced during the backward sweep
+        (_on_top_done)."""
         if self.world > 1:
-            for a, b in _reduce_ranges(plan["ranges"], done):
+            for a, b in _reduce_ranges(plan["ranges"], done, bucket.g.numel()):
                 dist.all_reduce(bucket.g[a:b], group=self.pg)
 
     # the critic block whose OUTPUT gradient marks "every layer above is done": progression[2]

@@ -1,7 +1,12 @@
 """GPU: the reference bar of SURVEY §8(d) — the oracle loop (fp32 restatement of train.py:122-169,
-pinned to the reference by the goldens) run on the SAME B200 through PyTorch/cuDNN, in torch's
-default fp32 mode (cuDNN convs may use TF32) and under bf16 autocast (NCHW images: the loop's
-`grad_x_hat.view(b, -1)`, train.py:148, rejects a channels_last x_hat), timed next to the product's Trainer on BASELINE config 4 (128 px, batch 64, alpha 0.5).
+pinned to the reference by the goldens) run on the SAME B200 through PyTorch/cuDNN, timed next to
+the product's Trainer on BASELINE config 4 (128 px, batch 64, alpha 0.5), in four modes:
+  fp32                  true fp32 convs (TF32 off — what the parity tests use as the checker)
+  tf32                  torch's GPU default (cuDNN convs and matmuls may use TF32)
+  bf16 autocast         NCHW tensors
+  bf16 autocast + channels_last weights (cuDNN then runs NHWC kernels); the loop's
+                        `grad_x_hat.view(b, -1)` (train.py:148) may reject the resulting layout, in
+                        which case the leg is recorded as unavailable instead of failing the test.
 
 Gate: the product's iteration is faster than the stronger (bf16) cuDNN bar.  The measured numbers
 are written to gpurun_out/gpu_reference_bar.json when that directory exists (copied to profiles/)."""
@@ -41,12 +46,17 @@ def _time(fn):
     return e0.elapsed_time(e1) / ITERS
 
 
-def _oracle_ms(autocast):
+def _oracle_ms(autocast, tf32=False, channels_last=False):
     torch.manual_seed(0)
     with torch.device("cpu"):
         G = progan_b200.Generator(128, 128, tanh=False)
         D = progan_b200.Discriminator(128)
     PG, PD, PR = O.params_of(G, device=DEV), O.params_of(D, device=DEV), O.params_of(G, False, device=DEV)
+    if channels_last:
+        for P in (PG, PD):
+            for k, v in list(P.items()):
+                if v.dim() == 4:
+                    P[k] = v.detach().contiguous(memory_format=torch.channels_last).requires_grad_(True)
     optG, optD = O.AdamState(PG), O.AdamState(PD)
     real, z, eps = _inputs()
 
@@ -54,12 +64,15 @@ def _oracle_ms(autocast):
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
             O.train_iteration(PG, PD, PR, optG, optD, real, z, eps, STEP, ALPHA)
 
-    prev = torch.backends.cudnn.benchmark
+    prev = (torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
     torch.backends.cudnn.benchmark = True          # give cuDNN its autotuned algorithms
+    torch.backends.cudnn.allow_tf32 = tf32
+    torch.backends.cuda.matmul.allow_tf32 = tf32
     try:
         return _time(it)
     finally:
-        torch.backends.cudnn.benchmark = prev
+        (torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32,
+         torch.backends.cuda.matmul.allow_tf32) = prev
 
 
 def _product_ms():
@@ -75,21 +88,33 @@ def _product_ms():
     return _time(lambda: tr.step(real, z, eps, STEP, ALPHA))
 
 
+def _leg(ms):
+    return {"ms_per_step": round(ms, 3), "img_per_s": round(B / ms * 1e3, 1)}
+
+
 def test_product_beats_the_cudnn_reference_bar():
     fp32 = _oracle_ms(False)
     torch.cuda.empty_cache()
+    tf32 = _oracle_ms(False, tf32=True)
+    torch.cuda.empty_cache()
     bf16 = _oracle_ms(True)
+    torch.cuda.empty_cache()
+    try:
+        bf16_cl = _leg(_oracle_ms(True, channels_last=True))
+    except Exception as e:                           # noqa: BLE001 — an optional, stronger bar
+        bf16_cl = {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:200])}
     torch.cuda.empty_cache()
     prod = _product_ms()
     rec = {"workload": "train.py G(128,128)/D(128) step 5 (128px) alpha=0.5 batch 64, full iteration",
-           "oracle_cudnn_fp32_tf32": {"ms_per_step": round(fp32, 3), "img_per_s": round(B / fp32 * 1e3, 1)},
-           "oracle_cudnn_bf16_autocast": {"ms_per_step": round(bf16, 3),
-                                                         "img_per_s": round(B / bf16 * 1e3, 1)},
-           "product_bf16_tcgen05_graph": {"ms_per_step": round(prod, 3), "img_per_s": round(B / prod * 1e3, 1)},
+           "oracle_cudnn_fp32": _leg(fp32), "oracle_cudnn_tf32": _leg(tf32),
+           "oracle_cudnn_bf16_autocast": _leg(bf16),
+           "oracle_cudnn_bf16_autocast_channels_last": bf16_cl,
+           "product_bf16_tcgen05_graph": _leg(prod),
            "iters": ITERS, "warmup": WARM, "timing": "CUDA events"}
     print(json.dumps(rec))
     out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
     if os.path.isdir(out):
         with open(os.path.join(out, "gpu_reference_bar.json"), "w") as f:
             json.dump(rec, f, indent=1)
-    assert prod < bf16 and prod < fp32, rec
+    best = min([fp32, tf32, bf16] + ([bf16_cl["ms_per_step"]] if "ms_per_step" in bf16_cl else []))
+    assert prod < best, rec

@@ -113,11 +113,12 @@ def test_n_critic_matches_reference_ordered_loop(name, n_critic):
         progan_b200.Trainer(G, D, Grun, n_critic=0)
 
 
-def test_reduce_ranges_cut_off_what_the_backward_sweep_already_reduced():
+def test_reduce_ranges_one_aligned_span_minus_what_the_backward_sweep_already_reduced():
     from progan_b200.train import _reduce_ranges
-    assert _reduce_ranges([(0, 100), (400, 420)]) == [(0, 100), (400, 420)]
-    assert _reduce_ranges([(0, 100), (110, 120)]) == [(0, 120)]            # small gap: one collective
-    assert _reduce_ranges([(0, 100), (400, 420)], done=(0, 60)) == [(60, 100), (400, 420)]
+    assert _reduce_ranges([(0, 100), (400, 420)]) == [(0, 420)]              # one collective, gaps are zeros
+    assert _reduce_ranges([(6, 101)], total=1000) == [(4, 104)]             # 16-byte boundaries
+    assert _reduce_ranges([(6, 999)], total=1000) == [(4, 1000)]
+    assert _reduce_ranges([(0, 100), (400, 420)], done=(0, 64)) == [(64, 420)]
     assert _reduce_ranges([(0, 100), (400, 420)], done=(0, 100)) == [(400, 420)]
     assert _reduce_ranges([(0, 100)], done=(0, 100)) == []
 
