@@ -13,10 +13,12 @@ from .progan_modules import (ConditionalCorrectDiscriminatorAda, ConditionalCorr
                              set_default_precision)
 from .functions import gradient_penalty
 from .train import MiniStepSchedule, ProgressiveSchedule, Trainer
-from . import mnist_pggan
+from .ada import AdaptiveAugment, AugmentPipe
+from . import ada, mnist_pggan
 
 __all__ = ["Generator", "Discriminator", "CorrectGenerator", "CorrectDiscriminator", "mnist_pggan", "ConditionalCorrectGenerator",
            "ConditionalCorrectDiscriminatorWgangp", "ConditionalGenerator", "ConditionalDiscriminatorWgangp",
            "ConditionalCorrectGeneratorAda", "ConditionalCorrectDiscriminatorAda", "EqualEmbed", "ConvBlock", "EqualConv2d", "EqualConvTranspose2d",
            "EqualLinear", "PixelNorm", "ConvOp", "get_kernels", "set_kernels",
-           "set_default_precision", "gradient_penalty", "Trainer", "ProgressiveSchedule", "MiniStepSchedule"]
+           "set_default_precision", "gradient_penalty", "Trainer", "ProgressiveSchedule", "MiniStepSchedule",
+           "AugmentPipe", "AdaptiveAugment", "ada"]

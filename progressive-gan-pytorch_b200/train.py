@@ -256,8 +256,16 @@ class Trainer:
     def __init__(self, generator, discriminator, g_running=None, lr=1e-3, betas=(0.0, 0.99),
                  eps=1e-8, ema_decay=0.999, gp_lambda=10.0, drift=0.001, process_group=None,
                  use_graph=False, segment_graphs=None, overlap_wgrad=True, overlap_passes=True,
-                 n_critic=1):
+                 n_critic=1, augment=None):
         self.G, self.D, self.G_run = generator, discriminator, g_running
+        # optional ADA pipe (progan_b200.AugmentPipe) in front of every critic input - real, fake
+        # and x_hat, each with its own draw, as StyleGAN2-ADA applies it; the pipe is twice
+        # differentiable, so the gradient penalty differentiates through it.  Its geometric stage
+        # sizes a padding from the sampled transforms on the host, so it cannot be graph-captured.
+        self.augment = augment
+        if augment is not None and use_graph:
+            raise RuntimeError("progan_b200.Trainer: augment= needs use_graph=False (the ADA pipe's "
+                               "geometric stage reads its padding margins on the host)")
         # the generator phase runs on iterations with (i + 1) % n_critic == 0 (train.py:158, 221)
         self.n_critic = int(n_critic)
         if self.n_critic < 1:
@@ -437,6 +445,9 @@ class Trainer:
         return dict(real=real, z=z, eps=eps, step=step, alpha=alpha, label=label, do_g=do_g,
                     planD=self.bD.plan(namesD), planG=self.bG.plan(namesG))
 
+    def _aug(self, images):
+        return images if self.augment is None else self.augment(images).contiguous()
+
     def _seg_d(self, st):
         # ---- D phase.  D(real) and D(fake) (train.py:126-139) run as ONE pass over
         # cat([real, fake]) with per-half minibatch statistics: same gradients (they accumulate
@@ -466,7 +477,7 @@ class Trainer:
             s2.wait_stream(cur)
         with (torch.cuda.stream(s2) if s2 is not None else _NullCtx()):
             x_hat = K.interp_xhat(real, fake.detach(), st["eps"].reshape(-1)).requires_grad_(True)
-            hat = D(x_hat, *la, step=step, alpha=alpha)
+            hat = D(self._aug(x_hat), *la, step=step, alpha=alpha)
             # d(sum_n hat_n)/dx_hat (train.py:146) with an explicit unit seed: no sum kernel and no
             # expand in its backward
             ones = self._ones.get(tuple(hat.shape))
@@ -477,7 +488,7 @@ class Trainer:
             if early is not None:
                 self._early["armed"] = True          # the first-order sweep above must not count
             gp.backward()
-        both = D(torch.cat([real, fake.detach()]), *la2, step=step, alpha=alpha, mbstd_group=B)
+        both = D(self._aug(torch.cat([real, fake.detach()])), *la2, step=step, alpha=alpha, mbstd_group=B)
         # loss value (-> metric) and dL/d(outputs) in one launch, then backward from that seed
         both.backward(K.wgan_loss(both.detach(), B, self.drift, self.metrics["disc_loss"]))
         if s2 is not None:
@@ -504,7 +515,7 @@ class Trainer:
         # ---- G phase (D already updated, train.py:158-169)
         self.bG.g.zero_()
         la = (st["label"],) if st.get("label") is not None else ()
-        out = self.D(st["fake"], *la, step=st["step"], alpha=st["alpha"])
+        out = self.D(self._aug(st["fake"]), *la, step=st["step"], alpha=st["alpha"])
         out.backward(K.wgan_loss(out.detach(), 0, 0.0, self.metrics["gen_loss"]), inputs=st["planG"]["params"])
         K.flush_wgrads()
 
