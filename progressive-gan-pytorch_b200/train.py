@@ -116,6 +116,27 @@ def _reduce_ranges(ranges, done=None, total=None):
     return [(a, b)]
 
 
+class _nvtx:
+    """NVTX range around a phase of the iteration (the reference's only tracing hook is
+    `profiled_function` -> record_function; here the three phases show up in nsys / ncu timelines).
+    Host-side markers only: safe under CUDA-graph capture, a no-op where NVTX is unavailable."""
+
+    def __init__(self, name):
+        self.name, self.on = name, False
+
+    def __enter__(self):
+        try:
+            torch.cuda.nvtx.range_push(self.name)
+            self.on = True
+        except Exception:                    # noqa: BLE001
+            self.on = False
+
+    def __exit__(self, *exc):
+        if self.on:
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
 class _NullCtx:
     def __enter__(self):
         return None
@@ -404,14 +425,18 @@ class Trainer:
         multi-GPU run captures as CUDA graphs; the collectives stay outside the graphs)."""
         st = self._state(real, z, eps, step, alpha, fading, label, do_g)
         with self._fast_paths(self._side):
-            self._seg_d(st)
-            self._allreduce(self.bD, st["planD"], st.get("reduced"))
+            with _nvtx("progan_b200/D phase"):
+                self._seg_d(st)
+                self._allreduce(self.bD, st["planD"], st.get("reduced"))
             if do_g:
-                self._seg_g(st)
-                self._allreduce(self.bG, st["planG"])
-                self._seg_end(st)
+                with _nvtx("progan_b200/D Adam + G phase"):
+                    self._seg_g(st)
+                    self._allreduce(self.bG, st["planG"])
+                with _nvtx("progan_b200/G Adam + EMA"):
+                    self._seg_end(st)
             else:
-                self._seg_d_end(st)
+                with _nvtx("progan_b200/D Adam"):
+                    self._seg_d_end(st)
 
     def _active(self, step, alpha, fading, label=None):
         """(live D groups, live G groups) for this (step, fading)."""

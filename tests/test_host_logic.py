@@ -169,3 +169,35 @@ def test_mini_step_schedule_matches_reference_loop(init_step, max_step, per_mini
             step_iteration += 1
         assert sched.next() == (step, alpha, reload_data), i
         assert sched.resolution == 2 * 2 ** step
+
+
+def test_partial_flush_of_weight_gradient_workspaces_by_address_range():
+    """CudaKernels.flush_wgrads(ptr_range=...) — what the data-parallel Trainer uses to fold and
+    all-reduce the top of the critic during the backward sweep: only the workspaces whose gradient
+    lives in the range are unpacked and removed from the pending set; two workspaces of the SAME
+    gradient go to different launches (the kernel's read-modify-write needs no atomics)."""
+    from progan_b200 import _lib
+    from progan_b200.kernels import CudaKernels
+    K = CudaKernels()                      # the C-ABI library loads without a GPU; nothing is launched
+    calls = []
+    K._call = lambda name, *a: calls.append((name, a[1]))         # (entry point, number of table rows)
+    K._upload = lambda rows, cls, dev: torch.zeros(len(rows))
+    K._stream = lambda: 0
+
+    def pend(grad_ptr, variant):
+        ws = torch.zeros(4)
+        key = (grad_ptr, variant, False, False, 32, 32, 32, 32, 3, 1.0)
+        K._pending[key] = (ws, _lib.UnpackEntry(0, grad_ptr, 32, 32, 32, 32, 9, 0, 0, 0, 1.0, 0.0))
+        return key
+
+    early = [pend(1000, "conv3"), pend(1000, "adjoint"), pend(2000, "conv3")]
+    late = [pend(5000, "conv3"), pend(6000, "conv3")]
+    K.flush_wgrads(ptr_range=(0, 4000), join=False)
+    assert [n for n, _ in calls] == ["pg_wgrad_unpack_multi"] * 2 and sorted(r for _, r in calls) == [1, 2]
+    assert list(K._pending) == late
+    calls.clear()
+    K.flush_wgrads(ptr_range=(0, 4000), join=False)               # nothing left in the range
+    assert calls == []
+    K.flush_wgrads(join=False)
+    assert [r for _, r in calls] == [2] and not K._pending
+    assert early[0] != early[1]
