@@ -171,7 +171,7 @@ def test_mini_step_schedule_matches_reference_loop(init_step, max_step, per_mini
         assert sched.resolution == 2 * 2 ** step
 
 
-def test_partial_flush_of_weight_gradient_workspaces_by_address_range():
+def test_partial_flush_of_weight_gradient_workspaces_by_address_range(monkeypatch):
     """CudaKernels.flush_wgrads(ptr_range=...) — what the data-parallel Trainer uses to fold and
     all-reduce the top of the critic during the backward sweep: only the workspaces whose gradient
     lives in the range are unpacked and removed from the pending set; two workspaces of the SAME
@@ -179,6 +179,7 @@ def test_partial_flush_of_weight_gradient_workspaces_by_address_range():
     from progan_b200 import _lib
     from progan_b200.kernels import CudaKernels
     K = CudaKernels()                      # the C-ABI library loads without a GPU; nothing is launched
+    monkeypatch.setattr(torch.cuda, "is_current_stream_capturing", lambda: False)
     calls = []
     K._call = lambda name, *a: calls.append((name, a[1]))         # (entry point, number of table rows)
     K._upload = lambda rows, cls, dev: torch.zeros(len(rows))
