@@ -202,3 +202,23 @@ def test_partial_flush_of_weight_gradient_workspaces_by_address_range(monkeypatc
     K.flush_wgrads(join=False)
     assert [r for _, r in calls] == [2] and not K._pending
     assert early[0] != early[1]
+
+
+def test_out_of_range_tensor_alpha_takes_the_no_blend_path():
+    """alpha passed as a plain 0-dim tensor of -1 or >= 1 must behave like the number
+    (the reference evaluates `0 <= alpha < 1` on it), not like 'fade active'."""
+    import common
+    import helpers
+    import progan_b200
+    from emul_kernels import EmulKernels
+    prev = progan_b200.set_kernels(EmulKernels())
+    try:
+        inp = common.make_inputs("s2_a0.5")
+        G, D = helpers.build_models(inp, "fp32")
+        with torch.no_grad():
+            for a in (-1.0, 1.0, 0.5):
+                assert torch.equal(D(inp["real"], step=2, alpha=torch.tensor(a)), D(inp["real"], step=2, alpha=a))
+                assert torch.equal(G(inp["z"], step=2, alpha=torch.tensor(a)), G(inp["z"], step=2, alpha=a))
+            assert not torch.equal(D(inp["real"], step=2, alpha=torch.tensor(-1.0)), D(inp["real"], step=2, alpha=0.5))
+    finally:
+        progan_b200.set_kernels(prev)
