@@ -249,8 +249,10 @@ def run_product(args):
         "config": {"workload": "train.py CelebA-shape G(128,128)/D(128) step %d (%dpx) alpha=%.2f "
                                "batch %d/GPU, full iteration incl. Adam+EMA" % (step, res, alpha, B),
                    "parallelism": "dp%d" % world, "conv": args.conv, "cuda_graph": not args.no_graph,
-                   "allreduce": ("captured in the iteration graph; top of the critic reduced during "
-                                 "the backward sweep" if world > 1 and not tr.segment_graphs
+                   "allreduce": (("captured in the iteration graph" +
+                                  ("; top of the critic reduced during the backward sweep"
+                                   if tr.early_reduce and step >= 4 else ""))
+                                 if world > 1 and not tr.segment_graphs
                                  else ("between segment graphs" if world > 1 else None)),
                    "l2": "working set %.0f MB per pass > 126 MB L2" % (B * res * res * 64 * 2 * 4 / 1e6)},
         "e2e": {"value": round(e2e, 2), "unit": "img/s", "h2d_bytes_per_step": h2d,
