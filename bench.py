@@ -94,6 +94,19 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons)}
 
 
+def arm_deadline(seconds=None):
+    """Hang guard for the product arm: if the process is still alive after `seconds`
+    (PG_BENCH_DEADLINE_S, default 1500; 0 disables) every thread's Python stack goes to stderr and
+    the process exits with status 1 — under torchrun that takes the other ranks down with it —
+    instead of holding the GPUs until an outer timeout kills the box."""
+    import faulthandler
+    if seconds is None:
+        seconds = float(os.environ.get("PG_BENCH_DEADLINE_S", "1500"))
+    if seconds > 0:
+        faulthandler.dump_traceback_later(seconds, exit=True)
+    return seconds
+
+
 def make_inputs(batch, res, zdim, seed):
     g = torch.Generator().manual_seed(seed)                      # CPU generator (train.py:133,142)
     real = (torch.rand(batch, 3, res, res, generator=g) * 2 - 1)
@@ -385,4 +398,5 @@ if __name__ == "__main__":
     if a.impl == "reference":
         run_reference(a)
     else:
+        arm_deadline()
         run_product(a)
